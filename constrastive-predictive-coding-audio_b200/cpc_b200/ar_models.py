@@ -1,0 +1,126 @@
+"""Autoregressive (context) models.  The north star keeps these *unchanged*: they are caller-side modules
+plugged into ``AudioPredictiveCodingModel`` and run on stock PyTorch.  They are restated here only so that
+the package is usable without the reference checkout (audio_model.py:47-161, attention_model.py:9-82).
+
+Two deliberate deviations, both numerically identical in the forward pass:
+  * ``ConvolutionalArBlock`` adds the residual out of place (the reference's in-place ``+=`` on a ReLU
+    output raises an autograd error on torch >= 1.5);
+  * ``PositionalEncoder`` scales out of place (the reference scales a view of ``z`` in place).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .model import ActivationWriter
+
+
+class AudioGRUModel(nn.Module):
+    """GRUCell unrolled over the visible steps; input (batch, input_size, steps) -> last hidden state."""
+
+    def __init__(self, input_size, hidden_size, bias=True, reset_hidden=True):
+        super().__init__()
+        self.gruCell = nn.GRUCell(input_size=input_size, hidden_size=hidden_size, bias=bias)
+        self.hidden = None
+        self.reset_hidden = reset_hidden
+
+    def forward(self, input):
+        state = None if self.reset_hidden else self.hidden
+        for frame in input.unbind(dim=2):
+            state = self.gruCell(frame, state)
+        self.hidden = None if self.reset_hidden else state
+        return state
+
+
+class ConvolutionalArBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, pooling=1, stride=1, bias=True, residual=False,
+                 batch_norm=False, name='ar_block', activation_register=None):
+        super().__init__()
+        self.name = name
+        self.main_modules = nn.ModuleList()
+        if pooling > 1:
+            self.main_modules.append(nn.MaxPool1d(pooling, ceil_mode=True))
+        self.main_modules.append(nn.Conv1d(in_channels, out_channels, kernel_size, stride=stride, bias=bias))
+        if batch_norm:
+            self.main_modules.append(nn.BatchNorm1d(out_channels))
+        self.main_modules.append(nn.ReLU())
+        self.residual = residual
+        self.residual_modules = None
+        if residual:
+            self.residual_modules = nn.ModuleList()
+            if pooling * stride > 1:
+                self.residual_modules.append(nn.MaxPool1d(pooling * stride, ceil_mode=True))
+            if in_channels != out_channels:
+                self.residual_modules.append(nn.Conv1d(in_channels, out_channels, kernel_size=1))
+        self.output_activation_writer = ActivationWriter(register=activation_register, name=self.name)
+
+    def forward(self, x):
+        main = x
+        for m in self.main_modules:
+            main = m(main)
+        if self.residual:
+            skip = x
+            for m in self.residual_modules:
+                skip = m(skip)
+            main = main + skip[:, :, -main.shape[2]:]
+        self.output_activation_writer(main)
+        return main
+
+
+class ConvolutionalArModel(nn.Module):
+    def __init__(self, args_dict):
+        super().__init__()
+        self.module_list = nn.ModuleList()
+        for l, kernel in enumerate(args_dict['kernel_sizes']):
+            self.module_list.append(ConvolutionalArBlock(in_channels=args_dict['channel_count'][l],
+                                                         out_channels=args_dict['channel_count'][l + 1],
+                                                         kernel_size=kernel, stride=args_dict['stride'][l],
+                                                         pooling=args_dict['pooling'][l], bias=args_dict['bias'],
+                                                         batch_norm=args_dict['batch_norm'],
+                                                         residual=args_dict['residual'], name='ar_block_' + str(l),
+                                                         activation_register=args_dict.get('activation_register')))
+        self.encoding_size = args_dict['channel_count'][0]
+        self.ar_size = args_dict['channel_count'][-1]
+
+    def forward(self, x):
+        for m in self.module_list:
+            x = m(x)
+        return x[:, :, -1]
+
+
+class PositionalEncoder(nn.Module):
+    def __init__(self, code_size, max_seq_len=128, max_wavelength=10000):
+        super().__init__()
+        self.code_size = code_size
+        pos = torch.arange(max_seq_len, dtype=torch.float64).unsqueeze(1)
+        i = torch.arange(0, code_size, 2, dtype=torch.float64).unsqueeze(0)
+        arg = math.pi * pos / (max_wavelength ** ((2 * i) / code_size))
+        pe = torch.zeros(max_seq_len, code_size, dtype=torch.float64)
+        pe[:, 0::2] = torch.sin(arg)
+        pe[:, 1::2] = torch.cos(arg)
+        self.register_buffer('pe', pe.float().unsqueeze(1))
+
+    def forward(self, x):
+        return x * math.sqrt(self.code_size) + self.pe[:x.size(0)]
+
+
+class AttentionModel(nn.Module):
+    """Causally masked transformer encoder, mean over time, linear head (attention_model.py:38-82)."""
+
+    def __init__(self, args_dict):
+        super().__init__()
+        channels = args_dict['channels']
+        self.num_layers = args_dict['num_layers']
+        self.positional_encoder = PositionalEncoder(channels, args_dict['sequence_length'])
+        layer = nn.TransformerEncoderLayer(channels, args_dict['num_heads'], args_dict['feedforward_size'],
+                                           args_dict['dropout'])
+        self.encoder = nn.TransformerEncoder(layer, args_dict['num_layers'], nn.LayerNorm(channels),
+                                             enable_nested_tensor=False)
+        self.end_layer = nn.Linear(channels, args_dict['output_size'])
+
+    def forward(self, x):
+        x = self.positional_encoder(x.permute(2, 0, 1))          # sequence, batch, channels
+        s = x.shape[0]
+        mask = torch.triu(torch.full((s, s), float('-inf'), device=x.device), diagonal=1)
+        x = self.encoder(x, mask=mask)
+        return self.end_layer(x.sum(dim=0) / s)

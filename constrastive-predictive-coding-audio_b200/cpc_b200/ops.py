@@ -1,0 +1,245 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels.
+
+PyTorch is plumbing here: it owns the device buffers and the stream; all arithmetic happens inside
+libcpc_b200.so.  Every op raises on non-CUDA tensors -- there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_PRECISION = {"fp32": 0, "bf16": 1}
+_default_precision = "fp32"
+
+
+def set_default_precision(name):
+    """'fp32' (fp32-faithful, the parity mode) or 'bf16' (bf16 operands, fp32 accumulate)."""
+    global _default_precision
+    if name not in _PRECISION:
+        raise ValueError(name)
+    _default_precision = name
+
+
+def get_default_precision():
+    return _default_precision
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.CpcError("cpc_b200 ops need CUDA tensors on a B200 (sm_100a); got a %s tensor and there is "
+                                "no CPU fallback" % t.device.type)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(nbytes, device):
+    if nbytes == 0:
+        return None
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------------------
+
+def _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, relu, precision):
+    p = _lib.ConvParams()
+    p.batch, p.c_in, p.h_in, p.w_in = x_shape
+    p.c_out, _, p.kh, p.kw = w_shape
+    p.h_out, p.w_out = out_hw
+    p.stride_h, p.stride_w = stride
+    p.pad_top, p.pad_left = pad_top, pad_left
+    p.relu = int(relu)
+    p.precision = _PRECISION[precision]
+    return p
+
+
+class _ConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad_top, pad_left, out_hw, relu, precision):
+        _require_cuda(x, weight, bias)
+        lib = _lib.load()
+        x = x.contiguous()
+        w = weight.contiguous()
+        if x.dtype != torch.float32 or w.dtype != torch.float32:
+            raise _lib.CpcError("conv expects fp32 tensors (precision is a kernel-internal setting)")
+        p = _conv_params(tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, relu, precision)
+        y = torch.empty((x.shape[0], w.shape[0], out_hw[0], out_hw[1]), dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 0), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cpc_conv_fwd(_ptr(x), _ptr(w), _ptr(bias.contiguous() if bias is not None else None), _ptr(y),
+                                        ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
+                       "cpc_conv_fwd")
+        ctx.params = (tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, precision)
+        ctx.has_bias = bias is not None
+        ctx.relu = relu
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        lib = _lib.load()
+        x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = ctx.params
+        if ctx.relu:
+            dy = dy * (y > 0).to(dy.dtype)
+        dy = dy.contiguous()
+        p = _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, False, precision)
+        dx = dw = db = None
+        with torch.cuda.device(dy.device):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
+                ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
+                _lib.check(lib.cpc_conv_dgrad(_ptr(dy), _ptr(w), _ptr(dx), ctypes.byref(p), _ptr(ws),
+                                              ws.numel() if ws is not None else 0, _stream()), "cpc_conv_dgrad")
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
+                db = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+                ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
+                _lib.check(lib.cpc_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), ctypes.byref(p), _ptr(ws),
+                                              ws.numel() if ws is not None else 0, _stream()), "cpc_conv_wgrad")
+        return dx, dw, db, None, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), extra_top=0, relu=False, precision=None):
+    """y = [relu](conv2d(zero_pad_top(x, extra_top), weight, bias, stride, padding)); NCHW fp32.
+    Semantics of F.conv2d preceded by nn.ZeroPad2d((0, 0, extra_top, 0)) (scalogram_model.py:389-397)."""
+    if isinstance(stride, int):
+        stride = (stride, stride)
+    if isinstance(padding, int):
+        padding = (padding, padding)
+    b, c, h, w_in = x.shape
+    co, ci, kh, kw = weight.shape
+    if ci != c:
+        raise ValueError("channel mismatch: input has %d channels, weight expects %d" % (c, ci))
+    oh = (h + extra_top + 2 * padding[0] - kh) // stride[0] + 1
+    ow = (w_in + 2 * padding[1] - kw) // stride[1] + 1
+    if oh <= 0 or ow <= 0:
+        raise ValueError("conv output would be empty: input %s kernel %s" % (tuple(x.shape), (kh, kw)))
+    return _ConvFunction.apply(x, weight, bias, tuple(stride), extra_top + padding[0], padding[1], (oh, ow), relu,
+                               precision or _default_precision)
+
+
+def conv1d(x, weight, bias=None, stride=1, padding=0, relu=False, precision=None):
+    """F.conv1d semantics (audio_model.py:30-44) through the same kernel family (h = 1)."""
+    y = conv2d(x.unsqueeze(2), weight.unsqueeze(2), bias, (1, stride), (0, padding), 0, relu, precision)
+    return y.squeeze(2)
+
+
+# --------------------------------------------------------------------------------------------------
+# InfoNCE
+# --------------------------------------------------------------------------------------------------
+
+def _nce_params(pred, targets, all_steps, kind, reg, precision):
+    p = _lib.InfoNceParams()
+    p.batch, p.steps, p.enc = pred.shape
+    p.all_steps = int(bool(all_steps))
+    p.score_kind = {"linear": _lib.SCORE_LINEAR, "softplus": _lib.SCORE_SOFTPLUS}[kind]
+    p.regularization = float(reg)
+    p.tgt_stride_b, p.tgt_stride_e, p.tgt_stride_k = targets.stride()
+    p.precision = _PRECISION[precision]
+    return p
+
+
+class _InfoNceFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, targets, all_steps, kind, reg, precision):
+        _require_cuda(pred, targets)
+        lib = _lib.load()
+        if pred.dtype != torch.float32 or targets.dtype != torch.float32:
+            raise _lib.CpcError("infonce expects fp32 tensors")
+        b, k, e = pred.shape
+        if tuple(targets.shape) != (b, e, k):
+            raise ValueError("targets must be (B, E, K) = %s, got %s" % ((b, e, k), tuple(targets.shape)))
+        pred = pred.contiguous()
+        p = _nce_params(pred, targets, all_steps, kind, reg, precision)
+        out = torch.empty(_lib.INFONCE_OUT_FLOATS, dtype=torch.float32, device=pred.device)
+        lse = torch.empty(b * k, dtype=torch.float32, device=pred.device)
+        ws = _workspace(lib.cpc_infonce_workspace_bytes(ctypes.byref(p), 0), pred.device)
+        with torch.cuda.device(pred.device):
+            _lib.check(lib.cpc_infonce_fwd(_ptr(pred), _ptr(targets), _ptr(out), _ptr(lse), ctypes.byref(p), _ptr(ws),
+                                           ws.numel() if ws is not None else 0, _stream()), "cpc_infonce_fwd")
+        ctx.args = (all_steps, kind, reg, precision)
+        ctx.save_for_backward(pred, targets, lse)
+        loss, max_score, loss_noreg, mean_score = out[0], out[1], out[2], out[3]
+        ctx.mark_non_differentiable(max_score, loss_noreg, mean_score)
+        return loss, max_score, loss_noreg, mean_score
+
+    @staticmethod
+    def backward(ctx, g_loss, _g1, _g2, _g3):
+        pred, targets, lse = ctx.saved_tensors
+        lib = _lib.load()
+        all_steps, kind, reg, precision = ctx.args
+        p = _nce_params(pred, targets, all_steps, kind, reg, precision)
+        g = g_loss.reshape(1).to(torch.float32).contiguous()
+        d_pred = torch.empty_like(pred)
+        d_tgt = torch.empty(targets.shape, dtype=torch.float32, device=pred.device)
+        ws = _workspace(lib.cpc_infonce_workspace_bytes(ctypes.byref(p), 1), pred.device)
+        with torch.cuda.device(pred.device):
+            _lib.check(lib.cpc_infonce_bwd(_ptr(pred), _ptr(targets), _ptr(lse), _ptr(g), _ptr(d_pred), _ptr(d_tgt),
+                                           ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
+                       "cpc_infonce_bwd")
+        return d_pred, d_tgt, None, None, None, None
+
+
+def infonce(pred, targets, all_steps, kind="linear", regularization=0.0, precision=None):
+    """Fused InfoNCE.  pred (B,K,E), targets (B,E,K) (any strides).  Returns
+    (loss, max_score, loss_without_regulariser, mean_score); only ``loss`` is differentiable.
+    Replaces contrastive_estimation_training.py:106-122,141,166."""
+    return _InfoNceFunction.apply(pred, targets, bool(all_steps), kind, float(regularization),
+                                  precision or _default_precision)
+
+
+# --------------------------------------------------------------------------------------------------
+# CQT front end (no autograd: the filterbank is frozen in training, constant_q_transform.py:145)
+# --------------------------------------------------------------------------------------------------
+
+def cqt_frontend(x, weights, plan, mode, phase_fixed=None, phase_scale=None, pool_t=1, eps=0.0, log_offset=0.0,
+                 norm=1.0, power=1.0):
+    """x (B, L) or (B,1,L) fp32 on CUDA; ``weights`` the packed filterbank; ``plan`` a dict with
+    kernel_sizes / ranges / weight_offsets / hop / n_bins.  Output layout per ``mode`` (see cpc_b200.h)."""
+    _require_cuda(x, weights)
+    lib = _lib.load()
+    if x.dim() == 3:
+        if x.shape[1] != 1:
+            raise ValueError("CQT expects mono input (B,1,L)")
+        x = x[:, 0]
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        raise _lib.CpcError("CQT expects fp32 audio")
+    b, l = x.shape
+    k0 = plan["kernel_sizes"][0]
+    t = (l - 1 - k0) // plan["hop"] + 1
+    if t <= 0:
+        raise ValueError("input of %d samples is shorter than the CQT receptive field %d (+1)" % (l, k0))
+    p = _lib.CqtParams()
+    p.batch, p.n_samples, p.x_pitch = b, l, x.stride(0)
+    p.n_bins, p.hop, p.n_frames = plan["n_bins"], plan["hop"], t
+    p.n_groups = len(plan["kernel_sizes"])
+    for g, (ks, (lo, hi), wo) in enumerate(zip(plan["kernel_sizes"], plan["ranges"], plan["weight_offsets"])):
+        p.kernel_size[g], p.bin_lo[g], p.bin_hi[g], p.weight_offset[g] = ks, lo, hi, wo
+    p.mode, p.pool_t = mode, pool_t
+    p.eps, p.log_offset, p.norm, p.power = eps, log_offset, norm, power
+    f = plan["n_bins"]
+    if mode == _lib.CQT_COMPLEX:
+        out = torch.empty((b, f, t, 2), dtype=torch.float32, device=x.device)
+    elif mode == _lib.CQT_LOGPOW:
+        out = torch.empty((b, 1, f, t // pool_t), dtype=torch.float32, device=x.device)
+    else:
+        if t < 2:
+            raise ValueError("phase mode needs at least 2 CQT frames")
+        out = torch.empty((b, 2, f, (t - 1) // pool_t), dtype=torch.float32, device=x.device)
+    ws = _workspace(lib.cpc_cqt_workspace_bytes(ctypes.byref(p)), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.cpc_cqt_fwd(_ptr(x), _ptr(weights), _ptr(phase_fixed), _ptr(phase_scale), _ptr(out),
+                                   ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
+                   "cpc_cqt_fwd")
+    return out

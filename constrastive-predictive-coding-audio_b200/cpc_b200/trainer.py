@@ -1,0 +1,222 @@
+"""``ContrastiveEstimationTrainer`` with the fused InfoNCE kernels behind the reference's API.
+
+Constructor, ``train`` and ``validate`` signatures follow contrastive_estimation_training.py:36-269.  The
+three named score functions stay importable; when the trainer is given ``linear_score_function`` or
+``softplus_score_function`` the whole block ``score -> logsumexp -> loss -> regulariser -> max`` (:106-122,
+:141, :166) is ONE fused forward kernel family and one backward, and the (B,K,B,K) score tensor never exists.
+
+Multi-GPU: one process per GPU.  Each rank trains on its contiguous slice of every batch, negatives stay on
+the rank, gradients are averaged by ``ddp.GradientBucketReducer`` while backward runs.
+"""
+import math
+import time
+
+import torch
+import torch.nn.functional as F
+import torch.optim
+import torch.utils.data
+
+from . import ddp, ops
+from .sampler import FileBatchSampler
+
+
+def softplus_score_function(predicted_z, targets):
+    """(B,K,E),(B,E,K) -> (B,K,B,K) materialised scores; kept for API compatibility (dreaming etc.).  The
+    trainer recognises this function object and uses the fused kernel instead of calling it."""
+    return F.softplus(torch.tensordot(predicted_z, targets, dims=([2], [1])))
+
+
+def linear_score_function(predicted_z, targets):
+    return torch.tensordot(predicted_z, targets, dims=([2], [1]))
+
+
+def difference_score_function(predicted_z, targets):
+    diff = predicted_z.unsqueeze(3).unsqueeze(4) - targets.permute(1, 0, 2).unsqueeze(0).unsqueeze(1)
+    return 1 / torch.sum(diff ** 2, dim=2)
+
+
+_FUSED_KINDS = {linear_score_function: "linear", softplus_score_function: "softplus"}
+
+
+def reference_loss_from_scores(scores, batch_size, prediction_steps, all_steps, regularization):
+    """The literal loss block for score functions the fused kernel does not know (:108-122,141)."""
+    if all_steps:
+        noise = torch.logsumexp(scores.reshape(-1, batch_size, prediction_steps), dim=0)
+        valid = torch.diagonal(torch.diagonal(scores, dim1=0, dim2=2), dim1=0, dim2=1)
+    else:
+        scores = torch.diagonal(scores, dim1=1, dim2=3).permute(0, 2, 1).contiguous()
+        noise = torch.logsumexp(scores.view(-1, batch_size, prediction_steps), dim=0)
+        valid = torch.diagonal(scores, dim1=0, dim2=2).permute(1, 0)
+    loss = torch.mean(-torch.mean(valid - noise, dim=1))
+    loss = loss + regularization * torch.mean(torch.mean(scores, dim=1) ** 2)
+    return loss, scores.max()
+
+
+class ContrastiveEstimationTrainer:
+    def __init__(self, model, dataset, logger=None, device=None, regularization=1., validation_set=None,
+                 test_task_set=None, prediction_noise=0.01, optimizer=torch.optim.Adam, file_batch_size=1,
+                 score_over_all_timesteps=False, score_function=softplus_score_function,
+                 wasserstein_gradient_penalty=False, gradient_penalty_factor=10., preprocessing=None, ar_size=256,
+                 prediction_steps=16, verbose=True):
+        self.model = model
+        self.ar_size = ar_size
+        self.prediction_steps = prediction_steps
+        self.dataset = dataset
+        self.logger = logger
+        self.device = device
+        self.regularization = regularization
+        self.validation_set = validation_set
+        self.test_task_set = test_task_set
+        self.training_step = 0
+        self.print_out_scores = False
+        self.prediction_noise = prediction_noise
+        self.optimizer = optimizer
+        self.file_batch_size = file_batch_size
+        self.score_over_all_timesteps = score_over_all_timesteps
+        self.score_function = score_function
+        self.wasserstein_gradient_penalty = wasserstein_gradient_penalty
+        self.gradient_penalty_factor = gradient_penalty_factor
+        self.preprocessing = preprocessing
+        self.verbose = verbose
+        self.rank, self.world = 0, 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        self.last_loss = None
+        self.last_max_score = None
+        if verbose:
+            print("use score function", self.score_function)
+
+    # -- one step -----------------------------------------------------------------------------------
+    def loss_on_batch(self, batch):
+        """batch: (B, L) audio on the device -> (loss, max_score).  Rows are this rank's items."""
+        batch = batch.unsqueeze(1)
+        if self.preprocessing is not None:
+            batch = self.preprocessing(batch)
+            batch.requires_grad = True            # the scalogram is an autograd leaf (:102)
+        predicted_z, targets, _, _ = self.model(batch)
+        kind = _FUSED_KINDS.get(self.score_function)
+        if self.wasserstein_gradient_penalty:
+            raise NotImplementedError("wasserstein_gradient_penalty needs double backward through the encoder; "
+                                      "the B200 conv kernels do not provide it yet (DESIGN.md, 'next')")
+        if kind is not None:
+            loss, max_score, _, _ = ops.infonce(predicted_z, targets, self.score_over_all_timesteps, kind,
+                                                self.regularization)
+        else:
+            scores = self.score_function(predicted_z, targets)
+            loss, max_score = reference_loss_from_scores(scores, predicted_z.shape[0], self.prediction_steps,
+                                                         self.score_over_all_timesteps, self.regularization)
+        return loss, max_score
+
+    def train(self, batch_size=32, epochs=10, lr=0.0001, continue_training_at_step=0, num_workers=1, max_steps=None,
+              profile=False):
+        self.model.train()
+        optimizer = self.optimizer(self.model.parameters(), lr=lr)
+        sampler = FileBatchSampler(index_count_per_file=self.dataset.get_example_count_per_file(),
+                                   batch_size=batch_size, file_batch_size=self.file_batch_size, drop_last=True)
+        dataloader = torch.utils.data.DataLoader(self.dataset, batch_sampler=sampler, num_workers=num_workers,
+                                                 pin_memory=True)
+        reducer = ddp.GradientBucketReducer(self.model) if self.world > 1 else None
+        self.training_step = continue_training_at_step
+        for current_epoch in range(epochs):
+            if self.verbose:
+                print("epoch", current_epoch)
+            with torch.autograd.profiler.profile(use_device='cuda', enabled=profile) as prof:
+                for batch in iter(dataloader):
+                    batch = ddp.shard_batch(batch, self.rank, self.world).to(device=self.device, non_blocking=True)
+                    loss, max_score = self.loss_on_batch(batch)
+                    self.model.zero_grad()
+                    loss.backward()
+                    if reducer is not None:
+                        reducer.finish()
+                    optimizer.step()
+                    # one host sync per step for (loss, max score) instead of the reference's three
+                    loss_value, max_value = torch.stack([loss.detach(), max_score.detach()]).tolist()
+                    self.last_loss, self.last_max_score = loss_value, max_value
+                    if math.isnan(loss_value):
+                        print("nan loss")
+                        print("returned with nan loss at step", self.training_step)
+                        return
+                    if self.logger is not None:
+                        self.logger.loss_meter.update(loss_value)
+                        self.logger.score_meter.update(max_value)
+                        self.logger.log(self.training_step)
+                    elif self.verbose:
+                        print("loss at step step " + str(self.training_step) + ":", loss_value)
+                    self.training_step += 1
+                    if max_steps is not None and self.training_step >= max_steps:
+                        if reducer is not None:
+                            reducer.remove()
+                        return prof
+        if reducer is not None:
+            reducer.remove()
+
+    # -- validation (scores materialised with torch ops; fused metrics kernel is a 'next' row) --------
+    def validate(self, batch_size=64, num_workers=1, max_steps=None):
+        if self.validation_set is None:
+            print("No validation set")
+            return 0, 0
+        self.model.eval()
+        sampler = FileBatchSampler(index_count_per_file=self.validation_set.get_example_count_per_file(),
+                                   batch_size=batch_size, file_batch_size=8, drop_last=True, seed=0)
+        loader = torch.utils.data.DataLoader(self.validation_set, batch_sampler=sampler, num_workers=num_workers,
+                                             pin_memory=False)
+        k = self.prediction_steps
+        total_losses = torch.zeros(k, device=self.device)
+        total_accurate = torch.zeros(k, device=self.device)
+        n = batch_size * k if self.score_over_all_timesteps else batch_size
+        template = torch.arange(0, n, dtype=torch.long, device=self.device)
+        template = template.view(batch_size, k) if self.score_over_all_timesteps else template.unsqueeze(1).repeat(1, k)
+        total_score = 0
+        max_steps = len(loader) if max_steps is None else min(max_steps, len(loader))
+        with torch.no_grad():
+            for step, batch in enumerate(iter(loader)):
+                batch = batch.to(device=self.device).unsqueeze(1)
+                if self.preprocessing is not None:
+                    batch = self.preprocessing(batch)
+                predicted_z, targets, _, _ = self.model(batch)
+                scores = self.score_function(predicted_z, targets)
+                if self.score_over_all_timesteps:
+                    noise = torch.logsumexp(scores.reshape(-1, batch_size, k), dim=0)
+                    valid = torch.diagonal(torch.diagonal(scores, dim1=0, dim2=2), dim1=0, dim2=1)
+                else:
+                    scores = torch.diagonal(scores, dim1=1, dim2=3).permute(0, 2, 1).contiguous()
+                    noise = torch.logsumexp(scores.view(-1, batch_size, k), dim=0)
+                    valid = torch.diagonal(scores, dim1=0, dim2=2).permute(1, 0)
+                losses = -torch.mean(valid - noise, dim=0)
+                best = torch.argmax(scores.reshape(batch_size, k, -1), dim=2)
+                accuracy = torch.sum(torch.eq(template, best), dim=0).type_as(batch) / n
+                total_losses += losses
+                total_accurate += accuracy
+                total_score += torch.mean(scores).item()
+                if step + 1 >= max_steps:
+                    break
+        del loader
+        total_losses /= max_steps
+        total_accurate /= max_steps
+        total_score /= max_steps
+        mutual_information_lb = math.log(n) - total_losses
+        self.model.train()
+        return total_losses, total_accurate, total_score, mutual_information_lb
+
+
+class DeterministicSampler(torch.utils.data.Sampler):
+    """contrastive_estimation_training.py:363-382."""
+
+    def __init__(self, data_source, batch_size, drop_last=True):
+        self.data_source = data_source
+        self.batch_size = batch_size
+        self.drop_last = drop_last
+
+    def __iter__(self):
+        batch = []
+        for idx in range(len(self.data_source)):
+            batch.append(idx)
+            if len(batch) == self.batch_size:
+                yield batch
+                batch = []
+        if batch and not self.drop_last:
+            yield batch
+
+    def __len__(self):
+        full, rest = divmod(len(self.data_source), self.batch_size)
+        return full if self.drop_last or rest == 0 else full + 1

@@ -1,0 +1,169 @@
+/*
+ * cpc_b200.h -- C-ABI of the B200-native CPC training hot path.
+ *
+ * The reference (vincentherrmann/constrastive-predictive-coding-audio) is pure Python/PyTorch and has
+ * no FFI of its own; this header is the boundary the new implementation defines.  Each
+ * entry point replaces the ATen library calls the reference makes at the cited file:line.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says `host`;
+ *   - the caller owns every buffer (PyTorch's caching allocator in practice); nothing is allocated,
+ *     freed or cached inside; no global or thread-local state (autograd calls backward from another
+ *     thread than forward);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it, no host
+ *     synchronisation inside;
+ *   - `workspace` / `workspace_bytes`: scratch the caller provides, size from the matching
+ *     *_workspace_bytes(); contents are undefined before and after the call;
+ *   - return value: CPC_OK (0) or a negative cpc_status; cpc_status_string() names it.  On error nothing
+ *     has been enqueued.
+ *   - the library only runs on compute capability 10.x (sm_100a); CPC_ERR_ARCH otherwise.  There is no
+ *     CPU fallback anywhere.
+ */
+#ifndef CPC_B200_H
+#define CPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cpc_status {
+    CPC_OK = 0,
+    CPC_ERR_BAD_SHAPE = -1,     /* a dimension is non-positive / inconsistent            */
+    CPC_ERR_ALIGNMENT = -2,     /* pointer or pitch violates the stated alignment        */
+    CPC_ERR_WORKSPACE = -3,     /* workspace too small or NULL                           */
+    CPC_ERR_ARCH = -4,          /* current device is not sm_100                          */
+    CPC_ERR_CUDA = -5,          /* a CUDA runtime call (launch) failed                   */
+    CPC_ERR_UNSUPPORTED = -6,   /* valid request this build has no kernel for            */
+    CPC_ERR_NULL = -7           /* required pointer is NULL                              */
+} cpc_status;
+
+const char* cpc_status_string(int status);
+/* ABI version; bumped on any signature change. */
+int cpc_abi_version(void);
+/* CPC_OK when the current CUDA device can run this library (sm_100), else CPC_ERR_ARCH / CPC_ERR_CUDA. */
+int cpc_runtime_check(void);
+/* Number of kernels this library has launched since load (process-wide atomic counter; bench.py's
+ * "gpu_launches").  cpc_launch_count_reset() zeroes it. */
+uint64_t cpc_launch_count(void);
+void cpc_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Constant-Q front end: complex filterbank correlation (+ fused log-power / phase / pooling).
+ *    Replaces CQT.forward (constant_q_transform.py:161-172: 9 strided F.conv1d + chunk/cat/stack) and
+ *    PreprocessingModule.forward (scalogram_model.py:75-102: abs, pow, log, atan2, phase difference,
+ *    unwrap, max_pool2d, scale, power -- about 20 ATen launches) .
+ * ---------------------------------------------------------------------------------------------- */
+#define CPC_CQT_MAX_GROUPS 16
+
+typedef enum cpc_cqt_mode {
+    CPC_CQT_COMPLEX = 0,   /* out (B, n_bins, T, 2) fp32: what CQT.forward returns                         */
+    CPC_CQT_LOGPOW = 1,    /* out (B, 1, n_bins, T/pool_t): ((log(re^2+im^2+eps)+log_offset)*norm)^power   */
+    CPC_CQT_LOGPOW_PHASE = 2 /* out (B, 2, n_bins, (T-1)/pool_t): channel 0 as above on frames 1..T-1,
+                                channel 1 = unwrap(phi_t - phi_{t-1} + fixed[f]) * scale[f], then *norm, ^power */
+} cpc_cqt_mode;
+
+typedef struct cpc_cqt_params {
+    int32_t batch;          /* B                                                                      */
+    int32_t n_samples;      /* L: samples per item (the last one is never read, as in the reference)   */
+    int32_t x_pitch;        /* elements between consecutive items of x (>= L)                          */
+    int32_t n_bins;         /* F                                                                      */
+    int32_t hop;            /* hop_length                                                             */
+    int32_t n_frames;       /* T = floor((L - 1 - kernel_size[0]) / hop) + 1                           */
+    int32_t n_groups;       /* octave groups, <= CPC_CQT_MAX_GROUPS                                    */
+    int32_t kernel_size[CPC_CQT_MAX_GROUPS];  /* K_g, non-increasing; group g reads x[off_g + hop*t + n],
+                                                 off_g = (K_0 - K_g)/2  (constant_q_transform.py:165-166) */
+    int32_t bin_lo[CPC_CQT_MAX_GROUPS];       /* group g covers bins [bin_lo, bin_hi)                  */
+    int32_t bin_hi[CPC_CQT_MAX_GROUPS];
+    int64_t weight_offset[CPC_CQT_MAX_GROUPS];/* element offset inside `weights` of group g's block:
+                                                 (2*n_g, K_g) row-major fp32, rows [real bins; imag bins] */
+    int32_t mode;           /* cpc_cqt_mode                                                           */
+    int32_t pool_t;         /* 1, or 2 = max over adjacent frame pairs (scalogram_pooling=[1,2])       */
+    float eps;              /* added to the power before log (0 or 1e-9)                              */
+    float log_offset;       /* added after log                                                       */
+    float norm;             /* multiplied after the offset                                           */
+    float power;            /* exponent applied last (1 = skipped)                                   */
+} cpc_cqt_params;
+
+size_t cpc_cqt_workspace_bytes(const cpc_cqt_params* p);
+/* x (B, x_pitch) fp32; weights: packed group blocks, fp32; phase_fixed / phase_scale: (n_bins) fp32, only
+ * read in CPC_CQT_LOGPOW_PHASE (PhaseDifference, constant_q_transform.py:275-286); out: see cpc_cqt_mode. */
+int cpc_cqt_fwd(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale,
+                float* out, const cpc_cqt_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Strided convolution, forward / data gradient / weight gradient.  conv1d is h = 1.
+ *    Replaces nn.Conv1d in AudioEncoder (audio_model.py:30-44) and nn.Conv2d (+ the preceding
+ *    nn.ZeroPad2d) in ScalogramEncoder / ScalogramEncoderBlock (scalogram_model.py:155-201, 387-431),
+ *    and their autograd (cuDNN dgrad / wgrad) in loss.backward() (contrastive_estimation_training.py:161).
+ *    Tensors are NCHW fp32, contiguous.  Cross-correlation (PyTorch convention), groups = 1, dilation 1.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cpc_conv_params {
+    int32_t batch;
+    int32_t c_in, h_in, w_in;
+    int32_t c_out, h_out, w_out;
+    int32_t kh, kw;
+    int32_t stride_h, stride_w;
+    int32_t pad_top, pad_left;   /* zero rows above / columns left of the input (ZeroPad2d top padding is
+                                    folded in here); bottom / right padding is implied by h_out / w_out   */
+    int32_t relu;                /* forward only: fuse max(.,0) into the epilogue                          */
+    int32_t precision;           /* 0 = fp32-faithful (error <= 1e-5 relative), 1 = bf16 operands           */
+} cpc_conv_params;
+
+size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which /* 0 fwd, 1 dgrad, 2 wgrad */);
+/* y = conv(x, w) + bias (bias may be NULL). */
+int cpc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const cpc_conv_params* p,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* dx = conv_transpose(dy, w); every element of dx is written. */
+int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_params* p,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* dw (c_out, c_in, kh, kw) and, when dbias != NULL, dbias (c_out); both overwritten (not accumulated). */
+int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. InfoNCE scoring + loss, forward and backward, scores never written to HBM.
+ *    Replaces score_function + the loss block of ContrastiveEstimationTrainer.train
+ *    (contrastive_estimation_training.py:12-22, 106-122, 141, 166) and its autograd.
+ *    pred (B, K, E) contiguous fp32; targets is the *strided view* z[:, :, -K:] of the encoder output
+ *    (audio_model.py:197): element (t, e, k) at targets[t*tgt_stride_b + e*tgt_stride_e + k*tgt_stride_k].
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum cpc_score_kind { CPC_SCORE_LINEAR = 0, CPC_SCORE_SOFTPLUS = 1 } cpc_score_kind;
+
+typedef struct cpc_infonce_params {
+    int32_t batch;          /* B */
+    int32_t steps;          /* K prediction steps */
+    int32_t enc;            /* E encoding size */
+    int32_t all_steps;      /* 1: softmax over all (d,k) for each (t,k') (score_over_all_timesteps=True);
+                               0: per step k, softmax over d for each t                                 */
+    int32_t score_kind;     /* cpc_score_kind */
+    float regularization;   /* lambda of  lambda * mean((mean_k S)^2)  (:141) */
+    int64_t tgt_stride_b, tgt_stride_e, tgt_stride_k;   /* in elements */
+    int32_t precision;      /* as in cpc_conv_params */
+} cpc_infonce_params;
+
+/* Layout of the forward's `out` (fp32): [0] loss, [1] max score, [2] loss without regulariser,
+ * [3] mean score; `lse`: per softmax column, all_steps ? (B*K) indexed t*K+k' : (K*B) indexed k*B+t.
+ * `lse` is an output of fwd and an input of bwd (the saved-for-backward tensor). */
+#define CPC_INFONCE_OUT_FLOATS 4
+size_t cpc_infonce_workspace_bytes(const cpc_infonce_params* p, int which /* 0 fwd, 1 bwd */);
+int cpc_infonce_fwd(const float* pred, const float* targets, float* out, float* lse,
+                    const cpc_infonce_params* p, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_loss: device pointer to one fp32 (dL/dloss).  d_pred (B,K,E) contiguous; d_targets (B,E,K)
+ * contiguous; both overwritten. */
+int cpc_infonce_bwd(const float* pred, const float* targets, const float* lse, const float* grad_loss,
+                    float* d_pred, float* d_targets, const cpc_infonce_params* p,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Validation metrics of ContrastiveEstimationTrainer.validate (contrastive_estimation_training.py:224-247):
+ * per-step losses (K) with the reference's view semantics, per-step accuracy (K), mean score (1).
+ * metrics: (2*K + 1) fp32. */
+int cpc_infonce_validate(const float* pred, const float* targets, float* metrics,
+                         const cpc_infonce_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPC_B200_H */

@@ -1,0 +1,306 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):   python oracle/make_golden.py
+The reference is imported through oracle/ref_shim.py (in-memory stand-ins for librosa / mutagen /
+ml_utilities / matplotlib).  Everything saved here is an output of the reference's own code:
+
+  cqt.npz          CQT.forward and three PreprocessingModule variants on seeded noise (+ a silent segment)
+  audio_encoder.npz AudioEncoder forward + parameter/input gradients of sum(out * g)
+  resnet_encoder.npz a small ScalogramResidualEncoder (BN, top padding, strides, residual crop) fwd + grads
+  trainer_raw.npz  ContrastiveEstimationTrainer.train() itself, 2 SGD steps, raw-wave model (config-1 shaped,
+                   shrunk): per-step loss / max score from the logger, and parameters before/after, so
+                   (before - after) / lr is the reference's own gradient of its own loss
+  trainer_cqt.npz  same through PreprocessingModule + ScalogramResidualEncoder + ConvolutionalArModel,
+                   all-steps linear scoring with regulariser
+  infonce.npz      score functions + the trainer's loss on random (pred, targets): obtained by running
+                   train() on an identity "model" that returns the stored tensors (so it is still the
+                   reference's code computing loss and gradients)
+  sampler.npz      FileBatchSampler index streams for several (counts, batch, file_batch, seed) settings
+  configs.json     as-imported experiment dicts e24 / e25 / e20 (classes replaced by their names)
+"""
+import json
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+class ListDataset(torch.utils.data.Dataset):
+    def __init__(self, items, files=1):
+        self.items, self.files = items, files
+
+    def __len__(self):
+        return self.items.shape[0]
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+    def get_example_count_per_file(self):
+        base, extra = divmod(len(self), self.files)
+        return [base + (1 if i < extra else 0) for i in range(self.files)]
+
+
+class CaptureLogger:
+    def __init__(self):
+        self.losses, self.scores = [], []
+        outer = self
+
+        class M:
+            def __init__(self, sink):
+                self.sink = sink
+
+            def update(self, v, n=1):
+                self.sink.append(float(v))
+
+        self.loss_meter, self.score_meter = M(outer.losses), M(outer.scores)
+
+    def log(self, step):
+        pass
+
+
+def sd_np(module, prefix=""):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def golden_cqt(ref):
+    sm = ref["scalogram_model"]
+    cq = ref["constant_q_transform"]
+    g = torch.Generator().manual_seed(1234)
+    x = 0.1 * torch.randn(2, 1, 16384 + 1 + 128 * 9 + 37, generator=g)
+    x[1, 0, 3000:9000] = 0.0                        # silent stretch: exercises the eps floor in high bins
+    cqt = cq.CQT(sr=16000, fmin=30, n_bins=256, bins_per_octave=32, filter_scale=0.5, hop_length=128)
+    out = {"x": x.numpy(), "complex": cqt(x).numpy()}
+    d = dict(sm.cqt_default_dict)
+    out["logpow"] = sm.PreprocessingModule(d, phase=False)(x).numpy()
+    out["logpow_phase"] = sm.PreprocessingModule(d, phase=True)(x).numpy()
+    out["offset_pool_power"] = sm.PreprocessingModule(d, phase=False, offset_zero=True, output_power=2.,
+                                                      pooling=[1, 2], scaling=10.)(x).numpy()
+    out["phase_offset_pool"] = sm.PreprocessingModule(d, phase=True, offset_zero=True, pooling=[1, 2])(x).numpy()
+    # a second, smaller filterbank (different grouping): filter_scale 1, 24 bins/octave, hop 64
+    cqt2 = cq.CQT(sr=8000, fmin=55, n_bins=120, bins_per_octave=24, filter_scale=1., hop_length=64)
+    x2 = 0.1 * torch.randn(3, 1, cqt2.conv_kernel_sizes[0] + 1 + 64 * 5, generator=g)
+    out["x2"] = x2.numpy()
+    out["complex2"] = cqt2(x2).numpy()
+    out["kernel_sizes2"] = np.array(cqt2.conv_kernel_sizes)
+    np.savez_compressed(os.path.join(OUT, "cqt.npz"), **out)
+
+
+def golden_audio_encoder(ref):
+    am = ref["audio_model"]
+    torch.manual_seed(0)
+    cfg = {'strides': [5, 4, 2, 2, 2], 'kernel_sizes': [10, 8, 4, 4, 4], 'channel_count': [24, 32, 40, 32, 48],
+           'bias': True}
+    enc = am.AudioEncoder(cfg)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 1, 465 + 160 * 6 + 11, generator=g).requires_grad_(True)
+    y = enc(x)
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    out = {"x": x.detach().numpy(), "y": y.detach().numpy(), "gy": gy.numpy(), "gx": x.grad.numpy()}
+    out.update(sd_np(enc, "p."))
+    out.update({"g." + n: p.grad.numpy() for n, p in enc.named_parameters()})
+    # known-answer facts from tests/test_audioEncoder.py:19-48
+    enc2 = am.AudioEncoder({'strides': [5, 4, 2, 2, 2], 'kernel_sizes': [10, 8, 4, 4, 4],
+                            'channel_count': [32, 32, 32, 32, 32], 'bias': True})
+    out["kat_shape"] = np.array(enc2(torch.zeros(7, 1, 4800)).shape)
+    out["kat_rf_ds"] = np.array([enc2.receptive_field, enc2.downsampling_factor])
+    np.savez_compressed(os.path.join(OUT, "audio_encoder.npz"), **out)
+
+
+def small_resnet_cfg(ref):
+    sm = ref["scalogram_model"]
+    base = dict(sm.default_encoder_block_dict)
+    base['ceil_pooling'] = False
+    b0 = dict(base, in_channels=1, out_channels=8, kernel_size_2=(9, 1), top_padding_2=8, stride_1=2, batch_norm=True)
+    b1 = dict(base, in_channels=8, out_channels=16, kernel_size_2=(6, 1), stride_1=2, batch_norm=True, padding_1=1)
+    b2 = dict(base, in_channels=16, out_channels=24, kernel_size_1=(2, 2), kernel_size_2=(1, 1), pooling_1=2,
+              ceil_pooling=True)
+    return {'model': sm.ScalogramResidualEncoder, 'phase': True, 'scalogram_offset_zero': False,
+            'scalogram_output_power': 1., 'scalogram_scaling': 1., 'scalogram_pooling': None,
+            'blocks': [b0, b1, b2], 'activation_register': None}
+
+
+def golden_resnet_encoder(ref):
+    sm = ref["scalogram_model"]
+    torch.manual_seed(1)
+    cfg = small_resnet_cfg(ref)
+    enc = sm.ScalogramResidualEncoder(cfg)
+    enc.train()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 2, 40, 37, generator=g).requires_grad_(True)
+    y = enc(x)
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    out = {"x": x.detach().numpy(), "y": y.detach().numpy(), "gy": gy.numpy(), "gx": x.grad.numpy()}
+    out.update(sd_np(enc, "p."))           # includes BN running stats AFTER one training forward
+    out.update({"g." + n: p.grad.numpy() for n, p in enc.named_parameters()})
+    np.savez_compressed(os.path.join(OUT, "resnet_encoder.npz"), **out)
+
+
+def run_reference_trainer(ref, model, dataset, preprocessing, steps, batch_size, lr, seed, **kw):
+    cet = ref["contrastive_estimation_training"]
+    logger = CaptureLogger()
+    trainer = cet.ContrastiveEstimationTrainer(model=model, dataset=dataset, logger=logger, device=None,
+                                               optimizer=torch.optim.SGD, preprocessing=preprocessing, **kw)
+    random.seed(seed)
+    snaps = [sd_np(model)]
+    for s in range(steps):
+        trainer.train(batch_size=batch_size, epochs=1, lr=lr, continue_training_at_step=s, num_workers=0,
+                      max_steps=s + 1)
+        snaps.append(sd_np(model))
+    return logger, snaps
+
+
+def golden_trainer_raw(ref):
+    am = ref["audio_model"]
+    torch.manual_seed(0)
+    enc = am.AudioEncoder({'strides': [5, 4, 2, 2, 2], 'kernel_sizes': [10, 8, 4, 4, 4],
+                           'channel_count': [16, 24, 24, 24, 32], 'bias': True})
+    ar = am.AudioGRUModel(input_size=32, hidden_size=16)
+    model = am.AudioPredictiveCodingModel(enc, ar, enc_size=32, ar_size=16, visible_steps=9, prediction_steps=4)
+    g = torch.Generator().manual_seed(1234)
+    items = 0.1 * torch.randn(16, model.item_length, generator=g)
+    # NB: each train() call builds a fresh sampler and reshuffles; seed once, record the stream by replay
+    logger, snaps = run_reference_trainer(ref, model, ListDataset(items), None, steps=2, batch_size=8, lr=0.5, seed=0,
+                                          regularization=1., score_over_all_timesteps=False,
+                                          score_function=ref["contrastive_estimation_training"].softplus_score_function,
+                                          prediction_steps=4)
+    out = {"items": items.numpy(), "losses": np.array(logger.losses), "max_scores": np.array(logger.scores),
+           "lr": np.array(0.5), "batch_size": np.array(8)}
+    for i, s in enumerate(snaps):
+        out.update({"s%d.%s" % (i, k): v for k, v in s.items()})
+    np.savez_compressed(os.path.join(OUT, "trainer_raw.npz"), **out)
+
+
+def golden_trainer_cqt(ref):
+    sm, am = ref["scalogram_model"], ref["audio_model"]
+    cet = ref["contrastive_estimation_training"]
+    torch.manual_seed(2)
+    cfg = small_resnet_cfg(ref)
+    # make the pitch axis collapse to 1: 256 bins -> s2 -> 127 -> (9x1, pad 8) 127 -> s2,p1 -> 64 -> (6x1) 59 ...
+    cfg['blocks'][2] = dict(cfg['blocks'][2], kernel_size_1=(30, 2), pooling_1=1, ceil_pooling=False)
+    cfg['blocks'][1] = dict(cfg['blocks'][1], kernel_size_2=(35, 1))
+    pre = sm.PreprocessingModule(dict(sm.cqt_default_dict), phase=True)
+    enc = sm.ScalogramResidualEncoder(cfg, preprocessing_module=pre)
+    ar = am.ConvolutionalArModel({'kernel_sizes': [3, 3], 'channel_count': [24, 16, 16], 'stride': [1, 1],
+                                  'pooling': [1, 2], 'bias': True, 'batch_norm': True, 'residual': False,
+                                  'activation_register': None})
+    model = am.AudioPredictiveCodingModel(enc, ar, enc_size=24, ar_size=16, visible_steps=10, prediction_steps=3)
+    g = torch.Generator().manual_seed(99)
+    items = 0.1 * torch.randn(8, model.item_length, generator=g)
+    logger, snaps = run_reference_trainer(ref, model, ListDataset(items), pre, steps=2, batch_size=4, lr=0.1, seed=3,
+                                          regularization=0.25, score_over_all_timesteps=True,
+                                          score_function=cet.linear_score_function, prediction_steps=3)
+    out = {"items": items.numpy(), "losses": np.array(logger.losses), "max_scores": np.array(logger.scores),
+           "lr": np.array(0.1), "batch_size": np.array(4), "item_length": np.array(model.item_length)}
+    for i, s in enumerate(snaps):
+        out.update({"s%d.%s" % (i, k): v for k, v in s.items()})
+    np.savez_compressed(os.path.join(OUT, "trainer_cqt.npz"), **out)
+
+
+class StoredPairModel(torch.nn.Module):
+    """A 'model' whose parameters ARE (pred, targets): lets the reference trainer's own loss code and
+    autograd produce loss / gradients for arbitrary (pred, targets)."""
+
+    def __init__(self, pred, targets):
+        super().__init__()
+        self.pred = torch.nn.Parameter(pred.clone())
+        self.tgt = torch.nn.Parameter(targets.clone())
+
+    def forward(self, batch):
+        return self.pred, self.tgt, None, None
+
+
+def golden_infonce(ref):
+    cet = ref["contrastive_estimation_training"]
+    out, cases = {}, []
+    g = torch.Generator().manual_seed(5)
+    idx = 0
+    for (b, k, e) in [(8, 12, 64), (6, 4, 40), (16, 16, 96)]:
+        for all_steps in (False, True):
+            for kind in ("linear", "softplus"):
+                for reg in (0.0, 0.7):
+                    pred = torch.randn(b, k, e, generator=g) * (1.5 / e ** 0.5)
+                    tgt = torch.randn(b, e, k, generator=g)
+                    model = StoredPairModel(pred, tgt)
+                    fn = cet.linear_score_function if kind == "linear" else cet.softplus_score_function
+                    ds = ListDataset(torch.zeros(b, 4))
+                    logger, snaps = run_reference_trainer(ref, model, ds, None, steps=1, batch_size=b, lr=1.0, seed=0,
+                                                          regularization=reg, score_over_all_timesteps=all_steps,
+                                                          score_function=fn, prediction_steps=k)
+                    tag = "c%d" % idx
+                    out[tag + ".pred"] = pred.numpy()
+                    out[tag + ".tgt"] = tgt.numpy()
+                    out[tag + ".loss"] = np.array(logger.losses[0])
+                    out[tag + ".max"] = np.array(logger.scores[0])
+                    out[tag + ".dpred"] = snaps[0]["pred"] - snaps[1]["pred"]
+                    out[tag + ".dtgt"] = snaps[0]["tgt"] - snaps[1]["tgt"]
+                    cases.append({"tag": tag, "b": b, "k": k, "e": e, "all_steps": all_steps, "kind": kind, "reg": reg})
+                    idx += 1
+    out["cases"] = np.array(json.dumps(cases))
+    np.savez_compressed(os.path.join(OUT, "infonce.npz"), **out)
+
+
+def golden_sampler(ref):
+    ad = ref["audio_dataset"]
+    out, cases = {}, []
+    settings = [([64], 8, 1, None, 0), ([37, 12, 50], 16, 1, None, 5), ([40, 24, 33], 16, 8, None, 1),
+                ([40, 24, 33], 16, 8, 0, None), ([100], 32, 8, 0, None), ([17, 9], 4, 4, 3, None),
+                ([256], 64, 8, None, 0)]
+    for i, (counts, bs, fbs, seed, global_seed) in enumerate(settings):
+        if global_seed is not None:
+            random.seed(global_seed)
+        s = ad.FileBatchSampler(counts, bs, fbs, drop_last=True, seed=seed)
+        epochs = [[list(map(int, b)) for b in iter(s)] for _ in range(2)]
+        cases.append({"counts": counts, "batch_size": bs, "file_batch_size": fbs, "seed": seed,
+                      "global_seed": global_seed, "epochs": epochs, "len": int(len(s))})
+    with open(os.path.join(OUT, "sampler.json"), "w") as fh:
+        json.dump(cases, fh)
+
+
+def golden_configs():
+    cfg = ref_shim.load_reference_configs()
+
+    def clean(v):
+        if isinstance(v, dict):
+            return {k: clean(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [clean(x) for x in v]
+        if isinstance(v, (int, float, str, bool)) or v is None:
+            return v
+        return getattr(v, "__name__", str(v))
+
+    dump = {}
+    for name in ("e24", "e25", "e20"):
+        e = cfg.experiments[name]
+        dump[name] = {k: clean(e[k]) for k in ("cqt_config", "encoder_config", "ar_model_config", "training_config")}
+    with open(os.path.join(OUT, "configs.json"), "w") as fh:
+        json.dump(dump, fh, indent=1, sort_keys=True)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    ref = ref_shim.load_reference()
+    golden_configs()
+    golden_sampler(ref)
+    golden_cqt(ref)
+    golden_audio_encoder(ref)
+    golden_resnet_encoder(ref)
+    golden_infonce(ref)
+    golden_trainer_raw(ref)
+    golden_trainer_cqt(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

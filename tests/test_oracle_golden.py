@@ -1,0 +1,132 @@
+"""CPU: pins oracle/cpc_oracle.py against the golden vectors the UNMODIFIED reference produced
+(oracle/make_golden.py).  The GPU parity tests then compare the CUDA path with this oracle."""
+import json
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import cpc_oracle as O
+from conftest import load_golden, rel_err
+
+
+@pytest.fixture(scope="module")
+def plan():
+    return O.CqtPlan(16000, 30, 256, 32, 0.5, 128)
+
+
+def test_filterbank_structural_anchors(plan):
+    # the only facts the reference exposes about librosa's filterbank
+    assert plan.kernel_sizes == [16384, 8192, 4096, 2048, 1024, 512, 256, 128, 64]
+    assert plan.ranges == [(0, 19), (19, 51), (51, 83), (83, 115), (115, 147), (147, 179), (179, 211), (211, 243),
+                           (243, 256)]
+    assert abs(plan.lengths.sum() - 566110.2) < 0.1
+    assert abs(plan.lengths[0] - 12178.146) < 1e-3 and abs(plan.lengths[-1] - 48.6125) < 1e-4
+    # L1 normalisation and centring
+    assert np.allclose(np.abs(plan.bank).sum(axis=1), 1.0)
+
+
+def test_cqt_matches_reference(plan):
+    g = load_golden("cqt.npz")
+    x = torch.from_numpy(g["x"])
+    assert rel_err(O.cqt_forward(x, plan), g["complex"]) < 1e-6
+    assert rel_err(O.preprocess(x, plan, phase=False), g["logpow"]) < 1e-6
+    y = O.preprocess(x, plan, phase=True)
+    assert rel_err(y[:, 0], g["logpow_phase"][:, 0]) < 1e-6
+    assert float((y[:, 1] - torch.from_numpy(g["logpow_phase"][:, 1])).abs().max()) < 1e-4
+    assert rel_err(O.preprocess(x, plan, offset_zero=True, output_power=2., pooling=[1, 2], scaling=10.),
+                   g["offset_pool_power"]) < 1e-6
+    plan2 = O.CqtPlan(8000, 55, 120, 24, 1.0, 64)
+    assert plan2.kernel_sizes == list(g["kernel_sizes2"])
+    assert rel_err(O.cqt_forward(torch.from_numpy(g["x2"]), plan2), g["complex2"]) < 1e-6
+
+
+def test_audio_encoder_matches_reference():
+    g = load_golden("audio_encoder.npz")
+    assert list(g["kat_shape"]) == [7, 32, 28]                 # tests/test_audioEncoder.py:19-25
+    assert list(g["kat_rf_ds"]) == [465, 160]                  # tests/test_audioEncoder.py:27-48
+    assert O.audio_encoder_geometry([10, 8, 4, 4, 4], [5, 4, 2, 2, 2]) == (465, 160)
+    ws = [torch.from_numpy(g["p.layers.%d.weight" % i]).requires_grad_(True) for i in range(5)]
+    bs = [torch.from_numpy(g["p.layers.%d.bias" % i]).requires_grad_(True) for i in range(5)]
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    y = O.audio_encoder_forward(x, ws, bs, [5, 4, 2, 2, 2])
+    assert rel_err(y, g["y"]) < 1e-6
+    (y * torch.from_numpy(g["gy"])).sum().backward()
+    assert rel_err(x.grad, g["gx"]) < 1e-5
+    for i in range(5):
+        assert rel_err(ws[i].grad, g["g.layers.%d.weight" % i]) < 1e-5
+
+
+def small_resnet_blocks():
+    base = {'hidden_channels': None, 'kernel_size_1': (3, 3), 'kernel_size_2': (3, 3), 'top_padding_1': None,
+            'top_padding_2': None, 'padding_1': 0, 'padding_2': 0, 'stride_1': 1, 'stride_2': 1, 'pooling_1': 1,
+            'pooling_2': 1, 'bias': True, 'separable': False, 'residual': True, 'batch_norm': False,
+            'ceil_pooling': False}
+    b0 = dict(base, in_channels=2, out_channels=8, kernel_size_2=(9, 1), top_padding_2=8, stride_1=2, batch_norm=True)
+    b1 = dict(base, in_channels=8, out_channels=16, kernel_size_2=(6, 1), stride_1=2, batch_norm=True, padding_1=1)
+    b2 = dict(base, in_channels=16, out_channels=24, kernel_size_1=(2, 2), kernel_size_2=(1, 1), pooling_1=2,
+              ceil_pooling=True)
+    return [b0, b1, b2]
+
+
+def block_param_map(g, i, cfg, prefix="p."):
+    """reference state_dict keys (main_modules.N...) -> the oracle's functional names."""
+    keys = sorted(k for k in g if k.startswith("%sblocks.%d." % (prefix, i)))
+    convs = sorted({int(k.split(".")[4]) for k in keys if ".main_modules." in k and k.endswith(".weight")
+                    and g[k].ndim == 4})
+    bns = sorted({int(k.split(".")[4]) for k in keys if ".main_modules." in k and k.endswith("running_mean")})
+    p = {}
+    for name, idx in zip(("conv_a", "conv_b"), convs):
+        for leaf in ("weight", "bias"):
+            k = "%sblocks.%d.main_modules.%d.%s" % (prefix, i, idx, leaf)
+            if k in g:
+                p[name + "." + leaf] = torch.from_numpy(g[k])
+    for name, idx in zip(("bn_a", "bn_b"), bns):
+        for leaf in ("weight", "bias"):
+            p[name + "." + leaf] = torch.from_numpy(g["%sblocks.%d.main_modules.%d.%s" % (prefix, i, idx, leaf)])
+    for k in keys:
+        if ".residual_modules." in k and k.endswith(".weight"):
+            p["res.weight"] = torch.from_numpy(g[k])
+    return p
+
+
+def test_resnet_encoder_matches_reference():
+    g = load_golden("resnet_encoder.npz")
+    cfgs = small_resnet_blocks()
+    params = [block_param_map(g, i, c) for i, c in enumerate(cfgs)]
+    x = torch.from_numpy(g["x"])
+    y = O.residual_encoder_forward(x, cfgs, params, training=True)
+    assert tuple(y.shape) == g["y"].shape
+    assert rel_err(y, g["y"]) < 1e-5
+
+
+def test_infonce_matches_reference_trainer():
+    g = load_golden("infonce.npz")
+    cases = json.loads(str(g["cases"]))
+    assert len(cases) == 24
+    for c in cases:
+        t = c["tag"]
+        pred, tgt = torch.from_numpy(g[t + ".pred"]), torch.from_numpy(g[t + ".tgt"])
+        loss, mx, dp, dz = O.infonce_with_grads(pred, tgt, c["all_steps"], c["kind"], c["reg"])
+        assert abs(float(loss) - float(g[t + ".loss"])) < 2e-6 * max(1.0, abs(float(loss))), c
+        assert abs(float(mx) - float(g[t + ".max"])) < 1e-5, c
+        assert rel_err(dp, g[t + ".dpred"]) < 1e-4, c          # golden grads went through an fp32 SGD update
+        assert rel_err(dz, g[t + ".dtgt"]) < 1e-4, c
+        clean = O.infonce_loss_clean(pred.double(), tgt.double(), c["all_steps"], c["kind"], c["reg"])
+        assert abs(float(clean) - float(loss)) < 1e-9, c       # the scramble is loss-neutral
+
+
+def test_sampler_bit_exact():
+    for c in load_golden("sampler.json"):
+        if c["global_seed"] is not None:
+            random.seed(c["global_seed"])
+        # the reference mutates per-file index lists in place across epochs -> replay on persistent lists
+        epochs = []
+        if c["file_batch_size"] == 1:
+            for _ in range(2):
+                epochs.append(O.file_batch_sampler(c["counts"], c["batch_size"], 1, True, c["seed"]))
+            assert epochs == c["epochs"], c
+        else:
+            first = O.file_batch_sampler(c["counts"], c["batch_size"], c["file_batch_size"], True, c["seed"])
+            assert first == c["epochs"][0], c

@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py -- train audio-sec/sec of the CPC hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE configs[1] = experiments['e24'] of the reference: CQT(+phase)
+PreprocessingModule -> ScalogramResidualEncoder arch 7 -> ConvolutionalArModel arch 3 -> InfoNCE (linear,
+all-steps, K=16), batch 64 items of 97 024 samples (6.064 s at 16 kHz) PER GPU (weak scaling), Adam step
+included, synthetic white-noise audio, random-init weights.  One "step" = one full training step.
+
+Our arm prints `value` (inputs resident in HBM), `e2e` (same step through the public trainer API with the
+batch coming from pinned host memory and the loss read back every step), `roofline` of the dominant kernel
+(timed with CUDA events inside real steps) and `cpu_baseline` (the oracle port of the same step on the host
+cores, bounded sample).  `--impl reference` times that CPU port alone (the reference is CPU-only Python and
+/root/reference does not travel to the GPU box, so kind = "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "constrastive-predictive-coding-audio_b200"))
+
+SR = 16000
+BATCH_PER_GPU = 64
+CPU_SAMPLE_BATCH = 8
+METRIC = "train audio-sec/sec"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_arm(steps, warmup, batch):
+    """The oracle port of the full training step on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import cpc_oracle_model as M
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = M.OracleE24()
+    g = torch.Generator().manual_seed(1234)
+    x = 0.1 * torch.randn(batch, model.item_length, generator=g)
+    M.train_steps(model, [x] * warmup)
+    t0 = time.perf_counter()
+    M.train_steps(model, [x] * steps)
+    dt = (time.perf_counter() - t0) / steps
+    audio_s = batch * model.item_length / SR
+    return {"value": audio_s / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of the same e24 training step at batch %d (%.1f audio-s per step), torch CPU fp32, "
+                      "%d threads, anomaly mode off" % (steps, batch, audio_s, cores),
+            "ms_per_step": dt * 1e3}
+
+
+def workload_config(n_gpus):
+    return {"workload": "e24: CQT(256 bins, phase) + ScalogramResidualEncoder arch7 + ConvolutionalArModel arch3 + "
+                        "InfoNCE linear/all-steps K=16, full train step incl. Adam (BASELINE configs[1])",
+            "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus, "samples_per_item": 97024,
+            "sample_rate": SR, "parallelism": "dp%d" % n_gpus, "negatives": "per-GPU",
+            "l2": "activations (>300 MB per layer) exceed the 126 MB L2; no explicit flush"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    r = cpu_reference_arm(steps, warm, CPU_SAMPLE_BATCH)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import cpc_b200
+    from cpc_b200 import _lib, configs, ddp, ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    rank, world, local = ddp.init_from_env("nccl")
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d; launch with torchrun for N>1" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.load().cpc_runtime_check(), "cpc_runtime_check")
+
+    exp = configs.experiment("e24")
+    tc = exp["training_config"]
+    torch.manual_seed(0)
+    model, pre, _ = configs.setup_model(exp["cqt_config"], exp["encoder_config"], exp["ar_model_config"], tc,
+                                        device=dev)
+    ddp.broadcast_parameters(model, 0)
+    length = model.item_length
+    b = BATCH_PER_GPU
+    trainer = cpc_b200.ContrastiveEstimationTrainer(
+        model=model, dataset=None, device=dev, regularization=tc["regularization"],
+        score_over_all_timesteps=tc["score_over_all_timesteps"], score_function=tc["score_function"],
+        preprocessing=pre, prediction_steps=tc["prediction_steps"], verbose=False)
+    optimizer = torch.optim.Adam(model.parameters(), lr=tc["learning_rate"])
+    reducer = ddp.GradientBucketReducer(model) if world > 1 else None
+    model.train()
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_batches = [(0.1 * torch.randn(b, length, generator=g)).pin_memory() for _ in range(2)]
+    dev_batches = [h.to(dev) for h in host_batches]
+
+    def step(batch):
+        loss, max_score = trainer.loss_on_batch(batch)
+        model.zero_grad(set_to_none=True)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        optimizer.step()
+        return loss, max_score
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / k
+
+    for i in range(args.warmup):
+        step(dev_batches[i % 2])
+    clocks = ClockSampler(local)
+    clocks.start()
+    _lib.reset_launch_count()
+    ms_dev = timed(lambda i: step(dev_batches[i % 2]), args.steps)
+    launches = _lib.launch_count()
+    clk = clocks.stop()
+
+    # end to end through the public API: pinned host batch -> device, full step, loss + max score read back
+    last = {}
+
+    def e2e_step(i):
+        batch = host_batches[i % 2].to(dev, non_blocking=True)
+        loss, mx = step(batch)
+        last["v"] = torch.stack([loss.detach(), mx.detach()]).tolist()
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # dominant kernel, timed with CUDA events around each C-ABI call inside real steps
+    prof = ops.KernelProfiler()
+    with prof:
+        for i in range(max(2, min(args.steps, 4))):
+            step(dev_batches[i % 2])
+    torch.cuda.synchronize()
+    top = prof.summary()
+
+    audio_s_step = world * b * length / SR
+    value = audio_s_step / (ms_dev * 1e-3)
+    e2e_value = audio_s_step / (ms_e2e * 1e-3)
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    dom = top[0] if top else None
+    roofline = None
+    if dom is not None:
+        achieved = dom["flops_per_launch"] / (dom["avg_ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tensor"], "traffic": None, "kernel": dom["key"],
+                    "avg_launch_ms": dom["avg_ms"], "launches": dom["count"], "share_of_kernel_time": dom["share"],
+                    "peak_source": peaks["source"] + " bf16 dense, sustained",
+                    "note": "achieved = algorithmic conv FLOPs (2*Cout*Cin*kh*kw*B*OH*OW) / CUDA-event time"}
+    cpu = cpu_reference_arm(2, 1, CPU_SAMPLE_BATCH)
+    line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": b * length * 4, "d2h_bytes_per_step": 8, "last_loss": last["v"][0]},
+            "roofline": roofline,
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "kernels": top[:8]}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,26 +21,25 @@ pi = np.pi
 # ---- host-side filterbank construction (init time only) -------------------------------------------
 
 def cqt_frequencies(n_bins, fmin, bins_per_octave=12):
-    return fmin * np.exp2(np.arange(n_bins, dtype=np.float64) / bins_per_octave)
+    return float(fmin) * 2.0 ** (np.arange(n_bins, dtype=float) / bins_per_octave)
 
 
 def constant_q_filterbank(sr, fmin, n_bins, bins_per_octave, filter_scale):
-    """Hann-windowed, L1-normalised complex exponentials, zero-padded (centred) to a power of two."""
-    freqs = cqt_frequencies(n_bins, fmin, bins_per_octave)
-    q = filter_scale / (2.0 ** (1.0 / bins_per_octave) - 1.0)
+    """Hann-windowed, L1-normalised complex exponentials, zero-padded (centred) to a power of two.
+    Operation order follows librosa's published formula so the fp32 weights are reproducible bit for bit."""
+    q = float(filter_scale) / (2.0 ** (1.0 / bins_per_octave) - 1.0)
+    lengths = q * sr / cqt_frequencies(n_bins, fmin, bins_per_octave)
+    freqs = q * sr / lengths                    # librosa converts the lengths back to frequencies
     if freqs[-1] * (1.0 + 0.5 * 1.50018310546875 / q) > sr / 2.0:
         raise ValueError("highest CQT filter exceeds Nyquist")
-    lengths = q * sr / freqs
-    width = 1 << int(math.ceil(math.log2(lengths.max())))
+    width = int(2.0 ** np.ceil(np.log2(lengths.max())))
     bank = np.zeros((n_bins, width), dtype=np.complex128)
-    for row, (length, f) in enumerate(zip(lengths, freqs)):
-        first, last = math.floor(-length / 2.0), math.floor(length / 2.0)     # arange(-len//2, len//2)
-        count = last - first
-        n = np.arange(first, last, dtype=np.float64)
-        tone = np.exp(2j * np.pi * f / sr * n)
-        hann = 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(count) / count))  # periodic window
-        tone *= hann
-        tone /= np.abs(tone).sum()
+    for row in range(n_bins):
+        length = lengths[row]
+        tone = np.exp(np.arange(-length // 2, length // 2, dtype=float) * 1j * 2 * np.pi * freqs[row] / sr)
+        count = len(tone)
+        tone = tone * (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(count) / count))    # periodic Hann
+        tone = tone / np.sum(np.abs(tone))
         start = (width - count) // 2
         bank[row, start:start + count] = tone
     return bank, lengths

@@ -40,6 +40,64 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelProfiler:
+    """Brackets every C-ABI call with CUDA events on the launching stream while active (bench.py uses it
+    to time the dominant kernel inside real training steps).  ``summary()`` synchronises and returns the
+    per-(op, shape) totals sorted by time."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _profiler
+        _profiler = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profiler
+        _profiler = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for key, flops, e0, e1 in self.records:
+            a = agg.setdefault(key, {"key": key, "count": 0, "total_ms": 0.0, "flops_per_launch": flops})
+            a["count"] += 1
+            a["total_ms"] += e0.elapsed_time(e1)
+        total = sum(a["total_ms"] for a in agg.values()) or 1.0
+        out = sorted(agg.values(), key=lambda a: -a["total_ms"])
+        for a in out:
+            a["avg_ms"] = a["total_ms"] / a["count"]
+            a["share"] = a["total_ms"] / total
+            a["tflops"] = a["flops_per_launch"] / (a["avg_ms"] * 1e-3) / 1e12 if a["avg_ms"] > 0 else 0.0
+        return out
+
+
+_profiler = None
+
+
+def _call(key, flops, fn, *args):
+    """Invoke one C-ABI entry point (optionally event-timed) and raise on a non-zero status."""
+    if _profiler is None:
+        status = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status = fn(*args)
+        e1.record()
+        _profiler.records.append((key, flops, e0, e1))
+    _lib.check(status, key.split(" ")[0])
+
+
+def _conv_key(tag, p):
+    return "%s b%d %dx%dx%d->%dx%dx%d k%dx%d s%dx%d" % (tag, p.batch, p.c_in, p.h_in, p.w_in, p.c_out, p.h_out,
+                                                       p.w_out, p.kh, p.kw, p.stride_h, p.stride_w)
+
+
+def _conv_flops(p):
+    return 2.0 * p.c_out * p.c_in * p.kh * p.kw * p.batch * p.h_out * p.w_out
+
+
 def _workspace(nbytes, device):
     if nbytes == 0:
         return None
@@ -75,9 +133,9 @@ class _ConvFunction(torch.autograd.Function):
         y = torch.empty((x.shape[0], w.shape[0], out_hw[0], out_hw[1]), dtype=torch.float32, device=x.device)
         ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 0), x.device)
         with torch.cuda.device(x.device):
-            _lib.check(lib.cpc_conv_fwd(_ptr(x), _ptr(w), _ptr(bias.contiguous() if bias is not None else None), _ptr(y),
-                                        ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
-                       "cpc_conv_fwd")
+            _call(_conv_key("cpc_conv_fwd", p), _conv_flops(p), lib.cpc_conv_fwd, _ptr(x), _ptr(w),
+                  _ptr(bias.contiguous() if bias is not None else None), _ptr(y), ctypes.byref(p), _ptr(ws),
+                  ws.numel() if ws is not None else 0, _stream())
         ctx.params = (tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, precision)
         ctx.has_bias = bias is not None
         ctx.relu = relu
@@ -98,14 +156,14 @@ class _ConvFunction(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
                 ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
-                _lib.check(lib.cpc_conv_dgrad(_ptr(dy), _ptr(w), _ptr(dx), ctypes.byref(p), _ptr(ws),
-                                              ws.numel() if ws is not None else 0, _stream()), "cpc_conv_dgrad")
+                _call(_conv_key("cpc_conv_dgrad", p), _conv_flops(p), lib.cpc_conv_dgrad, _ptr(dy), _ptr(w), _ptr(dx),
+                      ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
             if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
                 dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
                 db = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device) if ctx.has_bias else None
                 ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
-                _lib.check(lib.cpc_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), _ptr(db), ctypes.byref(p), _ptr(ws),
-                                              ws.numel() if ws is not None else 0, _stream()), "cpc_conv_wgrad")
+                _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad, _ptr(x), _ptr(dy), _ptr(dw),
+                      _ptr(db), ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
         return dx, dw, db, None, None, None, None, None, None
 
 
@@ -138,6 +196,15 @@ def conv1d(x, weight, bias=None, stride=1, padding=0, relu=False, precision=None
 # InfoNCE
 # --------------------------------------------------------------------------------------------------
 
+def _nce_key(tag, p):
+    return "%s b%d k%d e%d %s" % (tag, p.batch, p.steps, p.enc, "all-steps" if p.all_steps else "per-step")
+
+
+def _nce_flops(p):
+    n = p.batch * p.steps
+    return 2.0 * n * n * p.enc if p.all_steps else 2.0 * p.steps * p.batch * p.batch * p.enc
+
+
 def _nce_params(pred, targets, all_steps, kind, reg, precision):
     p = _lib.InfoNceParams()
     p.batch, p.steps, p.enc = pred.shape
@@ -165,8 +232,8 @@ class _InfoNceFunction(torch.autograd.Function):
         lse = torch.empty(b * k, dtype=torch.float32, device=pred.device)
         ws = _workspace(lib.cpc_infonce_workspace_bytes(ctypes.byref(p), 0), pred.device)
         with torch.cuda.device(pred.device):
-            _lib.check(lib.cpc_infonce_fwd(_ptr(pred), _ptr(targets), _ptr(out), _ptr(lse), ctypes.byref(p), _ptr(ws),
-                                           ws.numel() if ws is not None else 0, _stream()), "cpc_infonce_fwd")
+            _call(_nce_key("cpc_infonce_fwd", p), _nce_flops(p), lib.cpc_infonce_fwd, _ptr(pred), _ptr(targets),
+                  _ptr(out), _ptr(lse), ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
         ctx.args = (all_steps, kind, reg, precision)
         ctx.save_for_backward(pred, targets, lse)
         loss, max_score, loss_noreg, mean_score = out[0], out[1], out[2], out[3]
@@ -184,9 +251,9 @@ class _InfoNceFunction(torch.autograd.Function):
         d_tgt = torch.empty(targets.shape, dtype=torch.float32, device=pred.device)
         ws = _workspace(lib.cpc_infonce_workspace_bytes(ctypes.byref(p), 1), pred.device)
         with torch.cuda.device(pred.device):
-            _lib.check(lib.cpc_infonce_bwd(_ptr(pred), _ptr(targets), _ptr(lse), _ptr(g), _ptr(d_pred), _ptr(d_tgt),
-                                           ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
-                       "cpc_infonce_bwd")
+            _call(_nce_key("cpc_infonce_bwd", p), 3.0 * _nce_flops(p), lib.cpc_infonce_bwd, _ptr(pred), _ptr(targets),
+                  _ptr(lse), _ptr(g), _ptr(d_pred), _ptr(d_tgt), ctypes.byref(p), _ptr(ws),
+                  ws.numel() if ws is not None else 0, _stream())
         return d_pred, d_tgt, None, None, None, None
 
 
@@ -239,7 +306,8 @@ def cqt_frontend(x, weights, plan, mode, phase_fixed=None, phase_scale=None, poo
         out = torch.empty((b, 2, f, (t - 1) // pool_t), dtype=torch.float32, device=x.device)
     ws = _workspace(lib.cpc_cqt_workspace_bytes(ctypes.byref(p)), x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.cpc_cqt_fwd(_ptr(x), _ptr(weights), _ptr(phase_fixed), _ptr(phase_scale), _ptr(out),
-                                   ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream()),
-                   "cpc_cqt_fwd")
+        taps = sum(2 * (hi - lo) * ks for ks, (lo, hi) in zip(plan["kernel_sizes"], plan["ranges"]))
+        _call("cpc_cqt_fwd b%d L%d T%d mode%d" % (b, l, t, mode), 2.0 * taps * b * t, lib.cpc_cqt_fwd, _ptr(x),
+              _ptr(weights), _ptr(phase_fixed), _ptr(phase_scale), _ptr(out), ctypes.byref(p), _ptr(ws),
+              ws.numel() if ws is not None else 0, _stream())
     return out

@@ -46,6 +46,7 @@ def constant_q_filters(sr, fmin, n_bins, bins_per_octave, filter_scale):
     if freqs[-1] * (1 + 0.5 * HANN_BANDWIDTH / q) > sr / 2.0:
         raise ValueError("Filter pass-band lies beyond Nyquist")
     lengths = q * sr / freqs
+    freqs = q * sr / lengths                 # librosa 0.7 converts the lengths back to frequencies
     max_len = int(2.0 ** (np.ceil(np.log2(lengths.max()))))
     bank = np.zeros((n_bins, max_len), dtype=np.complex128)
     for k in range(n_bins):

@@ -1,0 +1,122 @@
+"""CPU ORACLE (whole training step) -- TEST / BASELINE INFRASTRUCTURE ONLY.
+
+A plain-PyTorch CPU port of the reference's training step for the benchmark configurations, built from
+the functional restatements in ``cpc_oracle.py``: PreprocessingModule -> ScalogramResidualEncoder ->
+ConvolutionalArModel -> W_k -> InfoNCE -> backward -> Adam (contrastive_estimation_training.py:97-162,
+scalogram_model.py:372-529, audio_model.py:80-213).  ``bench.py`` times it on the host cores as the
+``cpu_baseline`` / ``--impl reference`` arm (kind "port": /root/reference does not exist on the GPU box)
+and ``__graft_entry__.smoke()`` uses it as the checker.  Never imported by the product.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import cpc_oracle as O
+
+
+def block_7(i, o, k1=(3, 3), k2=(3, 3), **kw):
+    d = {'in_channels': i, 'hidden_channels': None, 'out_channels': o, 'kernel_size_1': k1, 'kernel_size_2': k2,
+         'top_padding_1': None, 'top_padding_2': None, 'padding_1': 0, 'padding_2': 0, 'stride_1': 1, 'stride_2': 1,
+         'pooling_1': 1, 'pooling_2': 1, 'bias': True, 'separable': False, 'residual': True, 'batch_norm': False,
+         'ceil_pooling': False}
+    d.update(kw)
+    return d
+
+
+def arch7_blocks(in_channels=2):
+    """scalogram_resnet_architecture_7 as imported (configs/scalogram_resnet_configs.py:215-257)."""
+    return [block_7(in_channels, 32, k2=(64, 1), top_padding_2=63, stride_1=2, batch_norm=True),
+            block_7(32, 128, k2=(30, 1), stride_1=2, batch_norm=True),
+            block_7(128, 256, k2=(15, 1), stride_1=2, batch_norm=True),
+            block_7(256, 512, k1=(2, 2), k2=(1, 1))]
+
+
+class OracleBlock(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        hid = cfg['hidden_channels'] or cfg['out_channels']
+        self.conv_a = nn.Conv2d(cfg['in_channels'], hid, cfg['kernel_size_1'], bias=cfg['bias'])
+        self.conv_b = nn.Conv2d(hid, cfg['out_channels'], cfg['kernel_size_2'], bias=cfg['bias'])
+        if cfg['batch_norm']:
+            self.bn_a, self.bn_b = nn.BatchNorm2d(hid), nn.BatchNorm2d(cfg['out_channels'])
+        if cfg['residual'] and cfg['in_channels'] != cfg['out_channels']:
+            self.res = nn.Conv2d(cfg['in_channels'], cfg['out_channels'], 1, bias=False)
+
+    def params(self):
+        p = {'conv_a.weight': self.conv_a.weight, 'conv_a.bias': self.conv_a.bias,
+             'conv_b.weight': self.conv_b.weight, 'conv_b.bias': self.conv_b.bias}
+        if self.cfg['batch_norm']:
+            for n in ('bn_a', 'bn_b'):
+                m = getattr(self, n)
+                p[n + '.weight'], p[n + '.bias'] = m.weight, m.bias
+        if hasattr(self, 'res'):
+            p['res.weight'] = self.res.weight
+        return p
+
+    def forward(self, x):
+        return O.encoder_block_forward(x, self.cfg, self.params(), training=True)
+
+
+class OracleConvAr(nn.Module):
+    """ConvolutionalArModel (audio_model.py:80-161) with the residual add written out of place."""
+
+    def __init__(self, kernel_sizes, channels, pooling, batch_norm=True, residual=True):
+        super().__init__()
+        self.pooling, self.residual = pooling, residual
+        self.convs = nn.ModuleList(nn.Conv1d(channels[i], channels[i + 1], k) for i, k in enumerate(kernel_sizes))
+        self.bns = nn.ModuleList(nn.BatchNorm1d(channels[i + 1]) if batch_norm else nn.Identity()
+                                 for i in range(len(kernel_sizes)))
+        self.skips = nn.ModuleList(nn.Conv1d(channels[i], channels[i + 1], 1) if channels[i] != channels[i + 1]
+                                   else nn.Identity() for i in range(len(kernel_sizes)))
+
+    def forward(self, x):
+        for conv, bn, skip, pool in zip(self.convs, self.bns, self.skips, self.pooling):
+            main = F.max_pool1d(x, pool, ceil_mode=True) if pool > 1 else x
+            main = F.relu(bn(conv(main)))
+            if self.residual:
+                r = F.max_pool1d(x, pool, ceil_mode=True) if pool > 1 else x
+                main = main + skip(r)[:, :, -main.shape[2]:]
+            x = main
+        return x[:, :, -1]
+
+
+class OracleE24(nn.Module):
+    """experiments['e24']: CQT(+phase) -> arch 7 -> conv AR arch 3 -> Linear(256 -> 16*512)."""
+
+    def __init__(self, visible_steps=60, prediction_steps=16):
+        super().__init__()
+        self.plan = O.CqtPlan(16000, 30, 256, 32, 0.5, 128)
+        self.blocks = nn.ModuleList(OracleBlock(c) for c in arch7_blocks(2))
+        self.ar = OracleConvAr([5] * 6, [512, 512, 512, 256, 256, 256, 256], [1, 1, 2, 1, 2, 1])
+        self.v, self.k, self.e = visible_steps, prediction_steps, 512
+        self.predict = nn.Linear(256, self.k * self.e, bias=False)
+        self.item_length = 19200 + (visible_steps + prediction_steps) * 1024
+
+    def forward(self, audio):
+        with torch.no_grad():
+            x = O.preprocess(audio.unsqueeze(1), self.plan, phase=True)
+        x = x.requires_grad_(True)
+        for i, b in enumerate(self.blocks):
+            x = b(x)
+            if i < len(self.blocks) - 1:
+                x = F.relu(x)
+        z = x[:, :, 0, :]
+        targets, vis = O.predictive_split(z, self.v, self.k)
+        pred = self.predict(self.ar(vis)).view(-1, self.k, self.e)
+        return pred, targets
+
+
+def train_steps(model, audio_batches, lr=1e-4, all_steps=True, kind='linear', regularization=0.0):
+    """Runs one optimiser step per batch; returns the list of loss values."""
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    losses = []
+    model.train()
+    for audio in audio_batches:
+        pred, targets = model(audio)
+        loss, _ = O.infonce_loss(pred, targets, all_steps, kind, regularization)
+        model.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    return losses

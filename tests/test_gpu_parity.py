@@ -1,0 +1,354 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the Python host mirror -> ctypes -> C-ABI,
+against (a) the golden vectors the unmodified reference produced and (b) the CPU oracle on fresh seeded
+inputs.  Tolerances follow the north star: 1e-3 relative (norm-wise) in fp32 mode for CQT magnitudes,
+encoder outputs, InfoNCE loss and gradients; sampler indices are covered bit-exactly on CPU."""
+import json
+import math
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cpc_oracle as O
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # north-star fp32 tolerance
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def cpc(built_lib):
+    import cpc_b200
+    assert cpc_b200._lib.load().cpc_runtime_check() == 0, "device is not a B200 (sm_100)"
+    return cpc_b200
+
+
+def phase_err_fraction(a, b, scale, tol=1e-3):
+    """fraction of phase-difference entries whose circular distance exceeds tol (scale: (F,) per-bin factor)."""
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    s = torch.as_tensor(scale, dtype=torch.float64).view(1, -1, 1)
+    d = (a - b) / s
+    d = torch.remainder(d + math.pi, 2 * math.pi) - math.pi
+    return float((d.abs() > tol).double().mean())
+
+
+# ---------------------------------------------------------------------------------------------------
+# CQT front end
+# ---------------------------------------------------------------------------------------------------
+
+def test_cqt_complex_and_scalograms_match_reference_golden(cpc):
+    g = load_golden("cqt.npz")
+    x = torch.from_numpy(g["x"]).to(DEV)
+    cqt = cpc.CQT(sr=16000, fmin=30, n_bins=256, bins_per_octave=32, filter_scale=0.5, hop_length=128).to(DEV)
+    z = cqt(x)
+    assert tuple(z.shape) == g["complex"].shape
+    assert rel_err(z, g["complex"]) < TOL
+    d = dict(cpc.cqt_default_dict)
+    y = cpc.PreprocessingModule(d, phase=False).to(DEV)(x)
+    assert y.grad_fn is None and not y.requires_grad            # must be an autograd leaf (trainer sets requires_grad)
+    assert rel_err(y, g["logpow"]) < TOL                        # includes exact -inf on the silent stretch
+    pre = cpc.PreprocessingModule(d, phase=True).to(DEV)
+    y = pre(x)
+    assert tuple(y.shape) == g["logpow_phase"].shape
+    assert rel_err(y[:, 0], g["logpow_phase"][:, 0]) < TOL
+    scale = pre.phase_diff.scaling.reshape(-1).cpu()
+    assert phase_err_fraction(y[:, 1], g["logpow_phase"][:, 1], scale) < 2e-3
+    y = cpc.PreprocessingModule(d, phase=False, offset_zero=True, output_power=2., pooling=[1, 2], scaling=10.).to(DEV)(x)
+    assert rel_err(y, g["offset_pool_power"]) < TOL
+    y = cpc.PreprocessingModule(d, phase=True, offset_zero=True, pooling=[1, 2]).to(DEV)(x)
+    assert tuple(y.shape) == g["phase_offset_pool"].shape
+    assert rel_err(y[:, 0], g["phase_offset_pool"][:, 0]) < TOL
+    cqt2 = cpc.CQT(sr=8000, fmin=55, n_bins=120, bins_per_octave=24, filter_scale=1., hop_length=64).to(DEV)
+    assert rel_err(cqt2(torch.from_numpy(g["x2"]).to(DEV)), g["complex2"]) < TOL
+
+
+def test_cqt_matches_oracle_on_fresh_input_and_ragged_lengths(cpc):
+    plan = O.CqtPlan(16000, 30, 256, 32, 0.5, 128)
+    cqt = cpc.CQT(filter_scale=0.5).to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    for b, extra in [(1, 0), (3, 127), (2, 128 * 3 + 5)]:       # T = 1 (minimum), partial hop, several frames
+        x = 0.1 * torch.randn(b, 1, 16384 + 1 + extra, generator=gen)
+        want = O.cqt_forward(x, plan)
+        got = cqt(x.to(DEV))
+        assert tuple(got.shape) == tuple(want.shape)
+        assert rel_err(got, want) < TOL
+    with pytest.raises(ValueError):
+        cqt(torch.zeros(1, 1, 16384, device=DEV))               # one sample short of a frame
+
+
+def test_cqt_full_size_properties(cpc):
+    """BASELINE config-2 size (B=64, L=97024): linearity and hop-shift equivariance."""
+    pre = cpc.CQT(filter_scale=0.5).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    x = 0.1 * torch.randn(64, 1, 97024, generator=gen, device=DEV)
+    z = pre(x)
+    assert tuple(z.shape) == (64, 256, 630, 2)
+    assert rel_err(pre(2.5 * x), 2.5 * z) < 1e-5
+    shifted = pre(x[:, :, 128:].contiguous())
+    assert rel_err(shifted, z[:, :, 1:]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------------
+
+CONV_CASES = [
+    # b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, top
+    (2, 1, 1, 200, 8, 1, 10, 1, 5, 0, 0, 0),        # AudioEncoder layer 0 shape (C_in = 1)
+    (3, 24, 1, 61, 40, 1, 8, 1, 4, 0, 0, 0),        # strided conv1d
+    (2, 2, 40, 37, 8, 3, 3, 2, 2, 0, 0, 0),         # first scalogram conv (C_in = 2, stride 2)
+    (2, 8, 19, 18, 8, 9, 1, 1, 1, 0, 0, 8),         # tall pitch conv with top-only zero padding
+    (2, 8, 19, 18, 16, 3, 3, 2, 2, 1, 1, 0),        # symmetric padding + stride
+    (1, 16, 5, 9, 24, 2, 2, 1, 1, 0, 0, 0),
+    (2, 70, 3, 7, 130, 1, 1, 1, 1, 2, 2, 0),        # 1x1 residual conv with padding; ragged channel counts
+    (1, 3, 6, 6, 5, 6, 6, 1, 1, 0, 0, 0),           # output 1x1
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_forward_backward_match_oracle(cpc, case):
+    b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, top = case
+    gen = torch.Generator().manual_seed(hash(case) & 0xffff)
+    x = torch.randn(b, cin, h, w, generator=gen)
+    wt = torch.randn(cout, cin, kh, kw, generator=gen) / math.sqrt(cin * kh * kw)
+    bias = torch.randn(cout, generator=gen)
+    xr, wr, br = (t.clone().double().requires_grad_(True) for t in (x, wt, bias))
+    want = F.conv2d(F.pad(xr, (0, 0, top, 0)), wr, br, stride=(sh, sw), padding=(ph, pw))
+    gy = torch.randn(want.shape, generator=gen)
+    (want * gy.double()).sum().backward()
+    xg, wg, bg = (t.clone().to(DEV).requires_grad_(True) for t in (x, wt, bias))
+    got = cpc.ops.conv2d(xg, wg, bg, (sh, sw), (ph, pw), extra_top=top)
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel_err(got, want) < TOL
+    (got * gy.to(DEV)).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < TOL
+    assert rel_err(wg.grad, wr.grad) < TOL
+    assert rel_err(bg.grad, br.grad) < TOL
+    # fused ReLU epilogue + no-bias variant
+    got = cpc.ops.conv2d(xg.detach(), wg.detach(), None, (sh, sw), (ph, pw), extra_top=top, relu=True)
+    want = F.relu(F.conv2d(F.pad(x.double(), (0, 0, top, 0)), wt.double(), None, stride=(sh, sw), padding=(ph, pw)))
+    assert rel_err(got, want) < TOL
+
+
+def test_audio_encoder_matches_reference_golden(cpc):
+    g = load_golden("audio_encoder.npz")
+    enc = cpc.AudioEncoder({'strides': [5, 4, 2, 2, 2], 'kernel_sizes': [10, 8, 4, 4, 4],
+                            'channel_count': [24, 32, 40, 32, 48], 'bias': True})
+    enc.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("p.")})
+    enc.to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    y = enc(x)
+    assert rel_err(y, g["y"]) < TOL
+    (y * torch.from_numpy(g["gy"]).to(DEV)).sum().backward()
+    assert rel_err(x.grad, g["gx"]) < TOL
+    for n, p in enc.named_parameters():
+        assert rel_err(p.grad, g["g." + n]) < TOL, n
+    # known answers, tests/test_audioEncoder.py:19-48 of the reference
+    enc2 = cpc.AudioEncoder({'strides': [5, 4, 2, 2, 2], 'kernel_sizes': [10, 8, 4, 4, 4],
+                             'channel_count': [32] * 5, 'bias': True}).to(DEV)
+    assert list(enc2(torch.zeros(7, 1, 4800, device=DEV)).shape) == [7, 32, 28]
+    with torch.no_grad():
+        for p in enc2.parameters():
+            p.fill_(0.1)
+        imp = torch.zeros(1, 1, 465 + 160, device=DEV)
+        base = enc2(imp)[0, 0, 0].item()
+        imp[0, 0, 464] = 1.0
+        assert enc2(imp)[0, 0, 0].item() != base            # last sample of the receptive field reaches out[0]
+        imp.zero_()
+        imp[0, 0, 465] = 1.0
+        assert enc2(imp)[0, 0, 0].item() == base            # the next one does not
+
+
+def small_resnet_cfg():
+    from test_oracle_golden import small_resnet_blocks
+    blocks = small_resnet_blocks()
+    blocks[0]['in_channels'] = 1           # the encoder itself sets 2 when phase=True, as in the reference
+    return {'phase': True, 'blocks': blocks, 'activation_register': None}
+
+
+def test_residual_encoder_matches_reference_golden(cpc):
+    g = load_golden("resnet_encoder.npz")
+    enc = cpc.ScalogramResidualEncoder(small_resnet_cfg())
+    sd = {k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("p.")}
+    assert set(sd) == set(enc.state_dict()), set(sd) ^ set(enc.state_dict())
+    # the golden state holds BN running stats AFTER the forward; reset them to the initial values
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = torch.zeros_like(sd[k])
+        if k.endswith("running_var"):
+            sd[k] = torch.ones_like(sd[k])
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros_like(sd[k])
+    enc.load_state_dict(sd)
+    enc.to(DEV).train()
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    y = enc(x)
+    assert tuple(y.shape) == g["y"].shape
+    assert rel_err(y, g["y"]) < TOL
+    (y * torch.from_numpy(g["gy"]).to(DEV)).sum().backward()
+    assert rel_err(x.grad, g["gx"]) < TOL
+    for n, p in enc.named_parameters():
+        assert rel_err(p.grad, g["g." + n]) < 2 * TOL, n
+    for k, v in enc.state_dict().items():                      # BN running statistics after one step
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel_err(v, g["p." + k]) < TOL, k
+
+
+# ---------------------------------------------------------------------------------------------------
+# InfoNCE
+# ---------------------------------------------------------------------------------------------------
+
+def test_infonce_matches_reference_trainer_golden(cpc):
+    g = load_golden("infonce.npz")
+    for c in json.loads(str(g["cases"])):
+        t = c["tag"]
+        pred = torch.from_numpy(g[t + ".pred"]).to(DEV).requires_grad_(True)
+        tgt = torch.from_numpy(g[t + ".tgt"]).to(DEV).requires_grad_(True)
+        loss, mx, _, _ = cpc.ops.infonce(pred, tgt, c["all_steps"], c["kind"], c["reg"])
+        loss.backward()
+        assert abs(loss.item() - float(g[t + ".loss"])) < TOL * max(1.0, abs(float(g[t + ".loss"]))), c
+        assert abs(mx.item() - float(g[t + ".max"])) < TOL * max(1.0, abs(float(g[t + ".max"]))), c
+        assert rel_err(pred.grad, g[t + ".dpred"]) < TOL, c
+        assert rel_err(tgt.grad, g[t + ".dtgt"]) < TOL, c
+
+
+@pytest.mark.parametrize("b,k,e", [(64, 16, 512), (8, 12, 512), (33, 5, 100), (70, 1, 64)])
+@pytest.mark.parametrize("all_steps", [False, True])
+def test_infonce_matches_oracle_native_sizes_and_strided_targets(cpc, b, k, e, all_steps):
+    gen = torch.Generator().manual_seed(b * 1000 + k)
+    pred = torch.randn(b, k, e, generator=gen) / math.sqrt(e)
+    z = torch.randn(b, e, k + 7, generator=gen)                 # targets = strided view z[:, :, -k:] (audio_model.py:197)
+    for kind, reg in (("linear", 0.0), ("softplus", 1.0), ("linear", 0.01)):
+        want_loss, want_max, want_dp, want_dz = O.infonce_with_grads(pred, z[:, :, -k:], all_steps, kind, reg)
+        pg = pred.clone().to(DEV).requires_grad_(True)
+        zg = z.clone().to(DEV).requires_grad_(True)
+        loss, mx, loss0, mean_s = cpc.ops.infonce(pg, zg[:, :, -k:], all_steps, kind, reg)
+        (3.0 * loss).backward()                                  # non-unit upstream gradient
+        assert abs(loss.item() - float(want_loss)) < TOL * max(1.0, abs(float(want_loss)))
+        assert abs(mx.item() - float(want_max)) < TOL * max(1.0, abs(float(want_max)))
+        assert rel_err(pg.grad, 3.0 * want_dp) < TOL
+        assert rel_err(zg.grad[:, :, -k:], 3.0 * want_dz) < TOL
+        assert float(zg.grad[:, :, :-k].abs().max()) == 0.0
+        if reg == 0.0:
+            assert abs(loss0.item() - loss.item()) < 1e-6
+
+
+def test_infonce_full_size_property(cpc):
+    """Sweep corner the reference cannot materialise (N = 4096 candidates, K = 8): loss of a perfectly
+    predictable batch -> ~0 and of an uninformative one -> log N."""
+    b, k, e = 4096, 8, 128
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    z = torch.randn(b, e, k, generator=gen, device=DEV)
+    zn = z / z.norm(dim=1, keepdim=True)
+    pred = 40.0 * zn.permute(0, 2, 1).contiguous()
+    loss, _, _, _ = cpc.ops.infonce(pred, zn, False, "linear", 0.0)
+    assert loss.item() < 1e-3
+    loss, _, _, _ = cpc.ops.infonce(torch.zeros_like(pred), zn, False, "linear", 0.0)
+    assert abs(loss.item() - math.log(b)) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole training steps against the reference's own train()
+# ---------------------------------------------------------------------------------------------------
+
+def _replay_trainer(cpc, g, model, pre, seed, steps=2, **kw):
+    lr, bs = float(g["lr"]), int(g["batch_size"])
+    sd0 = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("s0.")}
+    model.load_state_dict(sd0)
+    model.to(DEV)
+    if pre is not None:
+        pre.to(DEV)
+    from cpc_b200.sampler import SyntheticAudioDataset
+
+    class Items(torch.utils.data.Dataset):
+        def __init__(self, items):
+            self.items = items
+
+        def __len__(self):
+            return self.items.shape[0]
+
+        def __getitem__(self, i):
+            return self.items[i]
+
+        def get_example_count_per_file(self):
+            return [len(self)]
+
+    class Log:
+        def __init__(self):
+            self.l, self.s = [], []
+            outer = self
+
+            class M:
+                def __init__(self, sink):
+                    self.sink = sink
+
+                def update(self, v, n=1):
+                    self.sink.append(v)
+
+            self.loss_meter, self.score_meter = M(self.l), M(self.s)
+
+        def log(self, step):
+            pass
+
+    log = Log()
+    trainer = cpc.ContrastiveEstimationTrainer(model=model, dataset=Items(torch.from_numpy(g["items"])), logger=log,
+                                               device=DEV, optimizer=torch.optim.SGD, preprocessing=pre,
+                                               verbose=False, **kw)
+    random.seed(seed)
+    snaps = []
+    for s in range(steps):
+        trainer.train(batch_size=bs, epochs=1, lr=lr, continue_training_at_step=s, num_workers=0, max_steps=s + 1)
+        snaps.append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    return log, snaps, lr
+
+
+def _check_against_snapshots(g, log, snaps, lr, tol):
+    for s in range(len(snaps)):
+        assert abs(log.l[s] - g["losses"][s]) < tol * max(1.0, abs(g["losses"][s])), (s, log.l, g["losses"])
+        assert abs(log.s[s] - g["max_scores"][s]) < tol * max(1.0, abs(g["max_scores"][s]))
+    # step-1 gradients: (before - after) / lr for every float parameter, reference vs ours
+    for k, after in snaps[0].items():
+        if not after.dtype.is_floating_point or k.endswith("running_mean") or k.endswith("running_var"):
+            continue
+        before = torch.from_numpy(g["s0." + k])
+        ref_grad = (before - torch.from_numpy(g["s1." + k])) / lr
+        my_grad = (before - after) / lr
+        if float(ref_grad.norm()) < 1e-7:
+            assert float(my_grad.norm()) < 1e-5, k
+        else:
+            assert rel_err(my_grad, ref_grad) < tol, k
+    for k, after in snaps[-1].items():
+        if after.dtype.is_floating_point:
+            assert rel_err(after, g["s%d.%s" % (len(snaps), k)]) < tol, k
+
+
+def test_training_steps_raw_wave_match_reference_train(cpc):
+    g = load_golden("trainer_raw.npz")
+    enc = cpc.AudioEncoder({'strides': [5, 4, 2, 2, 2], 'kernel_sizes': [10, 8, 4, 4, 4],
+                            'channel_count': [16, 24, 24, 24, 32], 'bias': True})
+    model = cpc.AudioPredictiveCodingModel(enc, cpc.AudioGRUModel(32, 16), enc_size=32, ar_size=16, visible_steps=9,
+                                           prediction_steps=4)
+    log, snaps, lr = _replay_trainer(cpc, g, model, None, seed=0, regularization=1., score_over_all_timesteps=False,
+                                     score_function=cpc.softplus_score_function, prediction_steps=4)
+    _check_against_snapshots(g, log, snaps, lr, 2 * TOL)
+
+
+def test_training_steps_cqt_resnet_match_reference_train(cpc):
+    g = load_golden("trainer_cqt.npz")
+    cfg = small_resnet_cfg()
+    cfg['blocks'][2] = dict(cfg['blocks'][2], kernel_size_1=(30, 2), pooling_1=1, ceil_pooling=False)
+    cfg['blocks'][1] = dict(cfg['blocks'][1], kernel_size_2=(35, 1))
+    pre = cpc.PreprocessingModule(dict(cpc.cqt_default_dict), phase=True)
+    enc = cpc.ScalogramResidualEncoder(cfg, preprocessing_module=pre)
+    ar = cpc.ConvolutionalArModel({'kernel_sizes': [3, 3], 'channel_count': [24, 16, 16], 'stride': [1, 1],
+                                   'pooling': [1, 2], 'bias': True, 'batch_norm': True, 'residual': False,
+                                   'activation_register': None})
+    model = cpc.AudioPredictiveCodingModel(enc, ar, enc_size=24, ar_size=16, visible_steps=10, prediction_steps=3)
+    assert model.item_length == int(g["item_length"])
+    log, snaps, lr = _replay_trainer(cpc, g, model, pre, seed=3, regularization=0.25, score_over_all_timesteps=True,
+                                     score_function=cpc.linear_score_function, prediction_steps=3)
+    _check_against_snapshots(g, log, snaps, lr, 5 * TOL)

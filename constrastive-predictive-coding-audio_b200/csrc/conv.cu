@@ -33,9 +33,8 @@ static int validate(const cpc_conv_params* p) {
         p->w_out <= 0 || p->kh <= 0 || p->kw <= 0 || p->stride_h <= 0 || p->stride_w <= 0 || p->pad_top < 0 ||
         p->pad_left < 0)
         return CPC_ERR_BAD_SHAPE;
-    // every tap of every output must start inside the (virtually padded) input, and sizes must fit int32 indexing
-    if ((int64_t)(p->h_out - 1) * p->stride_h - p->pad_top >= p->h_in) return CPC_ERR_BAD_SHAPE;
-    if ((int64_t)(p->w_out - 1) * p->stride_w - p->pad_left >= p->w_in) return CPC_ERR_BAD_SHAPE;
+    // bottom / right zero padding is implied by (h_out, w_out) and may be arbitrarily large; sizes must fit
+    // int32 indexing
     const int64_t lim = (1ll << 31) - 1;
     if ((int64_t)p->batch * p->h_out * p->w_out > lim || (int64_t)p->batch * p->h_in * p->w_in > lim ||
         (int64_t)p->c_in * p->kh * p->kw > lim || (int64_t)p->c_out * p->kh * p->kw > lim)

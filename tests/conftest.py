@@ -56,3 +56,27 @@ def rel_err(a, b):
         assert bool((a[~fin] == b[~fin]).all()), "non-finite values differ"
         a, b = a[fin], b[fin]
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def grad_err(mine, ref, floor=1e-4):
+    """Relative gradient error with an absolute floor: parameters whose true gradient is zero (a conv bias
+    feeding a train-mode BatchNorm) carry only rounding noise in both implementations."""
+    import torch
+    a = torch.as_tensor(mine).detach().to(torch.float64).cpu()
+    b = torch.as_tensor(ref).detach().to(torch.float64).cpu()
+    return float((a - b).norm() / max(float(b.norm()), floor))
+
+
+def bn_shadowed_biases(keys):
+    """Conv biases that feed a train-mode BatchNorm directly: their true gradient is exactly zero, so both
+    implementations only hold rounding noise there and a relative comparison is meaningless."""
+    keys = set(keys)
+    out = set()
+    for k in keys:
+        if not k.endswith(".bias"):
+            continue
+        head, idx = k[:-len(".bias")].rsplit(".", 1)
+        if idx.isdigit() and ("%s.%d.running_mean" % (head, int(idx) + 1)) in keys and \
+                ("%s.%s.running_mean" % (head, idx)) not in keys:
+            out.add(k)
+    return out

@@ -36,7 +36,7 @@ def test_abi_rejects_bad_arguments_before_touching_the_device(built_lib):
     assert lib.cpc_conv_fwd(None, None, None, None, ctypes.byref(p), None, 0, None) == -1      # all-zero shape
     p.batch = p.c_in = p.h_in = p.w_in = p.c_out = p.h_out = p.w_out = p.kh = p.kw = p.stride_h = p.stride_w = 1
     assert lib.cpc_conv_fwd(None, None, None, None, ctypes.byref(p), None, 0, None) == -7      # null pointers
-    p.h_out = 5                                                                                 # outputs outside input
+    p.stride_h = 0                                                                              # bad stride
     assert lib.cpc_conv_fwd(None, None, None, None, ctypes.byref(p), None, 0, None) == -1
     q = _lib.InfoNceParams()
     q.batch, q.steps, q.enc = 4, 100, 8

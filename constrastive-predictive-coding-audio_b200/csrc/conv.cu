@@ -7,7 +7,22 @@
 // channel counts >= 16 lives in conv_umma.cu and is selected by the dispatcher in this file.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace cpc {
+
+// conv_umma.cu
+size_t umma_conv_workspace(const cpc_conv_params* p, int which);
+bool umma_conv_eligible(const cpc_conv_params* p, int which);
+int umma_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
+                     void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+// Debug switch (tests use it to A/B the two kernel families on one shape): CPC_FORCE_CUDA_CORE_CONV=1
+static bool tensor_core_path(const cpc_conv_params* p, int which) {
+    const char* e = std::getenv("CPC_FORCE_CUDA_CORE_CONV");
+    if (e && e[0] == '1') return false;
+    return umma_conv_eligible(p, which);
+}
 
 struct ConvGeom {
     int B, Cin, H, W, Cout, OH, OW, kh, kw, sh, sw, pt, pl;
@@ -216,17 +231,19 @@ __global__ void __launch_bounds__(256) conv_dbias_kernel(const float* __restrict
 using namespace cpc;
 
 extern "C" size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which) {
-    (void)p; (void)which;
+    if (validate(p) != CPC_OK) return 0;
+    if ((which == 0 || which == 1) && tensor_core_path(p, which)) return umma_conv_workspace(p, which);
     return 0;
 }
 
 extern "C" int cpc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const cpc_conv_params* p,
                             void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     int st = validate(p);
     if (st != CPC_OK) return st;
     if (!x || !w || !y) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
+    if (tensor_core_path(p, 0))
+        return umma_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream);
     ConvGeom g = make_geom(p);
     const int M = g.B * g.ohow, N = g.Cout, K = g.Cin * g.khkw;
     FwdA la{x, g, M, K};
@@ -240,11 +257,12 @@ extern "C" int cpc_conv_fwd(const float* x, const float* w, const float* bias, f
 
 extern "C" int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_params* p, void* workspace,
                               size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     int st = validate(p);
     if (st != CPC_OK) return st;
     if (!dy || !w || !dx) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
+    if (tensor_core_path(p, 1))
+        return umma_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream);
     ConvGeom g = make_geom(p);
     const int M = g.B * g.hw, N = g.Cin, K = g.Cout * g.khkw;
     DgradA la{dy, g, M, K};

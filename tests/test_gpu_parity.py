@@ -134,6 +134,43 @@ def test_conv_forward_backward_match_oracle(cpc, case):
     assert rel_err(got, want) < TOL
 
 
+UMMA_CASES = [
+    # b, cin, h, w, cout, kh, kw, ph, pw, top   (stride 1: the tcgen05 implicit-GEMM path)
+    (2, 32, 40, 150, 32, 9, 1, 0, 0, 8),          # tall pitch conv, top-only padding, C_in < 64 (taps share a K chunk)
+    (2, 128, 20, 70, 128, 5, 1, 0, 0, 0),         # C_in = 2 K chunks per tap
+    (1, 64, 9, 130, 256, 2, 2, 0, 0, 0),          # two N tiles, OW = 129 (three 64-pixel atoms per row)
+    (2, 16, 6, 40, 64, 3, 3, 1, 1, 0),            # symmetric padding, 4 taps per K chunk + phantom taps
+    (1, 256, 4, 33, 512, 1, 1, 0, 0, 0),          # 1x1, four N tiles
+    (3, 32, 1, 300, 96, 1, 5, 0, 0, 0),           # conv1d-shaped (h = 1)
+]
+
+
+@pytest.mark.parametrize("case", UMMA_CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_tensor_core_conv_matches_oracle(cpc, case, precision):
+    b, cin, h, w, cout, kh, kw, ph, pw, top = case
+    gen = torch.Generator().manual_seed(hash(case) & 0xffff)
+    x = torch.randn(b, cin, h, w, generator=gen)
+    wt = torch.randn(cout, cin, kh, kw, generator=gen) / math.sqrt(cin * kh * kw)
+    bias = torch.randn(cout, generator=gen)
+    xr, wr, br = (t.clone().double().requires_grad_(True) for t in (x, wt, bias))
+    want = F.conv2d(F.pad(xr, (0, 0, top, 0)), wr, br, padding=(ph, pw))
+    gy = torch.randn(want.shape, generator=gen)
+    (want * gy.double()).sum().backward()
+    xg, wg, bg = (t.clone().to(DEV).requires_grad_(True) for t in (x, wt, bias))
+    got = cpc.ops.conv2d(xg, wg, bg, (1, 1), (ph, pw), extra_top=top, precision=precision)
+    assert tuple(got.shape) == tuple(want.shape)
+    tol = 5e-5 if precision == "fp32" else 1e-2         # fp32 mode = 3x bf16 split, far inside the 1e-3 budget
+    assert rel_err(got, want) < tol
+    (got * gy.to(DEV)).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < tol
+    assert rel_err(wg.grad, wr.grad) < max(tol, TOL)
+    assert rel_err(bg.grad, br.grad) < TOL
+    got = cpc.ops.conv2d(xg.detach(), wg.detach(), None, (1, 1), (ph, pw), extra_top=top, relu=True, precision=precision)
+    want = F.relu(F.conv2d(F.pad(x.double(), (0, 0, top, 0)), wt.double(), None, padding=(ph, pw)))
+    assert rel_err(got, want) < tol
+
+
 def test_audio_encoder_matches_reference_golden(cpc):
     g = load_golden("audio_encoder.npz")
     enc = cpc.AudioEncoder({'strides': [5, 4, 2, 2, 2], 'kernel_sizes': [10, 8, 4, 4, 4],

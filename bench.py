@@ -242,7 +242,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": b * length * 4, "d2h_bytes_per_step": 8, "last_loss": last["v"][0]},
             "roofline": roofline,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "kernels": top[:8]}
+            "kernels": top[:24]}
     print(json.dumps(line))
 
 

@@ -92,7 +92,10 @@ class ContrastiveEstimationTrainer:
         batch = batch.unsqueeze(1)
         if self.preprocessing is not None:
             batch = self.preprocessing(batch)
-            batch.requires_grad = True            # the scalogram is an autograd leaf (:102)
+            # The reference marks the scalogram as requiring grad (:102) but only the gradient penalty ever
+            # reads that gradient; without the penalty the first layer's data gradient is dead work, so it is
+            # not requested here (identical losses and parameter gradients).
+            batch.requires_grad = bool(self.wasserstein_gradient_penalty)
         predicted_z, targets, _, _ = self.model(batch)
         kind = _FUSED_KINDS.get(self.score_function)
         if self.wasserstein_gradient_penalty:

@@ -17,11 +17,16 @@ bool umma_conv_eligible(const cpc_conv_params* p, int which);
 int umma_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
                      void* workspace, size_t workspace_bytes, cudaStream_t s);
 
+size_t umma_wgrad_workspace(const cpc_conv_params* p);
+bool umma_wgrad_eligible(const cpc_conv_params* p);
+int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
+                      size_t workspace_bytes, cudaStream_t s);
+
 // Debug switch (tests use it to A/B the two kernel families on one shape): CPC_FORCE_CUDA_CORE_CONV=1
 static bool tensor_core_path(const cpc_conv_params* p, int which) {
     const char* e = std::getenv("CPC_FORCE_CUDA_CORE_CONV");
     if (e && e[0] == '1') return false;
-    return umma_conv_eligible(p, which);
+    return which == 2 ? umma_wgrad_eligible(p) : umma_conv_eligible(p, which);
 }
 
 struct ConvGeom {
@@ -233,6 +238,7 @@ using namespace cpc;
 extern "C" size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which) {
     if (validate(p) != CPC_OK) return 0;
     if ((which == 0 || which == 1) && tensor_core_path(p, which)) return umma_conv_workspace(p, which);
+    if (which == 2 && tensor_core_path(p, 2)) return umma_wgrad_workspace(p);
     return 0;
 }
 
@@ -274,15 +280,31 @@ extern "C" int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const 
     return CPC_OK;
 }
 
+static int launch_dbias(const float* dy, float* dbias, const ConvGeom& g, cudaStream_t s) {
+    if (cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)g.Cout, s) != cudaSuccess) return CPC_ERR_CUDA;
+    long total = (long)g.B * g.ohow;
+    int sp = (int)((total + 256 * 8 - 1) / (256 * 8));
+    if (sp > 64) sp = 64;
+    if (sp < 1) sp = 1;
+    conv_dbias_kernel<<<dim3(g.Cout, sp), 256, 0, s>>>(dy, dbias, g.B, g.Cout, g.ohow);
+    CPC_LAUNCH_CHECK();
+    count_launch();
+    return CPC_OK;
+}
+
 extern "C" int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
                               void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     int st = validate(p);
     if (st != CPC_OK) return st;
     if (!x || !dy || !dw) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
     ConvGeom g = make_geom(p);
     cudaStream_t s = (cudaStream_t)stream;
+    if (tensor_core_path(p, 2)) {
+        st = umma_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s);
+        if (st != CPC_OK) return st;
+        return dbias ? launch_dbias(dy, dbias, g, s) : CPC_OK;
+    }
     const int M = g.Cout, N = g.Cin * g.khkw, K = g.B * g.ohow;
     if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)M * N, s) != cudaSuccess) return CPC_ERR_CUDA;
     const int tiles = ceil_div(M, TILE) * ceil_div(N, TILE);
@@ -298,15 +320,6 @@ extern "C" int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float*
     conv_wgrad_kernel<<<grid, TILE_THREADS, 0, s>>>(la, lb, dw, k_per_split);
     CPC_LAUNCH_CHECK();
     count_launch();
-    if (dbias) {
-        if (cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)g.Cout, s) != cudaSuccess) return CPC_ERR_CUDA;
-        long total = (long)g.B * g.ohow;
-        int sp = (int)((total + 256 * 8 - 1) / (256 * 8));
-        if (sp > 64) sp = 64;
-        if (sp < 1) sp = 1;
-        conv_dbias_kernel<<<dim3(g.Cout, sp), 256, 0, s>>>(dy, dbias, g.B, g.Cout, g.ohow);
-        CPC_LAUNCH_CHECK();
-        count_launch();
-    }
+    if (dbias) return launch_dbias(dy, dbias, g, s);
     return CPC_OK;
 }

@@ -1,4 +1,4 @@
-// Stride-1 convolution forward / data-gradient as an implicit GEMM on the 5th-gen tensor cores.
+// Strided convolution forward / data-gradient / weight-gradient as implicit GEMMs on the 5th-gen tensor cores.
 //
 //   D[pixel, n] = sum_{tap, c} A[pixel + tap, c] * Wp[n, (tap, c)]
 //
@@ -13,8 +13,13 @@
 // * Persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (one elected lane),
 //   warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> bias/ReLU -> coalesced NCHW stores).
 //   Two TMEM accumulator buffers let the epilogue of tile t overlap the MMAs of tile t+1.
-// * The data gradient of a stride-1 conv is the same kernel run on dy with flipped taps and swapped
-//   channel roles (weights re-packed accordingly).
+// * A TMA box must start on a 16-byte boundary of the innermost (w) dimension, so everything horizontal
+//   -- tap offset j, stride s_w, left padding -- is baked into "replicas" by the packing pass:
+//   replica_r[.., w'] = src[.., w_mul*w' + rep_mul*r + w_off].  Vertical taps/strides are plain TMA row
+//   coordinates  h = h_mul*oh + tap_h_mul*i + h_off.
+// * The data gradient runs the same kernel on dy with swapped channel roles, once per output parity class
+//   (h+pt mod s_h, w+pl mod s_w): inside a class it is a stride-1 correlation with the sub-kernel
+//   w[:, :, rh + s_h*i', rw + s_w*j'], and the epilogue scatters to h = s_h*a + rh - pt.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -28,11 +33,12 @@ constexpr int A_PLANE_BYTES = 2 * KCHUNK * 128;   // two 64-pixel atoms x 64 k-r
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct UmmaConv {
-    int n_atoms, OH, OW, AW;             // output geometry (atoms = 64-pixel runs along w)
+    int n_atoms, PH, PW, AW;             // GEMM pixel domain (PH x PW per item; atoms = 64-pixel runs along w)
     int n_rows_out;                      // output channels (GEMM N total)
     int n_tile, n_ntiles;
-    int kh, kw, ntaps, tpc, cin_eff, cin_chunks, n_chunks;
-    int pt, pl;
+    int th, tw, ntaps, tpc, cin_eff, cin_chunks, n_chunks;   // tap grid th x tw
+    int h_mul, tap_h_mul, h_off;         // source row = h_mul*ph + tap_h_mul*i + h_off
+    int out_H, out_W, oh_mul, oh_off, ow_mul, ow_off;        // output pixel = (oh_mul*ph + oh_off, ow_mul*pw + ow_off)
     int planes;                          // 2 = fp32-faithful split, 1 = bf16
     int relu, stages;
     const float* bias;
@@ -40,29 +46,29 @@ struct UmmaConv {
 };
 
 // ---- packing kernels --------------------------------------------------------------------------------
-// fp32 (rows, W) -> bf16 (planes, nshift, rows, Wp); Wp % 8 == 0; one thread per 8 output columns.
-// Replica s holds x[.., w + s - pad_left] (zero outside [0, W)): the horizontal tap offset is baked in here
-// because a TMA box must start on a 16-byte boundary of the innermost dimension.
+// fp32 (rows, W) -> bf16 (planes, nrep, rows, Wp); Wp % 8 == 0; one thread per 8 output columns.
+// replica r, column w' holds src[w_mul*w' + rep_mul*r + w_off] (zero outside [0, W)).
 __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                        long rows, int W, int Wp, int planes, int nshift, int pad_left) {
+                                                        long rows, int W, int Wp, int planes, int nrep, int w_mul,
+                                                        int rep_mul, int w_off) {
     const int groups = Wp >> 3;
     const long total = rows * groups;
-    const long plane_stride = (long)nshift * rows * Wp;
+    const long plane_stride = (long)nrep * rows * Wp;
     for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
         const long row = g / groups;
         const int w0 = (int)(g - row * groups) << 3;
         const float* src = x + row * W;
-        for (int s = 0; s < nshift; ++s) {
+        for (int r = 0; r < nrep; ++r) {
             __align__(16) __nv_bfloat16 hi[8];
             __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int w = w0 + i + s - pad_left;
+                const int w = w_mul * (w0 + i) + rep_mul * r + w_off;
                 const float v = (w >= 0 && w < W) ? __ldg(src + w) : 0.f;
                 hi[i] = __float2bfloat16_rn(v);
                 lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
             }
-            const long o = ((long)s * rows + row) * Wp + w0;
+            const long o = ((long)r * rows + row) * Wp + w0;
             *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
             if (planes == 2) *reinterpret_cast<uint4*>(out + plane_stride + o) = *reinterpret_cast<const uint4*>(lo);
         }
@@ -70,14 +76,15 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
 }
 
 // weights (Cout, Cin, kh, kw) fp32 -> bf16 (planes, n_chunks, Nrows, 64), K-major rows of one K chunk.
-// transpose_flip = 0: rows n = co, k = (tap, ci)              (forward)
-//                = 1: rows n = ci, k = (flipped tap, co)      (data gradient)
+// GEMM tap (i', j') of a (th x tw) tap grid reads source tap (i_off + i_mul*i', j_off + j_mul*j').
+// swap = 0: rows n = co, k channel = ci (forward);  swap = 1: rows n = ci, k channel = co (data gradient).
+struct TapMap { int th, tw, i_off, i_mul, j_off, j_mul, swap; };
+
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                          int Cout, int Cin, int kh, int kw, int n_rows, int k_ch,
-                                                          int cin_eff, int cin_chunks, int tpc, int n_chunks, int planes,
-                                                          int transpose_flip) {
+                                                          int Cin, int kh, int kw, int n_rows, int k_ch, int cin_eff,
+                                                          int cin_chunks, int tpc, int n_chunks, int planes, TapMap tm) {
     const long total = (long)n_chunks * n_rows * KCHUNK;
-    const int ntaps = kh * kw;
+    const int ntaps = tm.th * tm.tw;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int kk = (int)(idx % KCHUNK);
         const long t = idx / KCHUNK;
@@ -88,9 +95,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
         else                   { tap = chunk * tpc + kk / cin_eff; c = kk % cin_eff; }
         float v = 0.f;
         if (tap < ntaps && c < k_ch) {
-            int i = tap / kw, j = tap - i * kw;
-            if (transpose_flip) { i = kh - 1 - i; j = kw - 1 - j; v = __ldg(w + (((size_t)c * Cin + n) * kh + i) * kw + j); }
-            else                { v = __ldg(w + (((size_t)n * Cin + c) * kh + i) * kw + j); }
+            const int ti = tap / tm.tw, tj = tap - ti * tm.tw;
+            const int i = tm.i_off + tm.i_mul * ti, j = tm.j_off + tm.j_mul * tj;
+            const size_t co = tm.swap ? c : n, ci = tm.swap ? n : c;
+            v = __ldg(w + ((co * Cin + ci) * kh + i) * kw + j);
         }
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         out[idx] = hi;
@@ -140,8 +148,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                     const int atom = mtile * 2 + a;            // beyond n_atoms -> batch index OOB -> zero fill
                     const int row = atom / p.AW;
                     aw0[a] = (atom - row * p.AW) * ATOM;
-                    ab[a] = row / p.OH;
-                    aoh[a] = row - ab[a] * p.OH;
+                    ab[a] = row / p.PH;
+                    aoh[a] = (row - ab[a] * p.PH) * p.h_mul + p.h_off;
                 }
                 for (int q = 0; q < p.n_chunks; ++q) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -152,16 +160,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                         for (int a = 0; a < 2; ++a) {
                             if (p.cin_eff == KCHUNK) {
                                 const int tap = q / p.cin_chunks, c0 = (q - tap * p.cin_chunks) * KCHUNK;
-                                const int i = tap / p.kw, j = tap - i * p.kw;
+                                const int i = tap / p.tw, j = tap - i * p.tw;
                                 tma_load_5d(a_dst + a * (KCHUNK * 128), &tmap_a, &bars->full[stage], aw0[a],
-                                            aoh[a] + i - p.pt, c0, ab[a], pl * p.kw + j);
+                                            aoh[a] + i * p.tap_h_mul, c0, ab[a], pl * p.tw + j);
                             } else {
                                 for (int t = 0; t < p.tpc; ++t) {
                                     int tap = q * p.tpc + t;
                                     if (tap >= p.ntaps) tap = 0;        // phantom tap: its packed weights are zero
-                                    const int i = tap / p.kw, j = tap - i * p.kw;
+                                    const int i = tap / p.tw, j = tap - i * p.tw;
                                     tma_load_5d(a_dst + a * (KCHUNK * 128) + t * p.cin_eff * 128, &tmap_a, &bars->full[stage],
-                                                aw0[a], aoh[a] + i - p.pt, 0, ab[a], pl * p.kw + j);
+                                                aw0[a], aoh[a] + i * p.tap_h_mul, 0, ab[a], pl * p.tw + j);
                                 }
                             }
                         }
@@ -214,14 +222,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
             const int mtile = tile / p.n_ntiles, ntile = tile - mtile * p.n_ntiles;
             const int atom = mtile * 2 + (r >> 6);
             const int row = atom / p.AW;
-            const int ow = (atom - row * p.AW) * ATOM + (r & 63);
-            const int b = row / p.OH, oh = row - b * p.OH;
-            const bool valid = atom < p.n_atoms && ow < p.OW;
+            const int pw = (atom - row * p.AW) * ATOM + (r & 63);
+            const int b = row / p.PH;
+            const int oh = (row - b * p.PH) * p.oh_mul + p.oh_off, ow = pw * p.ow_mul + p.ow_off;
+            const bool valid = atom < p.n_atoms && pw < p.PW && oh < p.out_H && ow < p.out_W;
             mbar_wait(&bars->acc_full[buf], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 256;
-            float* ybase = p.y + ((size_t)b * p.n_rows_out * p.OH + oh) * p.OW + ow;
-            const size_t chan_stride = (size_t)p.OH * p.OW;
+            float* ybase = p.y + ((size_t)b * p.n_rows_out * p.out_H + oh) * p.out_W + ow;
+            const size_t chan_stride = (size_t)p.out_H * p.out_W;
             for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
@@ -249,113 +258,430 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
+// One launch of umma_conv_kernel: out[b, n, (oh,ow)(ph,pw)] = sum_{taps, c} src[b, c, row(ph,i), col(pw,j)] * w
+struct ConvProblem {
+    const float* src; int in_ch, srcH, srcW;          // operand read through TMA (x, or dy for the data gradient)
+    int out_ch;
+    TapMap tm;                                         // tap grid + where each tap sits in the (kh, kw) kernel
+    int PH, PW;                                        // pixel domain of the GEMM rows
+    int h_mul, tap_h_mul, h_off;                       // source row    = h_mul*ph + tap_h_mul*i + h_off
+    int w_mul, rep_mul, w_off;                         // source column = w_mul*pw + rep_mul*j + w_off (baked into replicas)
+    int out_H, out_W, oh_mul, oh_off, ow_mul, ow_off;  // destination pixel
+};
+
 struct UmmaPlan {
     bool ok;
-    int in_ch, out_ch, H, W, Wp, OH, OW;      // GEMM view: input (B,in_ch,H,W) -> output (B,out_ch,OH,OW)
-    int kh, kw, pt, pl;
-    int cin_eff, cin_chunks, tpc, n_chunks, n_tile, n_ntiles, planes, stages;
+    int Wp, cin_eff, cin_chunks, tpc, n_chunks, n_tile, n_ntiles, planes, stages;
     size_t act_bytes, w_bytes, smem_bytes;
 };
 
-static UmmaPlan make_plan(const cpc_conv_params* p, int which) {
+static UmmaPlan plan_problem(const ConvProblem& c, int batch, int precision) {
     UmmaPlan u{};
     u.ok = false;
-    if (p->stride_h != 1 || p->stride_w != 1) return u;
-    if (which == 0) {
-        u.in_ch = p->c_in; u.out_ch = p->c_out; u.H = p->h_in; u.W = p->w_in; u.OH = p->h_out; u.OW = p->w_out;
-        u.pt = p->pad_top; u.pl = p->pad_left;
-    } else {
-        u.in_ch = p->c_out; u.out_ch = p->c_in; u.H = p->h_out; u.W = p->w_out; u.OH = p->h_in; u.OW = p->w_in;
-        u.pt = p->kh - 1 - p->pad_top; u.pl = p->kw - 1 - p->pad_left;
-        if (u.pt < 0 || u.pl < 0) return u;
-    }
-    u.kh = p->kh; u.kw = p->kw;
-    const int ci = u.in_ch, co = u.out_ch;
+    const int ci = c.in_ch, co = c.out_ch;
     if (!(ci == 16 || ci == 32 || ci % 64 == 0)) return u;
     if (co % 32 != 0 || !(co <= 128 || co % 128 == 0)) return u;
-    if ((long)p->batch * u.OH * ((u.OW + ATOM - 1) / ATOM) > (1l << 30)) return u;
+    if (c.PH <= 0 || c.PW <= 0 || c.tm.th <= 0 || c.tm.tw <= 0) return u;
+    if ((long)batch * c.PH * ((c.PW + ATOM - 1) / ATOM) > (1l << 30)) return u;
     u.cin_eff = ci >= KCHUNK ? KCHUNK : ci;
     u.cin_chunks = ci >= KCHUNK ? ci / KCHUNK : 1;
     u.tpc = KCHUNK / u.cin_eff;
-    const int ntaps = u.kh * u.kw;
+    const int ntaps = c.tm.th * c.tm.tw;
     u.n_chunks = ci >= KCHUNK ? ntaps * u.cin_chunks : (ntaps + u.tpc - 1) / u.tpc;
     u.n_tile = co <= 128 ? co : 128;
     u.n_ntiles = co / u.n_tile;
-    u.planes = p->precision == 1 ? 1 : 2;
-    u.Wp = (u.W + 7) & ~7;
+    u.planes = precision == 1 ? 1 : 2;
+    u.Wp = (c.PW + 7) & ~7;                            // replicas are addressed by GEMM pixel column
     const int stage_bytes = u.planes * (A_PLANE_BYTES + u.n_tile * 128);
     u.stages = (SMEM_LIMIT - 2048) / stage_bytes;
     if (u.stages > 8) u.stages = 8;
     if (u.stages < 2) return u;
     u.smem_bytes = (size_t)u.stages * stage_bytes + sizeof(UmmaBarriers) + 1024;
-    u.act_bytes = align_up((size_t)u.planes * u.kw * p->batch * ci * u.H * u.Wp * 2, 1024);
+    u.act_bytes = align_up((size_t)u.planes * c.tm.tw * batch * ci * c.srcH * u.Wp * 2, 1024);
     u.w_bytes = align_up((size_t)u.planes * u.n_chunks * co * KCHUNK * 2, 1024);
     u.ok = true;
     return u;
 }
 
-size_t umma_conv_workspace(const cpc_conv_params* p, int which) {
-    UmmaPlan u = make_plan(p, which);
-    return u.ok ? u.act_bytes + u.w_bytes + 1024 : 0;
-}
-
-bool umma_conv_eligible(const cpc_conv_params* p, int which) { return make_plan(p, which).ok; }
-
-// which = 0: y = conv(x, w) + bias ; which = 1: dx = conv_transpose(dy, w).   `in` is x or dy, `out` is y or dx.
-int umma_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
-                     void* workspace, size_t workspace_bytes, cudaStream_t s) {
-    UmmaPlan u = make_plan(p, which);
+static int run_problem(const ConvProblem& c, const float* w, const float* bias, float* out, const cpc_conv_params* p,
+                       int relu, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    const int B = p->batch;
+    UmmaPlan u = plan_problem(c, B, p->precision);
     if (!u.ok) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < u.act_bytes + u.w_bytes + 1024) return CPC_ERR_WORKSPACE;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + u.act_bytes);
-    const int B = p->batch;
-    const long rows = (long)B * u.in_ch * u.H;
+    const long rows = (long)B * c.in_ch * c.srcH;
     {
         const long groups = rows * (u.Wp / 8);
         int blocks = (int)((groups + 255) / 256);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        pack_split_kernel<<<blocks, 256, 0, s>>>(in, act, rows, u.W, u.Wp, u.planes, u.kw, u.pl);
+        pack_split_kernel<<<blocks, 256, 0, s>>>(c.src, act, rows, c.srcW, u.Wp, u.planes, c.tm.tw, c.w_mul, c.rep_mul,
+                                                 c.w_off);
         CPC_LAUNCH_CHECK();
-        const long wtotal = (long)u.n_chunks * u.out_ch * KCHUNK;
+        const long wtotal = (long)u.n_chunks * c.out_ch * KCHUNK;
         int wblocks = (int)((wtotal + 255) / 256);
         if (wblocks > 148 * 8) wblocks = 148 * 8;
-        pack_weights_kernel<<<wblocks, 256, 0, s>>>(w, wp, p->c_out, p->c_in, p->kh, p->kw, u.out_ch, u.in_ch, u.cin_eff,
-                                                    u.cin_chunks, u.tpc, u.n_chunks, u.planes, which);
+        pack_weights_kernel<<<wblocks, 256, 0, s>>>(w, wp, p->c_in, p->kh, p->kw, c.out_ch, c.in_ch, u.cin_eff,
+                                                    u.cin_chunks, u.tpc, u.n_chunks, u.planes, c.tm);
         CPC_LAUNCH_CHECK();
     }
     CUtensorMap ta, tb;
     {
-        // replica / plane index is the outermost dimension; OW + pad columns of a replica may be addressed
-        const uint64_t dims[5] = {(uint64_t)u.Wp, (uint64_t)u.H, (uint64_t)u.in_ch, (uint64_t)B,
-                                  (uint64_t)u.planes * u.kw};
+        // replica / plane index is the outermost dimension
+        const uint64_t dims[5] = {(uint64_t)u.Wp, (uint64_t)c.srcH, (uint64_t)c.in_ch, (uint64_t)B,
+                                  (uint64_t)u.planes * c.tm.tw};
         const uint64_t row_b = (uint64_t)u.Wp * 2;
-        const uint64_t strides[4] = {row_b, row_b * u.H, row_b * u.H * u.in_ch, row_b * u.H * u.in_ch * B};
+        const uint64_t strides[4] = {row_b, row_b * c.srcH, row_b * c.srcH * c.in_ch, row_b * c.srcH * c.in_ch * B};
         const uint32_t box[5] = {ATOM, 1, (uint32_t)u.cin_eff, 1, 1};
         if (!make_tmap_bf16(&ta, act, 5, dims, strides, box)) return CPC_ERR_CUDA;
-        const uint64_t wd[4] = {KCHUNK, (uint64_t)u.out_ch, (uint64_t)u.n_chunks, (uint64_t)u.planes};
-        const uint64_t wsr[3] = {KCHUNK * 2, (uint64_t)KCHUNK * 2 * u.out_ch, (uint64_t)KCHUNK * 2 * u.out_ch * u.n_chunks};
+        const uint64_t wd[4] = {KCHUNK, (uint64_t)c.out_ch, (uint64_t)u.n_chunks, (uint64_t)u.planes};
+        const uint64_t wsr[3] = {KCHUNK * 2, (uint64_t)KCHUNK * 2 * c.out_ch, (uint64_t)KCHUNK * 2 * c.out_ch * u.n_chunks};
         const uint32_t wbox[4] = {KCHUNK, (uint32_t)u.n_tile, 1, 1};
         if (!make_tmap_bf16(&tb, wp, 4, wd, wsr, wbox)) return CPC_ERR_CUDA;
     }
     UmmaConv k{};
-    k.AW = (u.OW + ATOM - 1) / ATOM;
-    k.OH = u.OH; k.OW = u.OW;
-    k.n_atoms = B * u.OH * k.AW;
-    k.n_rows_out = u.out_ch; k.n_tile = u.n_tile; k.n_ntiles = u.n_ntiles;
-    k.kh = u.kh; k.kw = u.kw; k.ntaps = u.kh * u.kw; k.tpc = u.tpc; k.cin_eff = u.cin_eff; k.cin_chunks = u.cin_chunks;
-    k.n_chunks = u.n_chunks; k.pt = u.pt; k.pl = u.pl; k.planes = u.planes;
-    k.relu = which == 0 ? p->relu : 0;
-    k.stages = u.stages;
-    k.bias = which == 0 ? bias : nullptr;
-    k.y = out;
+    k.AW = (c.PW + ATOM - 1) / ATOM;
+    k.PH = c.PH; k.PW = c.PW;
+    k.n_atoms = B * c.PH * k.AW;
+    k.n_rows_out = c.out_ch; k.n_tile = u.n_tile; k.n_ntiles = u.n_ntiles;
+    k.th = c.tm.th; k.tw = c.tm.tw; k.ntaps = c.tm.th * c.tm.tw; k.tpc = u.tpc; k.cin_eff = u.cin_eff;
+    k.cin_chunks = u.cin_chunks; k.n_chunks = u.n_chunks;
+    k.h_mul = c.h_mul; k.tap_h_mul = c.tap_h_mul; k.h_off = c.h_off;
+    k.out_H = c.out_H; k.out_W = c.out_W; k.oh_mul = c.oh_mul; k.oh_off = c.oh_off; k.ow_mul = c.ow_mul; k.ow_off = c.ow_off;
+    k.planes = u.planes; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out;
     if (cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int n_tiles = ((k.n_atoms + 1) / 2) * k.n_ntiles;
-    int sms = 148;
-    int grid = n_tiles < sms ? n_tiles : sms;
+    const int grid = n_tiles < 148 ? n_tiles : 148;
     umma_conv_kernel<<<grid, UM_THREADS, u.smem_bytes, s>>>(ta, tb, k);
+    CPC_LAUNCH_CHECK();
+    count_launch(3);
+    return CPC_OK;
+}
+
+static ConvProblem fwd_problem(const float* x, const cpc_conv_params* p) {
+    ConvProblem c{};
+    c.src = x; c.in_ch = p->c_in; c.srcH = p->h_in; c.srcW = p->w_in; c.out_ch = p->c_out;
+    c.tm = TapMap{p->kh, p->kw, 0, 1, 0, 1, 0};
+    c.PH = p->h_out; c.PW = p->w_out;
+    c.h_mul = p->stride_h; c.tap_h_mul = 1; c.h_off = -p->pad_top;
+    c.w_mul = p->stride_w; c.rep_mul = 1; c.w_off = -p->pad_left;
+    c.out_H = p->h_out; c.out_W = p->w_out; c.oh_mul = 1; c.oh_off = 0; c.ow_mul = 1; c.ow_off = 0;
+    return c;
+}
+
+// Data gradient, parity class (rh, rw): dx[h, w] with (h + pt) % sh == rh, (w + pl) % sw == rw.
+//   h = sh*a + rh - pt, taps i = rh + sh*i' read dy row a - i'.  Returns false when the class has no pixels.
+static bool dgrad_problem(const float* dy, const cpc_conv_params* p, int rh, int rw, ConvProblem& c, bool& has_taps) {
+    const int sh = p->stride_h, sw = p->stride_w;
+    c = ConvProblem{};
+    c.src = dy; c.in_ch = p->c_out; c.srcH = p->h_out; c.srcW = p->w_out; c.out_ch = p->c_in;
+    const int th = rh < p->kh ? (p->kh - rh + sh - 1) / sh : 0;
+    const int tw = rw < p->kw ? (p->kw - rw + sw - 1) / sw : 0;
+    has_taps = th > 0 && tw > 0;
+    c.tm = TapMap{th, tw, rh, sh, rw, sw, 1};
+    const int a_min = p->pad_top > rh ? (p->pad_top - rh + sh - 1) / sh : 0;
+    const int e_min = p->pad_left > rw ? (p->pad_left - rw + sw - 1) / sw : 0;
+    const int a_top = p->h_in - 1 + p->pad_top - rh, e_top = p->w_in - 1 + p->pad_left - rw;
+    if (a_top < 0 || e_top < 0) return false;
+    c.PH = a_top / sh - a_min + 1; c.PW = e_top / sw - e_min + 1;
+    if (c.PH <= 0 || c.PW <= 0) return false;
+    c.h_mul = 1; c.tap_h_mul = -1; c.h_off = a_min;
+    c.w_mul = 1; c.rep_mul = -1; c.w_off = e_min;
+    c.out_H = p->h_in; c.out_W = p->w_in;
+    c.oh_mul = sh; c.oh_off = sh * a_min + rh - p->pad_top;
+    c.ow_mul = sw; c.ow_off = sw * e_min + rw - p->pad_left;
+    return true;
+}
+
+static bool channels_ok(int ci, int co) {
+    return (ci == 16 || ci == 32 || ci % 64 == 0) && co % 32 == 0 && (co <= 128 || co % 128 == 0);
+}
+
+bool umma_conv_eligible(const cpc_conv_params* p, int which) {
+    if (p->stride_h > 8 || p->stride_w > 8) return false;
+    if (which == 0) return plan_problem(fwd_problem(nullptr, p), p->batch, p->precision).ok;
+    if (!channels_ok(p->c_out, p->c_in)) return false;
+    // every non-empty class with taps must be plannable
+    for (int rh = 0; rh < p->stride_h; ++rh)
+        for (int rw = 0; rw < p->stride_w; ++rw) {
+            ConvProblem c; bool taps;
+            if (!dgrad_problem(nullptr, p, rh, rw, c, taps) || !taps) continue;
+            if (!plan_problem(c, p->batch, p->precision).ok) return false;
+        }
+    return true;
+}
+
+size_t umma_conv_workspace(const cpc_conv_params* p, int which) {
+    if (!umma_conv_eligible(p, which)) return 0;
+    size_t need = 0;
+    if (which == 0) {
+        UmmaPlan u = plan_problem(fwd_problem(nullptr, p), p->batch, p->precision);
+        need = u.act_bytes + u.w_bytes;
+    } else {
+        for (int rh = 0; rh < p->stride_h; ++rh)
+            for (int rw = 0; rw < p->stride_w; ++rw) {
+                ConvProblem c; bool taps;
+                if (!dgrad_problem(nullptr, p, rh, rw, c, taps) || !taps) continue;
+                UmmaPlan u = plan_problem(c, p->batch, p->precision);
+                if (u.act_bytes + u.w_bytes > need) need = u.act_bytes + u.w_bytes;
+            }
+    }
+    return need + 1024;
+}
+
+// which = 0: y = conv(x, w) + bias ; which = 1: dx = conv_transpose(dy, w).   `in` is x or dy, `out` is y or dx.
+int umma_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
+                     void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    if (which == 0) return run_problem(fwd_problem(in, p), w, bias, out, p, p->relu, workspace, workspace_bytes, s);
+    bool need_zero = false;
+    for (int rh = 0; rh < p->stride_h; ++rh)
+        for (int rw = 0; rw < p->stride_w; ++rw) {
+            ConvProblem c; bool taps;
+            if (dgrad_problem(in, p, rh, rw, c, taps) && !taps) need_zero = true;
+        }
+    if (need_zero &&
+        cudaMemsetAsync(out, 0, sizeof(float) * (size_t)p->batch * p->c_in * p->h_in * p->w_in, s) != cudaSuccess)
+        return CPC_ERR_CUDA;
+    for (int rh = 0; rh < p->stride_h; ++rh)
+        for (int rw = 0; rw < p->stride_w; ++rw) {
+            ConvProblem c; bool taps;
+            if (!dgrad_problem(in, p, rh, rw, c, taps) || !taps) continue;
+            const int st = run_problem(c, w, nullptr, out, p, 0, workspace, workspace_bytes, s);
+            if (st != CPC_OK) return st;
+        }
+    return CPC_OK;
+}
+
+
+// =====================================================================================================
+// Weight gradient of a (strided) conv on the tensor cores.
+//
+//   dW[co, ci, i, j] = sum_{b, oh, ow} dy[b, co, oh, ow] * x[b, ci, sh*oh + i - pt, sw*ow + j - pl]
+//
+// The reduction runs over pixels, which are contiguous in NCHW for BOTH operands, so both are K-major
+// SWIZZLE_128B tiles straight out of TMA: one K chunk = 64 consecutive pixels of one output row.
+//   A tile (M = 128 rows) = CB input channels x TH vertical taps of x, one TMA box (64 w, TH h, CB c);
+//   B tile (N rows)       = N output channels of dy,                   one TMA box (64 w, 1 h, N c).
+// A CTA owns one (x-row tile, co tile, horizontal tap j) output tile and a slice of the pixel range
+// (split-K); the fp32 TMEM accumulator is flushed with red.global.add into the zero-initialised dW.
+// =====================================================================================================
+struct UmmaWgrad {
+    int OH, AW, B;                        // pixel chunks: (b, oh, w-atom)
+    int n_chunks_total, chunks_per_split, n_splits;
+    int n_xtiles, n_ntiles, n_tile;
+    int CB, TH, cin, cout, kh, kw;        // M tile = CB channels x TH taps
+    int c_tiles, h_tiles;                 // x tiles = c_tiles * h_tiles
+    int pt, sh, planes, stages;
+    float* dw;
+};
+
+__global__ void __launch_bounds__(UM_THREADS, 1) umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                  const __grid_constant__ CUtensorMap tmap_dy,
+                                                                  const UmmaWgrad p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = 128 * 128;                           // 128 rows x 64 pixels bf16
+    const int b_bytes = p.n_tile * 128;
+    const int stage_bytes = p.planes * (A_BYTES + b_bytes);
+    UmmaBarriers* bars = reinterpret_cast<UmmaBarriers*>(smem + (size_t)p.stages * stage_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile decode: blockIdx.x = ((j * n_xtiles + xtile) * n_ntiles + ntile), blockIdx.y = split
+    int t = blockIdx.x;
+    const int ntile = t % p.n_ntiles; t /= p.n_ntiles;
+    const int xtile = t % p.n_xtiles;
+    const int j = t / p.n_xtiles;
+    const int ctile = xtile / p.h_tiles, htile = xtile - ctile * p.h_tiles;
+    const int c0 = ctile * p.CB, i0 = htile * p.TH;
+    const int q_begin = blockIdx.y * p.chunks_per_split;
+    const int q_end = min(p.n_chunks_total, q_begin + p.chunks_per_split);
+    const int nq = q_end - q_begin;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_dy);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->acc_full[0], 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(&bars->tmem_base, 256); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int q = q_begin; q < q_end; ++q) {
+                const int row = q / p.AW;
+                const int w0 = (q - row * p.AW) * ATOM;
+                const int b = row / p.OH, oh = row - b * p.OH;
+                mbar_wait(&bars->empty[stage], phase ^ 1);
+                uint8_t* st = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+                for (int pl = 0; pl < p.planes; ++pl) {
+                    tma_load_5d(st + pl * A_BYTES, &tmap_x, &bars->full[stage], w0, oh * p.sh + i0 - p.pt, c0, b, pl * p.kw + j);
+                    tma_load_5d(st + p.planes * A_BYTES + pl * b_bytes, &tmap_dy, &bars->full[stage], w0, oh,
+                                ntile * p.n_tile, b, pl);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int q = 0; q < nq; ++q) {
+                mbar_wait(&bars->full[stage], phase);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t b0 = st + p.planes * A_BYTES;
+                const int ncombo = p.planes == 2 ? 3 : 1;
+                for (int cb = 0; cb < ncombo; ++cb) {
+                    const uint32_t a_addr = st + (cb == 2 ? A_BYTES : 0);
+                    const uint32_t b_addr = b0 + (cb == 1 ? b_bytes : 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+                        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+                        mma_bf16(tmem_base, ad, bd, idesc, (q | cb | k) != 0);
+                    }
+                }
+                tc_commit(&bars->empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(&bars->acc_full[0]);
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        const int m = ew * 32 + lane;                            // accumulator row -> (channel, tap)
+        const int ci = c0 + m / p.TH, i = i0 + m % p.TH;
+        const bool valid = nq > 0 && ci < p.cin && i < p.kh;
+        mbar_wait(&bars->acc_full[0], 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
+        for (int n0 = 0; n0 < p.n_tile; n0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + n0, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int co = ntile * p.n_tile + n0 + c;
+                    atomicAdd(p.dw + (((size_t)co * p.cin + ci) * p.kh + i) * p.kw + j, __uint_as_float(v[c]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+struct WgradPlan {
+    bool ok;
+    int CB, TH, c_tiles, h_tiles, n_tile, n_ntiles, planes, stages, Wp_x, Wp_dy, AW;
+    size_t x_bytes, dy_bytes, smem_bytes;
+};
+
+static WgradPlan make_wgrad_plan(const cpc_conv_params* p) {
+    WgradPlan u{};
+    u.ok = false;
+    if (p->stride_h > 8 || p->stride_w > 8) return u;
+    const int ci = p->c_in, co = p->c_out;
+    if (!(ci == 16 || ci == 32 || ci == 64 || ci % 128 == 0)) return u;
+    if (co % 32 != 0 || !(co <= 256 || co % 256 == 0)) return u;
+    u.CB = ci < 128 ? ci : 128;
+    u.TH = 128 / u.CB;
+    u.c_tiles = ci / u.CB;
+    u.h_tiles = (p->kh + u.TH - 1) / u.TH;
+    u.n_tile = co <= 256 ? co : 256;
+    u.n_ntiles = co / u.n_tile;
+    u.planes = p->precision == 1 ? 1 : 2;
+    u.Wp_x = (p->w_out + 7) & ~7;                      // replicas are addressed by output column
+    u.Wp_dy = (p->w_out + 7) & ~7;
+    u.AW = (p->w_out + ATOM - 1) / ATOM;
+    if ((long)p->batch * p->h_out * u.AW > (1l << 30)) return u;
+    const int stage_bytes = u.planes * (128 * 128 + u.n_tile * 128);
+    u.stages = (SMEM_LIMIT - 2048) / stage_bytes;
+    if (u.stages > 8) u.stages = 8;
+    if (u.stages < 2) return u;
+    u.smem_bytes = (size_t)u.stages * stage_bytes + sizeof(UmmaBarriers) + 1024;
+    u.x_bytes = align_up((size_t)u.planes * p->kw * p->batch * ci * p->h_in * u.Wp_x * 2, 1024);
+    u.dy_bytes = align_up((size_t)u.planes * p->batch * co * p->h_out * u.Wp_dy * 2, 1024);
+    u.ok = true;
+    return u;
+}
+
+size_t umma_wgrad_workspace(const cpc_conv_params* p) {
+    WgradPlan u = make_wgrad_plan(p);
+    return u.ok ? u.x_bytes + u.dy_bytes + 1024 : 0;
+}
+bool umma_wgrad_eligible(const cpc_conv_params* p) { return make_wgrad_plan(p).ok; }
+
+int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
+                      size_t workspace_bytes, cudaStream_t s) {
+    WgradPlan u = make_wgrad_plan(p);
+    if (!u.ok) return CPC_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < u.x_bytes + u.dy_bytes + 1024) return CPC_ERR_WORKSPACE;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(ws + u.x_bytes);
+    const int B = p->batch;
+    {
+        const long rows_x = (long)B * p->c_in * p->h_in;
+        long groups = rows_x * (u.Wp_x / 8);
+        int blocks = (int)((groups + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        pack_split_kernel<<<blocks, 256, 0, s>>>(x, xp, rows_x, p->w_in, u.Wp_x, u.planes, p->kw, p->stride_w, 1,
+                                                 -p->pad_left);
+        CPC_LAUNCH_CHECK();
+        const long rows_dy = (long)B * p->c_out * p->h_out;
+        groups = rows_dy * (u.Wp_dy / 8);
+        blocks = (int)((groups + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        pack_split_kernel<<<blocks, 256, 0, s>>>(dy, dyp, rows_dy, p->w_out, u.Wp_dy, u.planes, 1, 1, 0, 0);
+        CPC_LAUNCH_CHECK();
+    }
+    CUtensorMap tx, tdy;
+    {
+        const uint64_t rb = (uint64_t)u.Wp_x * 2;
+        const uint64_t dims[5] = {(uint64_t)u.Wp_x, (uint64_t)p->h_in, (uint64_t)p->c_in, (uint64_t)B,
+                                  (uint64_t)u.planes * p->kw};
+        const uint64_t strides[4] = {rb, rb * p->h_in, rb * p->h_in * p->c_in, rb * p->h_in * p->c_in * B};
+        const uint32_t box[5] = {ATOM, (uint32_t)u.TH, (uint32_t)u.CB, 1, 1};
+        if (!make_tmap_bf16(&tx, xp, 5, dims, strides, box)) return CPC_ERR_CUDA;
+        const uint64_t rd = (uint64_t)u.Wp_dy * 2;
+        const uint64_t ddims[5] = {(uint64_t)p->w_out, (uint64_t)p->h_out, (uint64_t)p->c_out, (uint64_t)B,
+                                   (uint64_t)u.planes};
+        const uint64_t dstr[4] = {rd, rd * p->h_out, rd * p->h_out * p->c_out, rd * p->h_out * p->c_out * B};
+        const uint32_t dbox[5] = {ATOM, 1, (uint32_t)u.n_tile, 1, 1};
+        if (!make_tmap_bf16(&tdy, dyp, 5, ddims, dstr, dbox)) return CPC_ERR_CUDA;
+    }
+    UmmaWgrad k{};
+    k.OH = p->h_out; k.AW = u.AW; k.B = B;
+    k.n_chunks_total = B * p->h_out * u.AW;
+    k.n_xtiles = u.c_tiles * u.h_tiles; k.n_ntiles = u.n_ntiles; k.n_tile = u.n_tile;
+    k.CB = u.CB; k.TH = u.TH; k.cin = p->c_in; k.cout = p->c_out; k.kh = p->kh; k.kw = p->kw;
+    k.c_tiles = u.c_tiles; k.h_tiles = u.h_tiles;
+    k.pt = p->pad_top; k.sh = p->stride_h; k.planes = u.planes; k.stages = u.stages;
+    k.dw = dw;
+    const int tiles = k.n_xtiles * k.n_ntiles * p->kw;
+    int splits = (148 + tiles - 1) / tiles;
+    const int max_splits = (k.n_chunks_total + 15) / 16;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    k.chunks_per_split = (k.n_chunks_total + splits - 1) / splits;
+    k.n_splits = (k.n_chunks_total + k.chunks_per_split - 1) / k.chunks_per_split;
+    if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p->c_out * p->c_in * p->kh * p->kw, s) != cudaSuccess)
+        return CPC_ERR_CUDA;
+    if (cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
+        return CPC_ERR_CUDA;
+    umma_wgrad_kernel<<<dim3(tiles, k.n_splits), UM_THREADS, u.smem_bytes, s>>>(tx, tdy, k);
     CPC_LAUNCH_CHECK();
     count_launch(3);
     return CPC_OK;

@@ -142,6 +142,9 @@ UMMA_CASES = [
     (2, 16, 6, 40, 64, 3, 3, 1, 1, 0),            # symmetric padding, 4 taps per K chunk + phantom taps
     (1, 256, 4, 33, 512, 1, 1, 0, 0, 0),          # 1x1, four N tiles
     (3, 32, 1, 300, 96, 1, 5, 0, 0, 0),           # conv1d-shaped (h = 1)
+    (2, 64, 3, 8, 128, 1, 1, 2, 2, 0),            # 1x1 residual conv with padding: output wider than input
+    (2, 128, 70, 20, 128, 30, 1, 0, 0, 0),        # 30 vertical taps, one channel tile per tap (wgrad M tile = 128 ch)
+    (1, 256, 12, 9, 256, 5, 1, 0, 0, 0),          # two channel tiles in wgrad
 ]
 
 
@@ -169,6 +172,39 @@ def test_tensor_core_conv_matches_oracle(cpc, case, precision):
     got = cpc.ops.conv2d(xg.detach(), wg.detach(), None, (1, 1), (ph, pw), extra_top=top, relu=True, precision=precision)
     want = F.relu(F.conv2d(F.pad(x.double(), (0, 0, top, 0)), wt.double(), None, padding=(ph, pw)))
     assert rel_err(got, want) < tol
+
+
+UMMA_STRIDED_CASES = [
+    # b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, top
+    (2, 32, 41, 75, 128, 3, 3, 2, 2, 0, 0, 0),      # arch-7 block 1 conv_a shape (3x3, stride 2)
+    (2, 128, 20, 33, 256, 3, 3, 2, 2, 0, 0, 0),     # arch-7 block 2 conv_a shape
+    (1, 64, 9, 40, 64, 3, 3, 2, 2, 1, 1, 0),        # stride 2 with symmetric padding
+    (2, 64, 1, 203, 64, 1, 8, 1, 4, 0, 0, 0),       # AudioEncoder layer 1 shape (k 8, stride 4)
+    (2, 64, 1, 100, 128, 1, 4, 1, 2, 0, 0, 0),      # AudioEncoder layers 2-4 shape (k 4, stride 2)
+    (1, 32, 10, 20, 32, 1, 1, 2, 2, 0, 0, 0),       # stride larger than the kernel: some dgrad classes are empty
+    (1, 32, 12, 30, 64, 3, 1, 2, 1, 0, 0, 2),       # vertical stride + top padding
+]
+
+
+@pytest.mark.parametrize("case", UMMA_STRIDED_CASES)
+def test_tensor_core_strided_conv_matches_oracle(cpc, case):
+    b, cin, h, w, cout, kh, kw, sh, sw, ph, pw, top = case
+    gen = torch.Generator().manual_seed(hash(case) & 0xffff)
+    x = torch.randn(b, cin, h, w, generator=gen)
+    wt = torch.randn(cout, cin, kh, kw, generator=gen) / math.sqrt(cin * kh * kw)
+    bias = torch.randn(cout, generator=gen)
+    xr, wr, br = (t.clone().double().requires_grad_(True) for t in (x, wt, bias))
+    want = F.conv2d(F.pad(xr, (0, 0, top, 0)), wr, br, stride=(sh, sw), padding=(ph, pw))
+    gy = torch.randn(want.shape, generator=gen)
+    (want * gy.double()).sum().backward()
+    xg, wg, bg = (t.clone().to(DEV).requires_grad_(True) for t in (x, wt, bias))
+    got = cpc.ops.conv2d(xg, wg, bg, (sh, sw), (ph, pw), extra_top=top)
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel_err(got, want) < 5e-5
+    (got * gy.to(DEV)).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < 5e-5
+    assert rel_err(wg.grad, wr.grad) < TOL
+    assert rel_err(bg.grad, br.grad) < TOL
 
 
 def test_audio_encoder_matches_reference_golden(cpc):

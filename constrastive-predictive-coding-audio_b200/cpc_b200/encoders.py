@@ -240,20 +240,67 @@ class ScalogramEncoderBlock(nn.Module):
         self.output_activation_writer = ActivationWriter(register=activation_register,
                                                          name=self.name + '_main_conv_2')
 
-    def forward(self, x):
+    def _taps_attached(self):
+        return any(isinstance(m, ActivationWriter) and m.register is not None for m in self.main_modules) or \
+            self.output_activation_writer.register is not None
+
+    def _residual_branch(self, x, main_shape):
+        """Residual branch output and the crop origin that centre-aligns it with ``main`` (:456-470)."""
+        res = _run_modules(self.residual_modules, x)
+        m_h, m_w = main_shape
+        o_h = int((res.shape[2] - m_h + 1) / 2)
+        o_w = int((res.shape[3] - m_w + 1) / 2)
+        off_h = res.shape[2] - (o_h + m_h) if o_h > 0 else 0
+        off_w = res.shape[3] - (o_w + m_w) if o_w > 0 else 0
+        if off_h < 0 or off_w < 0 or off_h + m_h > res.shape[2] or off_w + m_w > res.shape[3]:
+            raise ValueError("residual branch %s cannot be cropped to %s" % (tuple(res.shape), (m_h, m_w)))
+        return res, (off_h, off_w)
+
+    def _forward_fused(self, x, outer_relu):
+        """conv -> fused(BN, ReLU) -> conv -> fused(BN, ReLU, + residual crop, [ReLU]); used when every stage is
+        ``[pad] conv bn relu`` and no activation tap is attached."""
+        mods = [m for m in self.main_modules if not isinstance(m, ActivationWriter)]
+        stages, i = [], 0
+        while i < len(mods):
+            top = 0
+            if isinstance(mods[i], nn.ZeroPad2d):
+                left, right, top, bottom = mods[i].padding
+                if left or right or bottom:
+                    return None
+                i += 1
+            if i + 3 > len(mods):
+                return None
+            conv, bn, act = mods[i], mods[i + 1], mods[i + 2]
+            if not (isinstance(conv, Conv2d) and isinstance(bn, nn.BatchNorm2d) and isinstance(act, nn.ReLU)):
+                return None
+            stages.append((top, conv, bn))
+            i += 3
+        if len(stages) != 2:
+            return None
+        h = x
+        for idx, (top, conv, bn) in enumerate(stages):
+            h = conv(h, extra_top=top)
+            if idx == 0 or not self.residual:
+                h = ops.bn_relu(h, bn, relu=True, outer_relu=False)
+                if idx == 1 and outer_relu:
+                    h = F.relu(h)
+            else:
+                res, off = self._residual_branch(x, (h.shape[2], h.shape[3]))
+                h = ops.bn_relu(h, bn, residual=res, res_off=off, relu=True, outer_relu=outer_relu)
+        return h
+
+    def forward(self, x, outer_relu=False):
+        """``outer_relu``: also apply the ReLU the encoder puts between blocks (scalogram_model.py:523-527)."""
+        if not self._taps_attached():
+            fused = self._forward_fused(x, outer_relu)
+            if fused is not None:
+                return fused
         main = _run_modules(self.main_modules, x)
         if self.residual:
-            res = _run_modules(self.residual_modules, x)
-            m_h, m_w = main.shape[2], main.shape[3]
-            o_h = int((res.shape[2] - m_h + 1) / 2)
-            o_w = int((res.shape[3] - m_w + 1) / 2)
-            if o_h > 0:
-                res = res[:, :, -(o_h + m_h):-o_h, :]
-            if o_w > 0:
-                res = res[:, :, :, -(o_w + m_w):-o_w]
-            main = main + res
+            res, (off_h, off_w) = self._residual_branch(x, (main.shape[2], main.shape[3]))
+            main = main + res[:, :, off_h:off_h + main.shape[2], off_w:off_w + main.shape[3]]
         self.output_activation_writer(main)
-        return main
+        return F.relu(main) if outer_relu else main
 
 
 class ScalogramResidualEncoder(nn.Module):
@@ -287,9 +334,7 @@ class ScalogramResidualEncoder(nn.Module):
             x = x.unsqueeze(2)
         last = len(self.blocks) - 1
         for i, block in enumerate(self.blocks):
-            x = block(x)
-            if i < last:
-                x = F.relu(x)
+            x = block(x, outer_relu=i < last)
             if self.verbose > 1:
                 print("activation shape after block", i, ":", x.shape)
         return x[:, :, 0, :]

@@ -60,8 +60,9 @@ class KernelProfiler:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for key, flops, e0, e1 in self.records:
-            a = agg.setdefault(key, {"key": key, "count": 0, "total_ms": 0.0, "flops_per_launch": flops})
+        for key, flops, nbytes, e0, e1 in self.records:
+            a = agg.setdefault(key, {"key": key, "count": 0, "total_ms": 0.0, "flops_per_launch": flops,
+                                     "bytes_per_launch": nbytes})
             a["count"] += 1
             a["total_ms"] += e0.elapsed_time(e1)
         total = sum(a["total_ms"] for a in agg.values()) or 1.0
@@ -70,14 +71,16 @@ class KernelProfiler:
             a["avg_ms"] = a["total_ms"] / a["count"]
             a["share"] = a["total_ms"] / total
             a["tflops"] = a["flops_per_launch"] / (a["avg_ms"] * 1e-3) / 1e12 if a["avg_ms"] > 0 else 0.0
+            a["gbs"] = a["bytes_per_launch"] / (a["avg_ms"] * 1e-3) / 1e9 if a["avg_ms"] > 0 else 0.0
         return out
 
 
 _profiler = None
 
 
-def _call(key, flops, fn, *args):
-    """Invoke one C-ABI entry point (optionally event-timed) and raise on a non-zero status."""
+def _call(key, flops, fn, *args, nbytes=0.0):
+    """Invoke one C-ABI entry point (optionally event-timed) and raise on a non-zero status.  ``flops`` /
+    ``nbytes`` are the ALGORITHMIC work of the call (what the roofline fractions are computed from)."""
     if _profiler is None:
         status = fn(*args)
     else:
@@ -85,7 +88,7 @@ def _call(key, flops, fn, *args):
         e0.record()
         status = fn(*args)
         e1.record()
-        _profiler.records.append((key, flops, e0, e1))
+        _profiler.records.append((key, flops, nbytes, e0, e1))
     _lib.check(status, key.split(" ")[0])
 
 
@@ -190,6 +193,95 @@ def conv1d(x, weight, bias=None, stride=1, padding=0, relu=False, precision=None
     """F.conv1d semantics (audio_model.py:30-44) through the same kernel family (h = 1)."""
     y = conv2d(x.unsqueeze(2), weight.unsqueeze(2), bias, (1, stride), (0, padding), 0, relu, precision)
     return y.squeeze(2)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused BatchNorm2d + ReLU (+ cropped residual add + ReLU)
+# --------------------------------------------------------------------------------------------------
+
+def _bn_params(x_shape, res_shape, res_off, relu, outer_relu, training, eps, momentum):
+    p = _lib.BnParams()
+    p.batch, p.channels, p.height, p.width = x_shape
+    if res_shape is not None:
+        p.res_height, p.res_width = res_shape[2], res_shape[3]
+        p.res_off_h, p.res_off_w = res_off
+    p.relu, p.outer_relu, p.training = int(relu), int(outer_relu), int(training)
+    p.eps, p.momentum = float(eps), float(momentum)
+    return p
+
+
+def _bn_key(tag, p):
+    return "%s b%d %dx%dx%d%s" % (tag, p.batch, p.channels, p.height, p.width, " +res" if p.res_height else "")
+
+
+class _BnReluFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, res_off, relu, outer_relu, training, eps,
+                momentum):
+        _require_cuda(x, gamma, beta, running_mean, running_var, residual)
+        lib = _lib.load()
+        x = x.contiguous()
+        if residual is not None:
+            residual = residual.contiguous()
+            if residual.shape[:2] != x.shape[:2]:
+                raise ValueError("residual %s does not match %s" % (tuple(residual.shape), tuple(x.shape)))
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise _lib.CpcError("bn_relu expects a 4-d fp32 tensor")
+        p = _bn_params(tuple(x.shape), None if residual is None else tuple(residual.shape), res_off, relu, outer_relu,
+                       training, eps, momentum)
+        c = x.shape[1]
+        out = torch.empty_like(x)
+        save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        save_rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p)), x.device)
+        n = x.numel()
+        with torch.cuda.device(x.device):
+            _call(_bn_key("cpc_bn_relu_fwd", p), 0.0, lib.cpc_bn_relu_fwd, _ptr(x), _ptr(gamma), _ptr(beta),
+                  _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(out), _ptr(save_mean), _ptr(save_rstd),
+                  ctypes.byref(p), _ptr(ws), ws.numel(), _stream(),
+                  nbytes=4.0 * n * ((3 if training else 2) + (1 if residual is not None else 0)))
+        ctx.cfg = (tuple(x.shape), None if residual is None else tuple(residual.shape), res_off, relu, outer_relu,
+                   training, eps, momentum)
+        ctx.save_for_backward(x, gamma, beta, save_mean, save_rstd, residual)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gamma, beta, save_mean, save_rstd, residual = ctx.saved_tensors
+        lib = _lib.load()
+        x_shape, res_shape, res_off, relu, outer_relu, training, eps, momentum = ctx.cfg
+        p = _bn_params(x_shape, res_shape, res_off, relu, outer_relu, training, eps, momentum)
+        dout = dout.contiguous()
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(gamma) if gamma is not None else None
+        dbeta = torch.empty_like(beta) if beta is not None else None
+        d_res = torch.empty_like(residual) if (residual is not None and ctx.needs_input_grad[5]) else None
+        ws = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p)), x.device)
+        n = x.numel()
+        with torch.cuda.device(x.device):
+            _call(_bn_key("cpc_bn_relu_bwd", p), 0.0, lib.cpc_bn_relu_bwd, _ptr(dout), _ptr(x), _ptr(gamma), _ptr(beta),
+                  _ptr(save_mean), _ptr(save_rstd), _ptr(residual), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(d_res),
+                  ctypes.byref(p), _ptr(ws), ws.numel(), _stream(),
+                  nbytes=4.0 * n * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0)))
+        return dx, dgamma, dbeta, None, None, d_res, None, None, None, None, None, None
+
+
+def bn_relu(x, bn, residual=None, res_off=(0, 0), relu=True, outer_relu=False):
+    """``relu_if(outer_relu, relu_if(relu, bn(x)) + crop(residual))`` for an ``nn.BatchNorm2d`` module ``bn``
+    (train mode: batch statistics + running-stat update; eval mode: running statistics).  One fused kernel family
+    forward, one backward (scalogram_model.py:399-431, 451-472, 523-527)."""
+    training = bn.training or bn.running_mean is None
+    momentum = bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    if momentum is None:
+        momentum = 0.0
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return _BnReluFunction.apply(x, bn.weight, bn.bias, rm, rv, residual, tuple(res_off), bool(relu), bool(outer_relu),
+                                 bool(training), bn.eps, momentum)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -209,16 +209,19 @@ __global__ void __launch_bounds__(TILE_THREADS) conv_wgrad_kernel(WgradA la, Wgr
     }
 }
 
-// dbias[co] = sum_{b, pix} dy[b, co, pix]; grid (Cout, splits)
-__global__ void __launch_bounds__(256) conv_dbias_kernel(const float* __restrict__ dy, float* __restrict__ dbias,
-                                                        int B, int Cout, int ohow) {
-    const int co = blockIdx.x;
+// dbias[co] = sum_{b, pix} dy[b, co, pix]; grid (segments of one plane, B*Cout), one float atomic per block
+constexpr int DB_THREADS = 256;
+constexpr int DB_PER_THREAD = 16;
+__global__ void __launch_bounds__(DB_THREADS) conv_dbias_kernel(const float* __restrict__ dy, float* __restrict__ dbias,
+                                                               int Cout, int ohow) {
+    const int plane = blockIdx.y;
+    const float* p = dy + (size_t)plane * ohow;
+    const int i0 = blockIdx.x * (DB_THREADS * DB_PER_THREAD) + threadIdx.x;
     float s = 0.f;
-    const long total = (long)B * ohow;
-    for (long idx = (long)blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.y * blockDim.x) {
-        const int b = (int)(idx / ohow);
-        const int pix = (int)(idx - (long)b * ohow);
-        s += __ldg(dy + ((size_t)b * Cout + co) * ohow + pix);
+#pragma unroll
+    for (int u = 0; u < DB_PER_THREAD; ++u) {
+        const int i = i0 + u * DB_THREADS;
+        if (i < ohow) s += __ldg(p + i);
     }
     __shared__ float red[8];
     s = warp_sum(s);
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(256) conv_dbias_kernel(const float* __restrict
     if (threadIdx.x < 32) {
         float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
         v = warp_sum(v);
-        if (threadIdx.x == 0) atomicAdd(dbias + co, v);
+        if (threadIdx.x == 0) atomicAdd(dbias + plane % Cout, v);
     }
 }
 
@@ -282,11 +285,8 @@ extern "C" int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const 
 
 static int launch_dbias(const float* dy, float* dbias, const ConvGeom& g, cudaStream_t s) {
     if (cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)g.Cout, s) != cudaSuccess) return CPC_ERR_CUDA;
-    long total = (long)g.B * g.ohow;
-    int sp = (int)((total + 256 * 8 - 1) / (256 * 8));
-    if (sp > 64) sp = 64;
-    if (sp < 1) sp = 1;
-    conv_dbias_kernel<<<dim3(g.Cout, sp), 256, 0, s>>>(dy, dbias, g.B, g.Cout, g.ohow);
+    const dim3 grid(ceil_div(g.ohow, DB_THREADS * DB_PER_THREAD), g.B * g.Cout);
+    conv_dbias_kernel<<<grid, DB_THREADS, 0, s>>>(dy, dbias, g.Cout, g.ohow);
     CPC_LAUNCH_CHECK();
     count_launch();
     return CPC_OK;

@@ -124,6 +124,38 @@ int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, con
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 2b. Fused BatchNorm2d + ReLU (+ centre-cropped residual add + ReLU), forward and backward.
+ *    Replaces nn.BatchNorm2d / nn.ReLU after each conv of ScalogramEncoderBlock (scalogram_model.py:399-431),
+ *    the residual crop-and-add (scalogram_model.py:451-472) and the F.relu between blocks (:523-527), and
+ *    their autograd (cuDNN batch-norm backward, threshold_backward, slice_backward, add).
+ *        v   = relu_if(relu, gamma * (x - mean) * rstd + beta)
+ *        out = relu_if(outer_relu, v + residual[:, :, res_off_h : res_off_h + H, res_off_w : res_off_w + W])
+ *    x / out / dout / dx: (B, C, H, W) contiguous fp32; residual / d_residual: (B, C, res_height, res_width).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cpc_bn_params {
+    int32_t batch, channels, height, width;
+    int32_t res_height, res_width;   /* 0, 0: no residual operand                                          */
+    int32_t res_off_h, res_off_w;    /* crop origin inside the residual plane                              */
+    int32_t relu;                    /* ReLU directly after the normalisation                              */
+    int32_t outer_relu;              /* ReLU after the residual add (ignored without residual)             */
+    int32_t training;                /* 1: batch statistics, running stats updated (nn.BatchNorm2d.train());
+                                        0: running statistics (eval())                                     */
+    float eps, momentum;
+} cpc_bn_params;
+
+size_t cpc_bn_relu_workspace_bytes(const cpc_bn_params* p);
+/* gamma / beta (C) may be NULL (affine=False).  running_mean / running_var (C): updated in place when
+ * training (may be NULL then), read when not.  save_mean / save_rstd (C): outputs, inputs of bwd. */
+int cpc_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    const float* residual, float* out, float* save_mean, float* save_rstd, const cpc_bn_params* p,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* dx overwritten; dgamma / dbeta (C) overwritten when non-NULL; d_residual (full residual shape, zero outside
+ * the crop) overwritten when non-NULL. */
+int cpc_bn_relu_bwd(const float* dout, const float* x, const float* gamma, const float* beta, const float* save_mean,
+                    const float* save_rstd, const float* residual, float* dx, float* dgamma, float* dbeta,
+                    float* d_residual, const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * 3. InfoNCE scoring + loss, forward and backward, scores never written to HBM.
  *    Replaces score_function + the loss block of ContrastiveEstimationTrainer.train
  *    (contrastive_estimation_training.py:12-22, 106-122, 141, 166) and its autograd.

@@ -277,6 +277,65 @@ def test_residual_encoder_matches_reference_golden(cpc):
 
 
 # ---------------------------------------------------------------------------------------------------
+# fused BatchNorm + ReLU (+ cropped residual + ReLU)
+# ---------------------------------------------------------------------------------------------------
+
+def _bn_reference(x, bn, res, off, relu, outer_relu):
+    """CPU restatement of scalogram_model.py:399-431 (bn, relu), :451-472 (crop + add), :523-527 (relu)."""
+    y = bn(x)
+    if relu:
+        y = F.relu(y)
+    if res is not None:
+        y = y + res[:, :, off[0]:off[0] + y.shape[2], off[1]:off[1] + y.shape[3]]
+        if outer_relu:
+            y = F.relu(y)
+    return y
+
+
+@pytest.mark.parametrize("shape,res_extra,off,relu,outer,train", [
+    ((3, 5, 7, 19), None, (0, 0), True, False, True),
+    ((4, 8, 13, 37), (1, 1), (0, 0), True, True, True),
+    ((2, 6, 9, 130), (2, 3), (1, 2), True, True, True),
+    ((2, 4, 5, 4200), (0, 0), (0, 0), True, False, True),       # more than one segment per plane
+    ((3, 7, 6, 11), (1, 0), (1, 0), False, True, True),
+    ((2, 5, 8, 33), (1, 1), (0, 1), True, True, False),        # eval(): running statistics
+])
+def test_bn_relu_matches_torch_reference(cpc, shape, res_extra, off, relu, outer, train):
+    g = torch.Generator().manual_seed(7)
+    b, c, h, w = shape
+    x = torch.randn(shape, generator=g) * 2 + 0.5
+    res = None if res_extra is None else torch.randn(b, c, h + res_extra[0], w + res_extra[1], generator=g)
+    gy = torch.randn(shape, generator=g)
+
+    def make_bn():
+        bn = torch.nn.BatchNorm2d(c)
+        with torch.no_grad():
+            bn.weight.copy_(torch.linspace(0.5, 1.5, c))
+            bn.bias.copy_(torch.linspace(-0.3, 0.3, c))
+            bn.running_mean.copy_(torch.linspace(-0.2, 0.6, c))
+            bn.running_var.copy_(torch.linspace(0.8, 4.0, c))
+        return bn.train(train)
+    ref_bn, our_bn = make_bn(), make_bn().to(DEV)
+    xr = x.clone().requires_grad_(True)
+    rr = None if res is None else res.clone().requires_grad_(True)
+    yr = _bn_reference(xr, ref_bn, rr, off, relu, outer)
+    (yr * gy).sum().backward()
+    xo = x.to(DEV).requires_grad_(True)
+    ro = None if res is None else res.to(DEV).requires_grad_(True)
+    yo = cpc.ops.bn_relu(xo, our_bn, residual=ro, res_off=off, relu=relu, outer_relu=outer)
+    (yo * gy.to(DEV)).sum().backward()
+    assert rel_err(yo, yr) < 1e-5
+    assert rel_err(xo.grad, xr.grad) < 1e-4
+    assert rel_err(our_bn.weight.grad, ref_bn.weight.grad) < 1e-4
+    assert rel_err(our_bn.bias.grad, ref_bn.bias.grad) < 1e-4
+    if res is not None:
+        assert rel_err(ro.grad, rr.grad) < 1e-5
+    assert rel_err(our_bn.running_mean, ref_bn.running_mean) < 1e-5
+    assert rel_err(our_bn.running_var, ref_bn.running_var) < 1e-5
+    assert int(our_bn.num_batches_tracked) == int(ref_bn.num_batches_tracked)
+
+
+# ---------------------------------------------------------------------------------------------------
 # InfoNCE
 # ---------------------------------------------------------------------------------------------------
 

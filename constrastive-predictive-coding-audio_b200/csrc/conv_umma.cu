@@ -75,6 +75,17 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
     }
 }
 
+// host launcher shared with conv_tall.cu
+int pack_split_launch(const float* x, __nv_bfloat16* out, long rows, int W, int Wp, int planes, int nrep, int w_mul,
+                      int rep_mul, int w_off, cudaStream_t s) {
+    const long groups = rows * (Wp / 8);
+    int blocks = (int)((groups + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    pack_split_kernel<<<blocks, 256, 0, s>>>(x, out, rows, W, Wp, planes, nrep, w_mul, rep_mul, w_off);
+    return cudaGetLastError() == cudaSuccess ? CPC_OK : CPC_ERR_CUDA;
+}
+
 // weights (Cout, Cin, kh, kw) fp32 -> bf16 (planes, n_chunks, Nrows, 64), K-major rows of one K chunk.
 // GEMM tap (i', j') of a (th x tw) tap grid reads source tap (i_off + i_mul*i', j_off + j_mul*j').
 // swap = 0: rows n = co, k channel = ci (forward);  swap = 1: rows n = ci, k channel = co (data gradient).

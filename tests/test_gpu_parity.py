@@ -145,6 +145,12 @@ UMMA_CASES = [
     (2, 64, 3, 8, 128, 1, 1, 2, 2, 0),            # 1x1 residual conv with padding: output wider than input
     (2, 128, 70, 20, 128, 30, 1, 0, 0, 0),        # 30 vertical taps, one channel tile per tap (wgrad M tile = 128 ch)
     (1, 256, 12, 9, 256, 5, 1, 0, 0, 0),          # two channel tiles in wgrad
+    # 32 -> 32 channel kh x 1 convs take the row-streaming kernels of conv_tall.cu in fp32 mode
+    (1, 32, 50, 200, 32, 64, 1, 0, 0, 63),        # arch-7 block 0 conv_b geometry: most taps of the top rows hit padding
+    (3, 32, 37, 64, 32, 16, 1, 0, 0, 0),          # no padding, one atom per row, odd unit count (phantom atom)
+    (2, 32, 20, 314, 32, 20, 1, 0, 0, 19),        # kh = tap-ring size, W = 314 (five atoms, last one ragged)
+    (1, 32, 8, 40, 32, 8, 1, 0, 0, 3),            # fewer output rows than a tile
+    (2, 32, 90, 70, 32, 30, 1, 0, 0, 10),         # several row tiles, partial top padding
 ]
 
 
@@ -172,6 +178,29 @@ def test_tensor_core_conv_matches_oracle(cpc, case, precision):
     got = cpc.ops.conv2d(xg.detach(), wg.detach(), None, (1, 1), (ph, pw), extra_top=top, relu=True, precision=precision)
     want = F.relu(F.conv2d(F.pad(x.double(), (0, 0, top, 0)), wt.double(), None, padding=(ph, pw)))
     assert rel_err(got, want) < tol
+
+
+def test_tall_conv_full_size_agrees_with_generic_kernel(cpc):
+    """BASELINE-size geometry of the 64x1 pitch conv (32x127x314, B = 4): the row-streaming kernels against
+    the generic implicit-GEMM tcgen05 kernels on the same data (size-independent A/B property)."""
+    import os
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 32, 127, 314, generator=gen).to(DEV)
+    wt = (torch.randn(32, 32, 64, 1, generator=gen) / math.sqrt(32 * 64)).to(DEV)
+    bias = torch.randn(32, generator=gen).to(DEV)
+    gy = torch.randn(4, 32, 127, 314, generator=gen).to(DEV)
+    outs = []
+    for flag in ("0", "1"):
+        os.environ["CPC_NO_TALL_CONV"] = flag
+        try:
+            xg, wg, bg = (t.clone().requires_grad_(True) for t in (x, wt, bias))
+            y = cpc.ops.conv2d(xg, wg, bg, (1, 1), (0, 0), extra_top=63)
+            (y * gy).sum().backward()
+            outs.append((y.detach(), xg.grad, wg.grad, bg.grad))
+        finally:
+            os.environ["CPC_NO_TALL_CONV"] = "0"
+    for a, b in zip(*outs):
+        assert rel_err(a, b) < 5e-5
 
 
 UMMA_STRIDED_CASES = [

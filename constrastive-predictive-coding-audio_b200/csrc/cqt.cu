@@ -8,6 +8,8 @@
 // Stage 2: one elementwise pass turning (re, im) into the scalogram the trainer consumes.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace cpc {
 
 struct CqtGroups {
@@ -36,12 +38,13 @@ struct FilterRows {
 };
 
 // grid (frame tiles, groups); complex out (B, F, T, 2)
+// cplx holds bins [f0, f0 + F) only: (B, F, T, 2); groups [g_first, g_first + gridDim.y) are computed
 __global__ void __launch_bounds__(TILE_THREADS) cqt_filterbank_kernel(const float* __restrict__ x,
                                                                      const float* __restrict__ weights,
                                                                      float* __restrict__ cplx, CqtGroups gr, int B, int T,
-                                                                     int F, int hop, int pitch) {
+                                                                     int F, int hop, int pitch, int g_first, int f0) {
     __shared__ TileSmem sm;
-    const int g = blockIdx.y;
+    const int g = blockIdx.y + g_first;
     const int ng = gr.hi[g] - gr.lo[g];
     const int M = B * T;
     FrameRows la{x, M, gr.ksize[g], T, hop, pitch, gr.off[g], FastDiv(T)};
@@ -62,27 +65,29 @@ __global__ void __launch_bounds__(TILE_THREADS) cqt_filterbank_kernel(const floa
                 const int n = col0 + ty * 4 + j;
                 if (n >= 2 * ng) continue;
                 const int part = n >= ng;
-                const int bin = gr.lo[g] + (part ? n - ng : n);
+                const int bin = gr.lo[g] + (part ? n - ng : n) - f0;
                 cplx[(((size_t)b * F + bin) * T + t) * 2 + part] = acc[i][j];
             }
         }
     }
 }
 
-// One thread per output element (b, f, to).  mode 1: out (B,1,F,To); mode 2: out (B,2,F,To).
+// One thread per output element (b, f, to) for the Fs bins [f0, f0 + Fs) held by cplx (B, Fs, T, 2).
+// mode 1: out (B,1,F,To); mode 2: out (B,2,F,To).
 __global__ void __launch_bounds__(256) cqt_scalogram_kernel(const float* __restrict__ cplx,
                                                            const float* __restrict__ phase_fixed,
                                                            const float* __restrict__ phase_scale, float* __restrict__ out,
                                                            int B, int F, int T, int To, int mode, int pool, float eps,
-                                                           float log_offset, float norm, float power) {
-    const long total = (long)B * F * To;
+                                                           float log_offset, float norm, float power, int f0, int Fs) {
+    const long total = (long)B * Fs * To;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int to = (int)(idx % To);
     const long bf = idx / To;
-    const int f = (int)(bf % F);
-    const int b = (int)(bf / F);
-    const float2* z = reinterpret_cast<const float2*>(cplx) + ((size_t)b * F + f) * T;
+    const int fl = (int)(bf % Fs);
+    const int f = f0 + fl;
+    const int b = (int)(bf / Fs);
+    const float2* z = reinterpret_cast<const float2*>(cplx) + ((size_t)b * Fs + fl) * T;
     const float kPi = 3.14159265358979323846f;
     float amp = -INFINITY, ph = -INFINITY;
     for (int q = 0; q < pool; ++q) {
@@ -139,9 +144,33 @@ static int cqt_validate(const cpc_cqt_params* p) {
 
 using namespace cpc;
 
+// cqt_umma.cu
+namespace cpc {
+bool cqt_umma_eligible(const cpc_cqt_params* p);
+int cqt_umma_tensor_groups(const cpc_cqt_params* p);
+size_t cqt_umma_workspace(const cpc_cqt_params* p);
+int cqt_umma_launch(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale, float* out,
+                    const cpc_cqt_params* p, void* workspace, size_t workspace_bytes, cudaStream_t s);
+}
+
+// CPC_NO_TENSOR_CQT=1 keeps every group on the CUDA-core kernels (A/B switch for tests)
+static bool tensor_cqt(const cpc_cqt_params* p) {
+    const char* e = std::getenv("CPC_NO_TENSOR_CQT");
+    if (e && e[0] == '1') return false;
+    return cqt_umma_eligible(p);
+}
+
+// bytes of the complex intermediate the CUDA-core path needs for groups [g_first, n_groups)
+static size_t simt_cplx_bytes(const cpc_cqt_params* p, int g_first) {
+    if (p->mode == CPC_CQT_COMPLEX || g_first >= p->n_groups) return 0;
+    const int fs = p->n_bins - p->bin_lo[g_first];
+    return align_up(sizeof(float) * 2 * (size_t)p->batch * fs * p->n_frames, 1024);
+}
+
 extern "C" size_t cpc_cqt_workspace_bytes(const cpc_cqt_params* p) {
-    if (!p || p->mode == CPC_CQT_COMPLEX) return 0;
-    return sizeof(float) * 2 * (size_t)p->batch * p->n_bins * p->n_frames;
+    if (!p || cqt_validate(p) != CPC_OK) return 0;
+    if (tensor_cqt(p)) return cqt_umma_workspace(p) + simt_cplx_bytes(p, cqt_umma_tensor_groups(p)) + 1024;
+    return simt_cplx_bytes(p, 0);
 }
 
 extern "C" int cpc_cqt_fwd(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale,
@@ -163,20 +192,34 @@ extern "C" int cpc_cqt_fwd(const float* x, const float* weights, const float* ph
         gr.off[g] = (p->kernel_size[0] - p->kernel_size[g]) / 2;
         gr.woff[g] = p->weight_offset[g];
     }
-    float* cplx = p->mode == CPC_CQT_COMPLEX ? out : reinterpret_cast<float*>(workspace);
+    int g_first = 0;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    if (tensor_cqt(p)) {
+        // groups with >= 128 taps: tensor cores, written in the final format
+        const size_t uw = cqt_umma_workspace(p);
+        st = cqt_umma_launch(x, weights, phase_fixed, phase_scale, out, p, ws, uw, s);
+        if (st != CPC_OK) return st;
+        g_first = cqt_umma_tensor_groups(p);
+        ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws) + uw, 1024));
+        if (g_first >= p->n_groups) return CPC_OK;
+    }
+    // remaining (short) groups: CUDA-core filterbank + elementwise pass over their bins
+    const int f0 = p->bin_lo[g_first], fs = p->n_bins - f0;
+    const bool direct = p->mode == CPC_CQT_COMPLEX;
+    float* cplx = direct ? out : reinterpret_cast<float*>(ws);
     const int M = p->batch * p->n_frames;
-    dim3 grid(ceil_div(M, TILE), p->n_groups);
-    cqt_filterbank_kernel<<<grid, TILE_THREADS, 0, s>>>(x, weights, cplx, gr, p->batch, p->n_frames, p->n_bins, p->hop,
-                                                       p->x_pitch);
+    dim3 grid(ceil_div(M, TILE), p->n_groups - g_first);
+    cqt_filterbank_kernel<<<grid, TILE_THREADS, 0, s>>>(x, weights, cplx, gr, p->batch, p->n_frames,
+                                                       direct ? p->n_bins : fs, p->hop, p->x_pitch, g_first, direct ? 0 : f0);
     CPC_LAUNCH_CHECK();
     count_launch();
-    if (p->mode != CPC_CQT_COMPLEX) {
+    if (!direct) {
         const int t_eff = p->mode == CPC_CQT_LOGPOW_PHASE ? p->n_frames - 1 : p->n_frames;
         const int to = t_eff / p->pool_t;
-        const long total = (long)p->batch * p->n_bins * to;
+        const long total = (long)p->batch * fs * to;
         cqt_scalogram_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
             cplx, phase_fixed, phase_scale, out, p->batch, p->n_bins, p->n_frames, to, p->mode, p->pool_t, p->eps,
-            p->log_offset, p->norm, p->power);
+            p->log_offset, p->norm, p->power, f0, fs);
         CPC_LAUNCH_CHECK();
         count_launch();
     }

@@ -30,14 +30,25 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
 int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
                       size_t workspace_bytes, cudaStream_t s);
 
+// conv_tall128.cu: row-streaming kernels for kh x 1, stride-1 convolutions with 128 output channels
+size_t tall128_workspace(const cpc_conv_params* p, int which);
+bool tall128_eligible(const cpc_conv_params* p, int which);
+int tall128_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
+                        void* workspace, size_t workspace_bytes, cudaStream_t s);
+int tall128_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
+                         size_t workspace_bytes, cudaStream_t s);
+
 // Debug switches (tests use them to A/B kernel families on one shape): CPC_FORCE_CUDA_CORE_CONV=1 selects the
 // fp32 CUDA-core kernels, CPC_NO_TALL_CONV=1 keeps tall convolutions on the generic tcgen05 kernel.
-static bool tall_path(const cpc_conv_params* p, int which) {
+// Returns 0 (not a tall conv), 1 (conv_tall.cu, 32 -> 32 channels) or 2 (conv_tall128.cu).
+static int tall_path(const cpc_conv_params* p, int which) {
     const char* e = std::getenv("CPC_FORCE_CUDA_CORE_CONV");
-    if (e && e[0] == '1') return false;
+    if (e && e[0] == '1') return 0;
     e = std::getenv("CPC_NO_TALL_CONV");
-    if (e && e[0] == '1') return false;
-    return tall_conv_eligible(p, which);
+    if (e && e[0] == '1') return 0;
+    if (tall_conv_eligible(p, which)) return 1;
+    if (tall128_eligible(p, which)) return 2;
+    return 0;
 }
 
 static bool tensor_core_path(const cpc_conv_params* p, int which) {
@@ -257,7 +268,8 @@ using namespace cpc;
 
 extern "C" size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which) {
     if (validate(p) != CPC_OK) return 0;
-    if (which >= 0 && which <= 2 && tall_path(p, which)) return tall_conv_workspace(p, which);
+    if (which >= 0 && which <= 2 && tall_path(p, which))
+        return tall_path(p, which) == 1 ? tall_conv_workspace(p, which) : tall128_workspace(p, which);
     if ((which == 0 || which == 1) && tensor_core_path(p, which)) return umma_conv_workspace(p, which);
     if (which == 2 && tensor_core_path(p, 2)) return umma_wgrad_workspace(p);
     return 0;
@@ -269,7 +281,9 @@ extern "C" int cpc_conv_fwd(const float* x, const float* w, const float* bias, f
     if (st != CPC_OK) return st;
     if (!x || !w || !y) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
-    if (tall_path(p, 0)) return tall_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (const int tp = tall_path(p, 0))
+        return tp == 1 ? tall_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream)
+                       : tall128_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream);
     if (tensor_core_path(p, 0))
         return umma_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream);
     ConvGeom g = make_geom(p);
@@ -289,8 +303,9 @@ extern "C" int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const 
     if (st != CPC_OK) return st;
     if (!dy || !w || !dx) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
-    if (tall_path(p, 1))
-        return tall_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (const int tp = tall_path(p, 1))
+        return tp == 1 ? tall_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream)
+                       : tall128_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream);
     if (tensor_core_path(p, 1))
         return umma_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream);
     ConvGeom g = make_geom(p);
@@ -321,8 +336,9 @@ extern "C" int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float*
     if ((st = check_device()) != CPC_OK) return st;
     ConvGeom g = make_geom(p);
     cudaStream_t s = (cudaStream_t)stream;
-    if (tall_path(p, 2)) {
-        st = tall_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s);
+    if (const int tp = tall_path(p, 2)) {
+        st = tp == 1 ? tall_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s)
+                     : tall128_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s);
         if (st != CPC_OK) return st;
         return dbias ? launch_dbias(dy, dbias, g, s) : CPC_OK;
     }

@@ -180,6 +180,12 @@ UMMA_CASES = [
     (2, 32, 20, 314, 32, 20, 1, 0, 0, 19),        # kh = tap-ring size, W = 314 (five atoms, last one ragged)
     (1, 32, 8, 40, 32, 8, 1, 0, 0, 3),            # fewer output rows than a tile
     (2, 32, 90, 70, 32, 30, 1, 0, 0, 10),         # several row tiles, partial top padding
+    # 128-output-channel kh x 1 convs take conv_tall128.cu (4 output rows per tile, channel-chunk-major)
+    (2, 128, 63, 156, 128, 30, 1, 0, 0, 0),       # arch-7 block 1 conv_b geometry
+    (1, 128, 9, 64, 128, 4, 1, 0, 0, 3),          # kh = rows per tile, top padding, single atom
+    (3, 64, 11, 70, 128, 6, 1, 0, 0, 2),          # one channel chunk forward; dgrad / wgrad fall to the generic kernels
+    (1, 256, 13, 40, 128, 7, 1, 0, 0, 0),         # four channel chunks forward
+    (2, 128, 12, 30, 64, 5, 1, 0, 0, 4),          # dgrad on the tall kernel (C_in = 128), forward generic
 ]
 
 
@@ -209,21 +215,23 @@ def test_tensor_core_conv_matches_oracle(cpc, case, precision):
     assert rel_err(got, want) < tol
 
 
-def test_tall_conv_full_size_agrees_with_generic_kernel(cpc):
-    """BASELINE-size geometry of the 64x1 pitch conv (32x127x314, B = 4): the row-streaming kernels against
-    the generic implicit-GEMM tcgen05 kernels on the same data (size-independent A/B property)."""
+@pytest.mark.parametrize("geom", [(32, 127, 314, 64, 63), (128, 63, 156, 30, 0)])
+def test_tall_conv_full_size_agrees_with_generic_kernel(cpc, geom):
+    """BASELINE-size geometry of the 64x1 and 30x1 pitch convs (B = 4): the row-streaming kernels against the
+    generic implicit-GEMM tcgen05 kernels on the same data (size-independent A/B property)."""
     import os
+    ch, h, w_, kh, top = geom
     gen = torch.Generator().manual_seed(5)
-    x = torch.randn(4, 32, 127, 314, generator=gen).to(DEV)
-    wt = (torch.randn(32, 32, 64, 1, generator=gen) / math.sqrt(32 * 64)).to(DEV)
-    bias = torch.randn(32, generator=gen).to(DEV)
-    gy = torch.randn(4, 32, 127, 314, generator=gen).to(DEV)
+    x = torch.randn(4, ch, h, w_, generator=gen).to(DEV)
+    wt = (torch.randn(ch, ch, kh, 1, generator=gen) / math.sqrt(ch * kh)).to(DEV)
+    bias = torch.randn(ch, generator=gen).to(DEV)
+    gy = torch.randn(4, ch, h + top - kh + 1, w_, generator=gen).to(DEV)
     outs = []
     for flag in ("0", "1"):
         os.environ["CPC_NO_TALL_CONV"] = flag
         try:
             xg, wg, bg = (t.clone().requires_grad_(True) for t in (x, wt, bias))
-            y = cpc.ops.conv2d(xg, wg, bg, (1, 1), (0, 0), extra_top=63)
+            y = cpc.ops.conv2d(xg, wg, bg, (1, 1), (0, 0), extra_top=top)
             (y * gy).sum().backward()
             outs.append((y.detach(), xg.grad, wg.grad, bg.grad))
         finally:

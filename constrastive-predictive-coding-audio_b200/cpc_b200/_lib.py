@@ -44,6 +44,11 @@ class BnParams(ctypes.Structure):
                 ("momentum", ctypes.c_float)]
 
 
+class PoolParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "channels", "h_in", "w_in", "h_out", "w_out", "kernel",
+                                              "ceil_mode")]
+
+
 class InfoNceParams(ctypes.Structure):
     _fields_ = [("batch", ctypes.c_int32), ("steps", ctypes.c_int32), ("enc", ctypes.c_int32),
                 ("all_steps", ctypes.c_int32), ("score_kind", ctypes.c_int32), ("regularization", ctypes.c_float),
@@ -68,6 +73,8 @@ SIGNATURES = {
     "cpc_bn_relu_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(BnParams)]),
     "cpc_bn_relu_fwd": (ctypes.c_int, [_P] * 9 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
     "cpc_bn_relu_bwd": (ctypes.c_int, [_P] * 11 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
+    "cpc_maxpool_fwd": (ctypes.c_int, [_P, _P, ctypes.POINTER(PoolParams), _P]),
+    "cpc_maxpool_bwd": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(PoolParams), _P]),
     "cpc_infonce_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(InfoNceParams), ctypes.c_int]),
     "cpc_infonce_fwd": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(InfoNceParams), _P, ctypes.c_size_t, _P]),
     "cpc_infonce_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(InfoNceParams), _P, ctypes.c_size_t, _P]),

@@ -54,6 +54,18 @@ class Conv2d(nn.Conv2d):
         return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, extra_top, relu)
 
 
+class MaxPool2d(nn.MaxPool2d):
+    """nn.MaxPool2d whose non-overlapping, unpadded square case (all the reference uses) runs on the B200 kernels."""
+
+    def forward(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else None
+        stride = self.stride if isinstance(self.stride, int) else None
+        if (k is not None and stride == k and self.padding == 0 and self.dilation == 1 and not self.return_indices
+                and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32):
+            return ops.max_pool2d(x, k, self.ceil_mode)
+        return super().forward(x)
+
+
 def _run_modules(modules, x):
     """Run a reference-ordered module list, folding ZeroPad2d(top) into the conv that follows it."""
     pending_top = 0
@@ -156,7 +168,7 @@ class ScalogramEncoder(nn.Module):
                               bias=args_dict['bias'] if ks[1] > 1 else False, stride=args_dict['stride'][l])
             self.module_list.add_module('conv_' + str(l), conv)
             if args_dict['pooling'][l] > 1:
-                self.module_list.add_module('pooling_' + str(l), nn.MaxPool2d(kernel_size=args_dict['pooling'][l]))
+                self.module_list.add_module('pooling_' + str(l), MaxPool2d(kernel_size=args_dict['pooling'][l]))
             if l < self.num_layers - 1:
                 self.module_list.add_module('relu_' + str(l), nn.ReLU())
                 if args_dict['dropout'] > 0.:
@@ -223,7 +235,7 @@ class ScalogramEncoderBlock(nn.Module):
             if args_dict['batch_norm']:
                 self.main_modules.append(nn.BatchNorm2d(c_out))
             if args_dict['pooling_' + tag] > 1:
-                self.main_modules.append(nn.MaxPool2d(kernel_size=args_dict['pooling_' + tag], ceil_mode=ceil_pooling))
+                self.main_modules.append(MaxPool2d(kernel_size=args_dict['pooling_' + tag], ceil_mode=ceil_pooling))
             self.main_modules.append(nn.ReLU())
             self.main_modules.append(ActivationWriter(register=activation_register,
                                                       name=self.name + '_main_conv_' + tag))
@@ -232,7 +244,7 @@ class ScalogramEncoderBlock(nn.Module):
             self.residual_modules = nn.ModuleList()
             stride_pool = args_dict['stride_1'] * args_dict['stride_2'] * args_dict['pooling_1'] * args_dict['pooling_2']
             if stride_pool > 1:
-                self.residual_modules.append(nn.MaxPool2d(kernel_size=stride_pool, ceil_mode=True))
+                self.residual_modules.append(MaxPool2d(kernel_size=stride_pool, ceil_mode=True))
             if args_dict['in_channels'] != args_dict['out_channels']:
                 self.residual_modules.append(Conv2d(args_dict['in_channels'], args_dict['out_channels'], 1,
                                                     padding=args_dict['padding_1'] + args_dict['padding_2'],

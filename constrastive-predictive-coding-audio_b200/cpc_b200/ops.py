@@ -285,6 +285,58 @@ def bn_relu(x, bn, residual=None, res_off=(0, 0), relu=True, outer_relu=False):
 
 
 # --------------------------------------------------------------------------------------------------
+# non-overlapping max pooling
+# --------------------------------------------------------------------------------------------------
+
+def _pool_params(x_shape, kernel, ceil_mode):
+    p = _lib.PoolParams()
+    p.batch, p.channels, p.h_in, p.w_in = x_shape
+    p.kernel, p.ceil_mode = int(kernel), int(bool(ceil_mode))
+    p.h_out = -(-p.h_in // kernel) if ceil_mode else p.h_in // kernel
+    p.w_out = -(-p.w_in // kernel) if ceil_mode else p.w_in // kernel
+    return p
+
+
+class _MaxPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, ceil_mode):
+        _require_cuda(x)
+        lib = _lib.load()
+        x = x.contiguous()
+        if x.dtype != torch.float32 or x.dim() != 4:
+            raise _lib.CpcError("max_pool2d expects a 4-d fp32 tensor")
+        p = _pool_params(tuple(x.shape), kernel, ceil_mode)
+        if p.h_out <= 0 or p.w_out <= 0:
+            raise ValueError("max_pool2d output would be empty for input %s, kernel %d" % (tuple(x.shape), kernel))
+        y = torch.empty((p.batch, p.channels, p.h_out, p.w_out), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _call("cpc_maxpool_fwd b%d %dx%dx%d k%d" % (p.batch, p.channels, p.h_in, p.w_in, kernel), 0.0,
+                  lib.cpc_maxpool_fwd, _ptr(x), _ptr(y), ctypes.byref(p), _stream(), nbytes=4.0 * (x.numel() + y.numel()))
+        ctx.cfg = (tuple(x.shape), kernel, ceil_mode)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        lib = _lib.load()
+        x_shape, kernel, ceil_mode = ctx.cfg
+        p = _pool_params(x_shape, kernel, ceil_mode)
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _call("cpc_maxpool_bwd b%d %dx%dx%d k%d" % (p.batch, p.channels, p.h_in, p.w_in, kernel), 0.0,
+                  lib.cpc_maxpool_bwd, _ptr(x), _ptr(dy), _ptr(dx), ctypes.byref(p), _stream(),
+                  nbytes=4.0 * (2 * x.numel() + dy.numel()))
+        return dx, None, None
+
+
+def max_pool2d(x, kernel, ceil_mode=False):
+    """nn.MaxPool2d(kernel_size=kernel, ceil_mode=ceil_mode) (stride = kernel, no padding) on the B200 kernels."""
+    return _MaxPoolFunction.apply(x, int(kernel), bool(ceil_mode))
+
+
+# --------------------------------------------------------------------------------------------------
 # InfoNCE
 # --------------------------------------------------------------------------------------------------
 

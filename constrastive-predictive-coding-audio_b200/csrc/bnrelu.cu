@@ -63,14 +63,14 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return r;
 }
 
-// grid (segments of one plane, B*C).  sums[c*2 + {0,1}] += sum x, sum x^2 (double).
+// grid (B*C planes, segments of one plane).  sums[c*2 + {0,1}] += sum x, sum x^2 (double).
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
                                                              int C, int HW) {
     __shared__ double red[BN_THREADS / 32];
-    const int plane = blockIdx.y;
+    const int plane = blockIdx.x;
     const int c = plane % C;
     const float* px = x + (size_t)plane * HW;
-    const int i0 = blockIdx.x * BN_SEG + threadIdx.x;
+    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
@@ -116,13 +116,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ affine,
                                                              const float* __restrict__ res, float* __restrict__ out,
                                                              BnGeom g) {
-    const int plane = blockIdx.y;
+    const int plane = blockIdx.x;
     const int c = plane % g.C;
     const float sc = __ldg(affine + 2 * c), sh = __ldg(affine + 2 * c + 1);
     const float* px = x + (size_t)plane * g.HW;
     float* po = out + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
-    const int i0 = blockIdx.x * BN_SEG + threadIdx.x;
+    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
         const int i = i0 + u * BN_THREADS;
@@ -160,14 +160,14 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
                                                                   const float* __restrict__ res, double* __restrict__ sums2,
                                                                   BnGeom g) {
     __shared__ double red[BN_THREADS / 32];
-    const int plane = blockIdx.y;
+    const int plane = blockIdx.x;
     const int c = plane % g.C;
     const float mean = __ldg(save_mean + c), rstd = __ldg(save_rstd + c);
     const float gam = gamma ? __ldg(gamma + c) : 1.f, bet = beta ? __ldg(beta + c) : 0.f;
     const float* px = x + (size_t)plane * g.HW;
     const float* pd = dout + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
-    const int i0 = blockIdx.x * BN_SEG + threadIdx.x;
+    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
@@ -203,12 +203,12 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                  float* __restrict__ d_res, BnGeom g, double count,
                                                                  int training) {
-    const int plane = blockIdx.y;
+    const int plane = blockIdx.x;
     const int c = plane % g.C;
     const float mean = __ldg(save_mean + c), rstd = __ldg(save_rstd + c);
     const float gam = gamma ? __ldg(gamma + c) : 1.f, bet = beta ? __ldg(beta + c) : 0.f;
     const double sg = sums2[2 * c], sgx = sums2[2 * c + 1];
-    if (plane < g.C && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (plane < g.C && blockIdx.y == 0 && threadIdx.x == 0) {
         if (dbeta) dbeta[c] = (float)sg;
         if (dgamma) dgamma[c] = (float)sgx;
     }
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     const size_t roff = (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row;
     const float* pr = res ? res + roff : nullptr;
     float* pdr = d_res ? d_res + roff : nullptr;
-    const int i0 = blockIdx.x * BN_SEG + threadIdx.x;
+    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
         const int i = i0 + u * BN_THREADS;
@@ -263,7 +263,7 @@ extern "C" int cpc_bn_relu_fwd(const float* x, const float* gamma, const float* 
     BnGeom g = bn_geom(p);
     double* sums = reinterpret_cast<double*>(workspace);
     float* affine = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(sizeof(double) * 2 * (size_t)g.C, 256));
-    const dim3 grid(ceil_div(g.HW, BN_SEG), g.B * g.C);
+    const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
     int launches = 2;
     if (p->training) {
         if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)g.C, s) != cudaSuccess) return CPC_ERR_CUDA;
@@ -301,7 +301,7 @@ extern "C" int cpc_bn_relu_bwd(const float* dout, const float* x, const float* g
     if (d_residual && crop &&
         cudaMemsetAsync(d_residual, 0, sizeof(float) * (size_t)g.B * g.C * g.RH * g.RW, s) != cudaSuccess)
         return CPC_ERR_CUDA;
-    const dim3 grid(ceil_div(g.HW, BN_SEG), g.B * g.C);
+    const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
     bn_bwd_reduce_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g);
     CPC_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx, dgamma,

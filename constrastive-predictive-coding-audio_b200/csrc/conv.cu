@@ -242,9 +242,9 @@ constexpr int DB_THREADS = 256;
 constexpr int DB_PER_THREAD = 16;
 __global__ void __launch_bounds__(DB_THREADS) conv_dbias_kernel(const float* __restrict__ dy, float* __restrict__ dbias,
                                                                int Cout, int ohow) {
-    const int plane = blockIdx.y;
+    const int plane = blockIdx.x;
     const float* p = dy + (size_t)plane * ohow;
-    const int i0 = blockIdx.x * (DB_THREADS * DB_PER_THREAD) + threadIdx.x;
+    const int i0 = blockIdx.y * (DB_THREADS * DB_PER_THREAD) + threadIdx.x;
     float s = 0.f;
 #pragma unroll
     for (int u = 0; u < DB_PER_THREAD; ++u) {
@@ -321,7 +321,7 @@ extern "C" int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const 
 
 static int launch_dbias(const float* dy, float* dbias, const ConvGeom& g, cudaStream_t s) {
     if (cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)g.Cout, s) != cudaSuccess) return CPC_ERR_CUDA;
-    const dim3 grid(ceil_div(g.ohow, DB_THREADS * DB_PER_THREAD), g.B * g.Cout);
+    const dim3 grid(g.B * g.Cout, ceil_div(g.ohow, DB_THREADS * DB_PER_THREAD));
     conv_dbias_kernel<<<grid, DB_THREADS, 0, s>>>(dy, dbias, g.Cout, g.ohow);
     CPC_LAUNCH_CHECK();
     count_launch();

@@ -40,6 +40,7 @@ struct UmmaConv {
     int h_mul, tap_h_mul, h_off;         // source row = h_mul*ph + tap_h_mul*i + h_off
     int out_H, out_W, oh_mul, oh_off, ow_mul, ow_off;        // output pixel = (oh_mul*ph + oh_off, ow_mul*pw + ow_off)
     int planes;                          // 2 = fp32-faithful split, 1 = bf16
+    int srcH;                            // rows of the source tensor (taps landing outside are all-zero)
     int relu, stages;
     const float* bias;
     float* y;
@@ -118,6 +119,21 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 }
 
 // ---- the GEMM kernel ----------------------------------------------------------------------------------
+// A K chunk contributes nothing when every tap in it reads a source row outside [0, srcH) for both atoms of the
+// tile (vertical zero padding, or the empty parts of a data gradient).  Chunk 0 always runs: it initialises the
+// accumulator.  Producer and MMA issuer evaluate the same predicate.
+__device__ __forceinline__ bool umma_chunk_live(const UmmaConv& p, int q, int row0, int row1) {
+    if (q == 0) return true;
+    int t_lo, t_hi;
+    if (p.cin_eff == KCHUNK) { t_lo = q / p.cin_chunks; t_hi = t_lo + 1; }
+    else { t_lo = q * p.tpc; t_hi = min(t_lo + p.tpc, p.ntaps); }
+    for (int tap = t_lo; tap < t_hi; ++tap) {
+        const int d = (tap / p.tw) * p.tap_h_mul;
+        if ((unsigned)(row0 + d) < (unsigned)p.srcH || (unsigned)(row1 + d) < (unsigned)p.srcH) return true;
+    }
+    return false;
+}
+
 struct __align__(8) UmmaBarriers {
     uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -163,6 +179,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                     aoh[a] = (row - ab[a] * p.PH) * p.h_mul + p.h_off;
                 }
                 for (int q = 0; q < p.n_chunks; ++q) {
+                    if (!umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     uint8_t* st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
@@ -201,7 +218,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                 mbar_wait(&bars->acc_empty[buf], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256;
+                int aoh[2];
+                {
+                    const int mtile = tile / p.n_ntiles;
+                    for (int a = 0; a < 2; ++a) {
+                        const int row = (mtile * 2 + a) / p.AW;
+                        aoh[a] = (row - (row / p.PH) * p.PH) * p.h_mul + p.h_off;
+                    }
+                }
                 for (int q = 0; q < p.n_chunks; ++q) {
+                    if (!umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -361,7 +387,7 @@ static int run_problem(const ConvProblem& c, const float* w, const float* bias, 
     k.cin_chunks = u.cin_chunks; k.n_chunks = u.n_chunks;
     k.h_mul = c.h_mul; k.tap_h_mul = c.tap_h_mul; k.h_off = c.h_off;
     k.out_H = c.out_H; k.out_W = c.out_W; k.oh_mul = c.oh_mul; k.oh_off = c.oh_off; k.ow_mul = c.ow_mul; k.ow_off = c.ow_off;
-    k.planes = u.planes; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out;
+    k.planes = u.planes; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out; k.srcH = c.srcH;
     if (cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int n_tiles = ((k.n_atoms + 1) / 2) * k.n_ntiles;

@@ -1,0 +1,107 @@
+// Non-overlapping max pooling (kernel = stride, no padding, optional ceil mode), forward and backward.
+// Replaces nn.MaxPool2d on the residual branch of ScalogramEncoderBlock (scalogram_model.py:434-441,
+// MaxPool2d(kernel_size = stride_pool, ceil_mode = True)) and the main-path poolings (:402-403, :424-425),
+// plus their autograd (max_pool2d_with_indices_backward).  No index tensor is kept: the backward pass
+// re-derives the arg-max from x (first maximum in row-major window order, the tie rule of the reference's
+// ATen kernels), so it streams x and dy once and writes dx once.
+#include "common.cuh"
+
+namespace cpc {
+
+struct PoolGeom {
+    int H, W, OH, OW, k;
+    FastDiv d_ow;
+};
+
+// one thread per output window; grid (B*C planes, window chunks of one plane)
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, PoolGeom g) {
+    const int plane = blockIdx.x;
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= g.OH * g.OW) return;
+    int oh, ow;
+    g.d_ow.divmod(idx, oh, ow);
+    const float* px = x + (size_t)plane * g.H * g.W;
+    const int h0 = oh * g.k, w0 = ow * g.k;
+    const int h1 = min(h0 + g.k, g.H), w1 = min(w0 + g.k, g.W);
+    float m = -INFINITY;
+    for (int h = h0; h < h1; ++h)
+        for (int w = w0; w < w1; ++w) {
+            const float v = __ldg(px + (size_t)h * g.W + w);
+            if (v > m || v != v) m = v;
+        }
+    y[(size_t)plane * g.OH * g.OW + idx] = m;
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ dx, PoolGeom g) {
+    const int plane = blockIdx.x;
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= g.OH * g.OW) return;
+    int oh, ow;
+    g.d_ow.divmod(idx, oh, ow);
+    const float* px = x + (size_t)plane * g.H * g.W;
+    float* pdx = dx + (size_t)plane * g.H * g.W;
+    const int h0 = oh * g.k, w0 = ow * g.k;
+    const int h1 = min(h0 + g.k, g.H), w1 = min(w0 + g.k, g.W);
+    float m = -INFINITY;
+    int ah = h0, aw = w0;
+    for (int h = h0; h < h1; ++h)
+        for (int w = w0; w < w1; ++w) {
+            const float v = __ldg(px + (size_t)h * g.W + w);
+            if (v > m || v != v) { m = v; ah = h; aw = w; }
+        }
+    const float gval = __ldg(dy + (size_t)plane * g.OH * g.OW + idx);
+    for (int h = h0; h < h1; ++h)
+        for (int w = w0; w < w1; ++w) pdx[(size_t)h * g.W + w] = (h == ah && w == aw) ? gval : 0.f;
+}
+
+static int pool_validate(const cpc_pool_params* p) {
+    if (!p) return CPC_ERR_NULL;
+    if (p->batch <= 0 || p->channels <= 0 || p->h_in <= 0 || p->w_in <= 0 || p->kernel <= 0) return CPC_ERR_BAD_SHAPE;
+    const int oh = p->ceil_mode ? ceil_div(p->h_in, p->kernel) : p->h_in / p->kernel;
+    const int ow = p->ceil_mode ? ceil_div(p->w_in, p->kernel) : p->w_in / p->kernel;
+    if (oh <= 0 || ow <= 0 || oh != p->h_out || ow != p->w_out) return CPC_ERR_BAD_SHAPE;
+    if ((int64_t)p->batch * p->channels > (1ll << 30) || (int64_t)p->h_out * p->w_out > 65535ll * 256) return CPC_ERR_BAD_SHAPE;
+    return CPC_OK;
+}
+
+static PoolGeom pool_geom(const cpc_pool_params* p) {
+    PoolGeom g;
+    g.H = p->h_in; g.W = p->w_in; g.OH = p->h_out; g.OW = p->w_out; g.k = p->kernel;
+    g.d_ow = FastDiv(g.OW);
+    return g;
+}
+
+}  // namespace cpc
+
+using namespace cpc;
+
+extern "C" int cpc_maxpool_fwd(const float* x, float* y, const cpc_pool_params* p, void* stream) {
+    int st = pool_validate(p);
+    if (st != CPC_OK) return st;
+    if (!x || !y) return CPC_ERR_NULL;
+    if ((st = check_device()) != CPC_OK) return st;
+    PoolGeom g = pool_geom(p);
+    const int planes = p->batch * p->channels;
+    maxpool_fwd_kernel<<<dim3(planes, ceil_div(g.OH * g.OW, 256)), 256, 0, (cudaStream_t)stream>>>(x, y, g);
+    CPC_LAUNCH_CHECK();
+    count_launch();
+    return CPC_OK;
+}
+
+extern "C" int cpc_maxpool_bwd(const float* x, const float* dy, float* dx, const cpc_pool_params* p, void* stream) {
+    int st = pool_validate(p);
+    if (st != CPC_OK) return st;
+    if (!x || !dy || !dx) return CPC_ERR_NULL;
+    if ((st = check_device()) != CPC_OK) return st;
+    PoolGeom g = pool_geom(p);
+    const int planes = p->batch * p->channels;
+    cudaStream_t s = (cudaStream_t)stream;
+    // floor mode can leave trailing rows / columns outside every window: they get zero gradient
+    if (g.OH * g.k < g.H || g.OW * g.k < g.W)
+        if (cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)planes * g.H * g.W, s) != cudaSuccess) return CPC_ERR_CUDA;
+    maxpool_bwd_kernel<<<dim3(planes, ceil_div(g.OH * g.OW, 256)), 256, 0, s>>>(x, dy, dx, g);
+    CPC_LAUNCH_CHECK();
+    count_launch();
+    return CPC_OK;
+}

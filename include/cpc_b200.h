@@ -156,6 +156,22 @@ int cpc_bn_relu_bwd(const float* dout, const float* x, const float* gamma, const
                     float* d_residual, const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 2c. Non-overlapping max pooling (kernel = stride, no padding), forward and backward.
+ *    Replaces nn.MaxPool2d on the residual branch (scalogram_model.py:434-441, ceil_mode=True) and the main-path
+ *    poolings (:402-403, :424-425) and max_pool2d_with_indices_backward.  x / dx (B, C, h_in, w_in),
+ *    y / dy (B, C, h_out, w_out); h_out = ceil_mode ? ceil(h_in / kernel) : floor(h_in / kernel), same for w.
+ *    The backward pass re-derives the arg-max from x (first maximum in row-major window order).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cpc_pool_params {
+    int32_t batch, channels, h_in, w_in, h_out, w_out;
+    int32_t kernel;
+    int32_t ceil_mode;
+} cpc_pool_params;
+
+int cpc_maxpool_fwd(const float* x, float* y, const cpc_pool_params* p, void* stream);
+int cpc_maxpool_bwd(const float* x, const float* dy, float* dx, const cpc_pool_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * 3. InfoNCE scoring + loss, forward and backward, scores never written to HBM.
  *    Replaces score_function + the loss block of ContrastiveEstimationTrainer.train
  *    (contrastive_estimation_training.py:12-22, 106-122, 141, 166) and its autograd.

@@ -343,6 +343,27 @@ def test_residual_encoder_matches_reference_golden(cpc):
 
 
 # ---------------------------------------------------------------------------------------------------
+# max pooling
+# ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape,k,ceil", [((2, 3, 9, 11), 2, True), ((2, 3, 9, 11), 2, False), ((1, 5, 12, 12), 3, True),
+                                          ((3, 2, 7, 5), 4, True), ((2, 4, 127, 314), 2, True), ((1, 2, 6, 8), 1, False)])
+def test_max_pool_matches_torch_reference(cpc, shape, k, ceil):
+    """nn.MaxPool2d(k, ceil_mode) forward / backward incl. ties (integer-valued input) -- bit exact."""
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randint(-3, 4, shape, generator=gen).float()          # many ties: first maximum must win
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, k, ceil_mode=ceil)
+    gy = torch.randn(yr.shape, generator=gen)
+    (yr * gy).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    yg = cpc.ops.max_pool2d(xg, k, ceil)
+    (yg * gy.to(DEV)).sum().backward()
+    assert torch.equal(yg.cpu(), yr)
+    assert torch.equal(xg.grad.cpu(), xr.grad)
+
+
+# ---------------------------------------------------------------------------------------------------
 # fused BatchNorm + ReLU (+ cropped residual + ReLU)
 # ---------------------------------------------------------------------------------------------------
 

@@ -30,6 +30,16 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
 int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
                       size_t workspace_bytes, cudaStream_t s);
 
+// conv_smallk.cu: direct kernels for C_in * kh * kw <= 36 (forward and weight gradient)
+bool smallk_eligible(const cpc_conv_params* p, int which);
+int smallk_launch(int which, const float* x, const float* w, const float* bias, const float* dy, float* out,
+                  const cpc_conv_params* p, cudaStream_t s);
+static bool smallk_path(const cpc_conv_params* p, int which) {
+    const char* e = std::getenv("CPC_NO_SMALLK_CONV");          // A/B switch: keep tiny-K convs on the tiled kernels
+    if (e && e[0] == '1') return false;
+    return smallk_eligible(p, which);
+}
+
 // conv_tall128.cu: row-streaming kernels for kh x 1, stride-1 convolutions with 128 output channels
 size_t tall128_workspace(const cpc_conv_params* p, int which);
 bool tall128_eligible(const cpc_conv_params* p, int which);
@@ -268,6 +278,7 @@ using namespace cpc;
 
 extern "C" size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which) {
     if (validate(p) != CPC_OK) return 0;
+    if ((which == 0 || which == 2) && smallk_path(p, which)) return 0;
     if (which >= 0 && which <= 2 && tall_path(p, which))
         return tall_path(p, which) == 1 ? tall_conv_workspace(p, which) : tall128_workspace(p, which);
     if ((which == 0 || which == 1) && tensor_core_path(p, which)) return umma_conv_workspace(p, which);
@@ -281,6 +292,7 @@ extern "C" int cpc_conv_fwd(const float* x, const float* w, const float* bias, f
     if (st != CPC_OK) return st;
     if (!x || !w || !y) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
+    if (smallk_path(p, 0)) return smallk_launch(0, x, w, bias, nullptr, y, p, (cudaStream_t)stream);
     if (const int tp = tall_path(p, 0))
         return tp == 1 ? tall_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream)
                        : tall128_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -336,6 +348,11 @@ extern "C" int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float*
     if ((st = check_device()) != CPC_OK) return st;
     ConvGeom g = make_geom(p);
     cudaStream_t s = (cudaStream_t)stream;
+    if (smallk_path(p, 2)) {
+        st = smallk_launch(2, x, nullptr, nullptr, dy, dw, p, s);
+        if (st != CPC_OK) return st;
+        return dbias ? launch_dbias(dy, dbias, g, s) : CPC_OK;
+    }
     if (const int tp = tall_path(p, 2)) {
         st = tp == 1 ? tall_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s)
                      : tall128_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s);

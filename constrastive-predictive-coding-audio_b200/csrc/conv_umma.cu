@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 // A K chunk contributes nothing when every tap in it reads a source row outside [0, srcH) for both atoms of the
 // tile (vertical zero padding, or the empty parts of a data gradient).  Chunk 0 always runs: it initialises the
 // accumulator.  Producer and MMA issuer evaluate the same predicate.
+// true when some tap of the tile can land outside the source (only then are chunks tested one by one)
+__device__ __forceinline__ bool umma_tile_may_skip(const UmmaConv& p, int row0, int row1) {
+    const int span = (p.th - 1) * p.tap_h_mul;
+    const int lo = min(min(row0, row1), min(row0, row1) + span), hi = max(max(row0, row1), max(row0, row1) + span);
+    return lo < 0 || hi >= p.srcH;
+}
 __device__ __forceinline__ bool umma_chunk_live(const UmmaConv& p, int q, int row0, int row1) {
     if (q == 0) return true;
     int t_lo, t_hi;
@@ -178,8 +184,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                     ab[a] = row / p.PH;
                     aoh[a] = (row - ab[a] * p.PH) * p.h_mul + p.h_off;
                 }
+                const bool may_skip = umma_tile_may_skip(p, aoh[0], aoh[1]);
                 for (int q = 0; q < p.n_chunks; ++q) {
-                    if (!umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
+                    if (may_skip && !umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     uint8_t* st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
@@ -226,8 +233,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                         aoh[a] = (row - (row / p.PH) * p.PH) * p.h_mul + p.h_off;
                     }
                 }
+                const bool may_skip = umma_tile_may_skip(p, aoh[0], aoh[1]);
                 for (int q = 0; q < p.n_chunks; ++q) {
-                    if (!umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
+                    if (may_skip && !umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);

@@ -221,6 +221,9 @@ def run_ours(args):
     audio_s_step = world * b * length / SR
     value = audio_s_step / (ms_dev * 1e-3)
     e2e_value = audio_s_step / (ms_e2e * 1e-3)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = measured_peaks()

@@ -409,6 +409,28 @@ def infonce(pred, targets, all_steps, kind="linear", regularization=0.0, precisi
                                   precision or _default_precision)
 
 
+def infonce_validate(pred, targets, all_steps, kind="linear", precision=None):
+    """Validation metrics of one batch (contrastive_estimation_training.py:224-247) without materialising the
+    (B,K,B,K) score tensor: returns (per_step_losses (K), per_step_accuracy (K), mean_score ()).  The per-step
+    losses reproduce the reference's re-viewed ("scrambled") noise term in per-step mode."""
+    _require_cuda(pred, targets)
+    lib = _lib.load()
+    if pred.dtype != torch.float32 or targets.dtype != torch.float32:
+        raise _lib.CpcError("infonce_validate expects fp32 tensors")
+    b, k, e = pred.shape
+    if tuple(targets.shape) != (b, e, k):
+        raise ValueError("targets must be (B, E, K) = %s, got %s" % ((b, e, k), tuple(targets.shape)))
+    pred = pred.detach().contiguous()
+    targets = targets.detach()
+    p = _nce_params(pred, targets, all_steps, kind, 0.0, precision or _default_precision)
+    metrics = torch.empty(2 * k + 1, dtype=torch.float32, device=pred.device)
+    ws = _workspace(lib.cpc_infonce_workspace_bytes(ctypes.byref(p), 2), pred.device)
+    with torch.cuda.device(pred.device):
+        _call(_nce_key("cpc_infonce_validate", p), _nce_flops(p), lib.cpc_infonce_validate, _ptr(pred), _ptr(targets),
+              _ptr(metrics), ctypes.byref(p), _ptr(ws), ws.numel(), _stream())
+    return metrics[:k], metrics[k:2 * k], metrics[2 * k]
+
+
 # --------------------------------------------------------------------------------------------------
 # CQT front end (no autograd: the filterbank is frozen in training, constant_q_transform.py:145)
 # --------------------------------------------------------------------------------------------------

@@ -153,7 +153,7 @@ class ContrastiveEstimationTrainer:
         if reducer is not None:
             reducer.remove()
 
-    # -- validation (scores materialised with torch ops; fused metrics kernel is a 'next' row) --------
+    # -- validation: fused metrics kernel for the known score functions, literal block otherwise --------
     def validate(self, batch_size=64, num_workers=1, max_steps=None):
         if self.validation_set is None:
             print("No validation set")
@@ -177,6 +177,16 @@ class ContrastiveEstimationTrainer:
                 if self.preprocessing is not None:
                     batch = self.preprocessing(batch)
                 predicted_z, targets, _, _ = self.model(batch)
+                kind = _FUSED_KINDS.get(self.score_function)
+                if kind is not None and predicted_z.is_cuda:
+                    losses, accuracy, mean_score = ops.infonce_validate(predicted_z, targets,
+                                                                        self.score_over_all_timesteps, kind)
+                    total_losses += losses
+                    total_accurate += accuracy
+                    total_score += mean_score.item()
+                    if step + 1 >= max_steps:
+                        break
+                    continue
                 scores = self.score_function(predicted_z, targets)
                 if self.score_over_all_timesteps:
                     noise = torch.logsumexp(scores.reshape(-1, batch_size, k), dim=0)

@@ -129,7 +129,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 __global__ void __launch_bounds__(TILE_THREADS) nce_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Z,
                                                               NceGeom g, float* __restrict__ part_m,
                                                               float* __restrict__ part_s, float* __restrict__ diag,
-                                                              float* __restrict__ cta) {
+                                                              float* __restrict__ cta, float* __restrict__ rowp_m,
+                                                              int* __restrict__ rowp_i) {
     __shared__ TileSmem sm;
     __shared__ float Ss[TILE][TILE + 1];
     __shared__ float red[8];
@@ -173,6 +174,29 @@ __global__ void __launch_bounds__(TILE_THREADS) nce_fwd_kernel(const float* __re
                 part_m[o] = m;
                 part_s[o] = e;
             }
+        }
+        if (rowp_m != nullptr) {
+            // validation accuracy: per row, the best column of this column tile (first maximum wins)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Ss[tx * 4 + i][ty * 4 + j] = s[i][j];      // -inf outside the problem
+            __syncthreads();
+            if (threadIdx.x < TILE) {
+                const int lr = threadIdx.x, r = row0 + lr;
+                if (lr < g.tmr && r < g.R) {
+                    float best = -INFINITY;
+                    int arg = 0;
+                    for (int cc = 0; cc < TILE; ++cc) {
+                        const float v = Ss[lr][cc];
+                        if (v > best) { best = v; arg = col0 + cc; }
+                    }
+                    const size_t o = ((size_t)blockIdx.x * g.nprob + prob) * g.R + r;
+                    rowp_m[o] = best;
+                    rowp_i[o] = arg;
+                }
+            }
+            __syncthreads();
         }
         if (g.all && g.lambda != 0.f) {
             // regulariser: rows of one item d are K consecutive rows, whole groups live in this tile
@@ -248,6 +272,47 @@ __global__ void __launch_bounds__(256) nce_final_kernel(const float* __restrict_
         out[2] = loss0;
         out[3] = (float)(sm / nscores);
     }
+}
+
+// Validation metrics (contrastive_estimation_training.py:224-247), one block.
+//   metrics[0..K)   per-step losses  -mean_b(valid[b, c] - noise[b, c]); in per-step mode noise is the reference's
+//                   re-viewed (scrambled) array: noise[b, c] = lse[flat = b*K + c], flat = k*B + t  (Appendix B)
+//   metrics[K..2K)  per-step accuracy = #(arg-max over targets hits the own target) / n, n = B*K (all-steps) or B
+//   metrics[2K]     mean score
+__global__ void __launch_bounds__(256) nce_validate_final_kernel(const float* __restrict__ lse, const float* __restrict__ diag,
+                                                                const float* __restrict__ rowp_m,
+                                                                const int* __restrict__ rowp_i, int ncoltiles,
+                                                                const float* __restrict__ out4, NceGeom g,
+                                                                float* __restrict__ metrics) {
+    __shared__ float acc_loss[TILE], acc_hit[TILE];
+    for (int k = threadIdx.x; k < g.K; k += blockDim.x) { acc_loss[k] = 0.f; acc_hit[k] = 0.f; }
+    __syncthreads();
+    for (int f = threadIdx.x; f < g.ncols; f += blockDim.x) {
+        int kk;
+        float term;
+        if (g.all) { kk = f % g.K; term = lse[f] - diag[f]; }                     // f = t*K + k'
+        else { const int b = f / g.K; kk = f - b * g.K; term = lse[f] - diag[kk * g.B + b]; }
+        atomicAdd(&acc_loss[kk], term);
+    }
+    const int nrows = g.nprob * g.R;
+    for (int idx = threadIdx.x; idx < nrows; idx += blockDim.x) {
+        const int prob = idx / g.R, r = idx - prob * g.R;
+        float best = -INFINITY;
+        int arg = -1;
+        for (int t = 0; t < ncoltiles; ++t) {
+            const size_t o = ((size_t)t * g.nprob + prob) * g.R + r;
+            const float v = rowp_m[o];
+            if (v > best) { best = v; arg = rowp_i[o]; }
+        }
+        if (arg == r) atomicAdd(&acc_hit[g.all ? r % g.K : prob], 1.f);
+    }
+    __syncthreads();
+    const float n = g.all ? (float)g.B * (float)g.K : (float)g.B;
+    for (int k = threadIdx.x; k < g.K; k += blockDim.x) {
+        metrics[k] = acc_loss[k] / (float)g.B;
+        metrics[g.K + k] = acc_hit[k] / n;
+    }
+    if (threadIdx.x == 0) metrics[2 * g.K] = out4[3];
 }
 
 // ---- backward -----------------------------------------------------------------------------------
@@ -390,8 +455,13 @@ using namespace cpc;
 
 extern "C" size_t cpc_infonce_workspace_bytes(const cpc_infonce_params* p, int which) {
     if (nce_validate(p) != CPC_OK) return 0;
-    if (which != 0) return 0;
-    return nce_ws(nce_geom(p), nullptr).bytes;
+    if (which == 1) return 0;
+    const NceGeom g = nce_geom(p);
+    const size_t fwd = nce_ws(g, nullptr).bytes;
+    if (which == 0) return fwd;
+    // validate: forward scratch + lse + 4 scalars + per-(column tile, row) arg-max partials
+    const size_t rows = (size_t)ceil_div(g.C, TILE) * g.nprob * g.R;
+    return fwd + align_up(sizeof(float) * (size_t)g.ncols, 256) + 256 + 2 * align_up(sizeof(float) * rows, 256);
 }
 
 extern "C" int cpc_infonce_fwd(const float* pred, const float* targets, float* out, float* lse,
@@ -405,7 +475,7 @@ extern "C" int cpc_infonce_fwd(const float* pred, const float* targets, float* o
     if ((st = check_device()) != CPC_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(ceil_div(g.C, TILE), g.nrowtiles);
-    nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta);
+    nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta, nullptr, nullptr);
     CPC_LAUNCH_CHECK();
     nce_combine_kernel<<<w.nblk, 256, 0, s>>>(w.part_m, w.part_s, w.diag, lse, w.blk, g.ncols, g.nrowtiles);
     CPC_LAUNCH_CHECK();
@@ -437,6 +507,34 @@ extern "C" int cpc_infonce_bwd(const float* pred, const float* targets, const fl
 
 extern "C" int cpc_infonce_validate(const float* pred, const float* targets, float* metrics,
                                     const cpc_infonce_params* p, void* workspace, size_t workspace_bytes, void* stream) {
-    (void)pred; (void)targets; (void)metrics; (void)p; (void)workspace; (void)workspace_bytes; (void)stream;
-    return CPC_ERR_UNSUPPORTED;
+    int st = nce_validate(p);
+    if (st != CPC_OK) return st;
+    if (!pred || !targets || !metrics) return CPC_ERR_NULL;
+    const size_t need = cpc_infonce_workspace_bytes(p, 2);
+    if (!workspace || workspace_bytes < need) return CPC_ERR_WORKSPACE;
+    if ((st = check_device()) != CPC_OK) return st;
+    NceGeom g = nce_geom(p);
+    g.lambda = 0.f;                                            // validation reports the un-regularised loss
+    NceWs w = nce_ws(g, workspace);
+    char* base = reinterpret_cast<char*>(workspace) + w.bytes;
+    float* lse = reinterpret_cast<float*>(base);
+    base += align_up(sizeof(float) * (size_t)g.ncols, 256);
+    float* out4 = reinterpret_cast<float*>(base);
+    base += 256;
+    const int ncoltiles = ceil_div(g.C, TILE);
+    const size_t rows = (size_t)ncoltiles * g.nprob * g.R;
+    float* rowp_m = reinterpret_cast<float*>(base);
+    int* rowp_i = reinterpret_cast<int*>(base + align_up(sizeof(float) * rows, 256));
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(ncoltiles, g.nrowtiles);
+    nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta, rowp_m, rowp_i);
+    CPC_LAUNCH_CHECK();
+    nce_combine_kernel<<<w.nblk, 256, 0, s>>>(w.part_m, w.part_s, w.diag, lse, w.blk, g.ncols, g.nrowtiles);
+    CPC_LAUNCH_CHECK();
+    nce_final_kernel<<<1, 256, 0, s>>>(w.blk, w.nblk, w.cta, w.ncta, g, out4);
+    CPC_LAUNCH_CHECK();
+    nce_validate_final_kernel<<<1, 256, 0, s>>>(lse, w.diag, rowp_m, rowp_i, ncoltiles, out4, g, metrics);
+    CPC_LAUNCH_CHECK();
+    count_launch(4);
+    return CPC_OK;
 }

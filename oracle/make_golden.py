@@ -251,6 +251,41 @@ def golden_infonce(ref):
     np.savez_compressed(os.path.join(OUT, "infonce.npz"), **out)
 
 
+def golden_validate(ref):
+    """The reference's own ContrastiveEstimationTrainer.validate() (contrastive_estimation_training.py:178-269) on
+    stored (pred, targets) pairs -> per-step losses, accuracies, mean score, MI bound."""
+    cet = ref["contrastive_estimation_training"]
+    out, cases = {}, []
+    g = torch.Generator().manual_seed(17)
+    idx = 0
+    for (b, k, e) in [(8, 12, 64), (16, 4, 40), (24, 16, 96)]:
+        for all_steps in (False, True):
+            for kind in ("linear", "softplus"):
+                pred = torch.randn(b, k, e, generator=g) * (2.5 / e ** 0.5)
+                tgt = torch.randn(b, e, k, generator=g)
+                # make some predictions actually hit their own target so that accuracies are not all ~1/n
+                for d in range(0, b, 2):
+                    pred[d] = pred[d] + 0.6 * tgt[d].t()
+                model = StoredPairModel(pred, tgt)
+                fn = cet.linear_score_function if kind == "linear" else cet.softplus_score_function
+                ds = ListDataset(torch.zeros(b, 4))
+                trainer = cet.ContrastiveEstimationTrainer(model=model, dataset=ds, validation_set=ds, device=None,
+                                                           score_over_all_timesteps=all_steps, score_function=fn,
+                                                           prediction_steps=k)
+                losses, acc, score, mi = trainer.validate(batch_size=b, num_workers=0, max_steps=1)
+                tag = "v%d" % idx
+                out[tag + ".pred"] = pred.numpy()
+                out[tag + ".tgt"] = tgt.numpy()
+                out[tag + ".losses"] = losses.detach().numpy()
+                out[tag + ".acc"] = acc.detach().numpy()
+                out[tag + ".score"] = np.array(float(score))
+                out[tag + ".mi"] = mi.detach().numpy()
+                cases.append({"tag": tag, "b": b, "k": k, "e": e, "all_steps": all_steps, "kind": kind})
+                idx += 1
+    out["cases"] = np.array(json.dumps(cases))
+    np.savez_compressed(os.path.join(OUT, "validate.npz"), **out)
+
+
 def golden_sampler(ref):
     ad = ref["audio_dataset"]
     out, cases = {}, []
@@ -300,6 +335,7 @@ def main():
     golden_infonce(ref)
     golden_trainer_raw(ref)
     golden_trainer_cqt(ref)
+    golden_validate(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

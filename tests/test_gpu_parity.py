@@ -475,6 +475,22 @@ def test_infonce_full_size_property(cpc):
     assert abs(loss.item() - math.log(b)) < 1e-3
 
 
+def test_infonce_validate_matches_reference_validate_golden(cpc):
+    """cpc_infonce_validate against the reference's own ContrastiveEstimationTrainer.validate() outputs."""
+    g = load_golden("validate.npz")
+    for c in json.loads(str(g["cases"])):
+        t = c["tag"]
+        pred = torch.from_numpy(g[t + ".pred"]).to(DEV)
+        tgt = torch.from_numpy(g[t + ".tgt"]).to(DEV)
+        losses, acc, score = cpc.ops.infonce_validate(pred, tgt, c["all_steps"], c["kind"])
+        scale = max(1.0, float(np.abs(g[t + ".losses"]).max()))
+        assert float((losses.cpu() - torch.from_numpy(g[t + ".losses"])).abs().max()) < TOL * scale, c
+        assert torch.equal(acc.cpu(), torch.from_numpy(g[t + ".acc"])), c          # counts / n: exact
+        assert abs(float(score) - float(g[t + ".score"])) < TOL * max(1.0, abs(float(g[t + ".score"]))), c
+        want = O.validation_metrics(pred.cpu(), tgt.cpu(), c["all_steps"], c["kind"])
+        assert rel_err(losses, want[0]) < TOL and torch.equal(acc.cpu(), want[1])
+
+
 # ---------------------------------------------------------------------------------------------------
 # whole training steps against the reference's own train()
 # ---------------------------------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 """CPU: pins oracle/cpc_oracle.py against the golden vectors the UNMODIFIED reference produced
 (oracle/make_golden.py).  The GPU parity tests then compare the CUDA path with this oracle."""
 import json
+import math
 import random
 
 import numpy as np
@@ -130,3 +131,17 @@ def test_sampler_bit_exact():
         else:
             first = O.file_batch_sampler(c["counts"], c["batch_size"], c["file_batch_size"], True, c["seed"])
             assert first == c["epochs"][0], c
+
+
+def test_validation_metrics_match_reference_validate():
+    """oracle.validation_metrics vs the reference's own validate() (contrastive_estimation_training.py:178-269)."""
+    g = load_golden("validate.npz")
+    for c in json.loads(str(g["cases"])):
+        t = c["tag"]
+        pred, tgt = torch.from_numpy(g[t + ".pred"]), torch.from_numpy(g[t + ".tgt"])
+        losses, acc, score = O.validation_metrics(pred, tgt, c["all_steps"], c["kind"])
+        assert torch.allclose(losses, torch.from_numpy(g[t + ".losses"]), rtol=1e-5, atol=1e-5), c
+        assert torch.equal(acc, torch.from_numpy(g[t + ".acc"])), c
+        assert abs(float(score) - float(g[t + ".score"])) < 1e-5 * max(1.0, abs(float(g[t + ".score"]))), c
+        n = c["b"] * c["k"] if c["all_steps"] else c["b"]
+        assert torch.allclose(math.log(n) - losses, torch.from_numpy(g[t + ".mi"]), rtol=1e-5, atol=1e-5), c

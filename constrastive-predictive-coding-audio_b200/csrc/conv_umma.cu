@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
     }
 }
 
-// host launcher shared with conv_tall.cu
+// host launcher shared with conv_tall.cu / conv_tall128.cu
 int pack_split_launch(const float* x, __nv_bfloat16* out, long rows, int W, int Wp, int planes, int nrep, int w_mul,
                       int rep_mul, int w_off, cudaStream_t s) {
     const long groups = rows * (Wp / 8);
@@ -359,12 +359,8 @@ static int run_problem(const ConvProblem& c, const float* w, const float* bias, 
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + u.act_bytes);
     const long rows = (long)B * c.in_ch * c.srcH;
     {
-        const long groups = rows * (u.Wp / 8);
-        int blocks = (int)((groups + 255) / 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        pack_split_kernel<<<blocks, 256, 0, s>>>(c.src, act, rows, c.srcW, u.Wp, u.planes, c.tm.tw, c.w_mul, c.rep_mul,
-                                                 c.w_off);
-        CPC_LAUNCH_CHECK();
+        if (pack_split_launch(c.src, act, rows, c.srcW, u.Wp, u.planes, c.tm.tw, c.w_mul, c.rep_mul, c.w_off, s) != CPC_OK)
+            return CPC_ERR_CUDA;
         const long wtotal = (long)u.n_chunks * c.out_ch * KCHUNK;
         int wblocks = (int)((wtotal + 255) / 256);
         if (wblocks > 148 * 8) wblocks = 148 * 8;
@@ -679,18 +675,10 @@ int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv
     const int B = p->batch;
     {
         const long rows_x = (long)B * p->c_in * p->h_in;
-        long groups = rows_x * (u.Wp_x / 8);
-        int blocks = (int)((groups + 255) / 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        pack_split_kernel<<<blocks, 256, 0, s>>>(x, xp, rows_x, p->w_in, u.Wp_x, u.planes, p->kw, p->stride_w, 1,
-                                                 -p->pad_left);
-        CPC_LAUNCH_CHECK();
+        if (pack_split_launch(x, xp, rows_x, p->w_in, u.Wp_x, u.planes, p->kw, p->stride_w, 1, -p->pad_left, s) != CPC_OK)
+            return CPC_ERR_CUDA;
         const long rows_dy = (long)B * p->c_out * p->h_out;
-        groups = rows_dy * (u.Wp_dy / 8);
-        blocks = (int)((groups + 255) / 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        pack_split_kernel<<<blocks, 256, 0, s>>>(dy, dyp, rows_dy, p->w_out, u.Wp_dy, u.planes, 1, 1, 0, 0);
-        CPC_LAUNCH_CHECK();
+        if (pack_split_launch(dy, dyp, rows_dy, p->w_out, u.Wp_dy, u.planes, 1, 1, 0, 0, s) != CPC_OK) return CPC_ERR_CUDA;
     }
     CUtensorMap tx, tdy;
     {

@@ -70,6 +70,11 @@ SIGNATURES = {
     "cpc_conv_fwd": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_dgrad": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_wgrad": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
+    "cpc_conv_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvParams), ctypes.c_int]),
+    "cpc_conv_pack": (ctypes.c_int, [_P, _P, ctypes.POINTER(ConvParams), ctypes.c_int, _P]),
+    "cpc_conv_fwd_ex": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, _P, ctypes.c_size_t, _P]),
+    "cpc_conv_dgrad_ex": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P, _P, ctypes.c_size_t, _P]),
+    "cpc_conv_wgrad_ex": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, _P, _P, ctypes.c_size_t, _P]),
     "cpc_bn_relu_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(BnParams)]),
     "cpc_bn_relu_fwd": (ctypes.c_int, [_P] * 9 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
     "cpc_bn_relu_bwd": (ctypes.c_int, [_P] * 11 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),

@@ -123,6 +123,18 @@ def _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, relu, prec
     return p
 
 
+def _pack_operand(lib, t, p, operand):
+    """bf16 hi/lo planes of a conv operand, packed once for every kernel that reads it (None when the
+    configuration has no tensor-core kernel that would use them)."""
+    nbytes = lib.cpc_conv_packed_bytes(ctypes.byref(p), operand)
+    if nbytes == 0:
+        return None
+    packed = torch.empty(int(nbytes), dtype=torch.uint8, device=t.device)
+    _call("cpc_conv_pack %s" % ("x" if operand == 0 else "dy"), 0.0, lib.cpc_conv_pack, _ptr(t), _ptr(packed), ctypes.byref(p),
+          operand, _stream(), nbytes=4.0 * t.numel() + float(nbytes))
+    return packed
+
+
 class _ConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad_top, pad_left, out_hw, relu, precision):
@@ -136,18 +148,21 @@ class _ConvFunction(torch.autograd.Function):
         y = torch.empty((x.shape[0], w.shape[0], out_hw[0], out_hw[1]), dtype=torch.float32, device=x.device)
         ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 0), x.device)
         with torch.cuda.device(x.device):
-            _call(_conv_key("cpc_conv_fwd", p), _conv_flops(p), lib.cpc_conv_fwd, _ptr(x), _ptr(w),
-                  _ptr(bias.contiguous() if bias is not None else None), _ptr(y), ctypes.byref(p), _ptr(ws),
-                  ws.numel() if ws is not None else 0, _stream())
+            # the packed copy of x serves the forward pass now and the weight gradient later
+            keep = weight.requires_grad and torch.is_grad_enabled()
+            packed_x = _pack_operand(lib, x, p, 0) if keep else None
+            _call(_conv_key("cpc_conv_fwd", p), _conv_flops(p), lib.cpc_conv_fwd_ex, _ptr(x), _ptr(w),
+                  _ptr(bias.contiguous() if bias is not None else None), _ptr(y), ctypes.byref(p), _ptr(packed_x),
+                  _ptr(ws), ws.numel() if ws is not None else 0, _stream())
         ctx.params = (tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, precision)
         ctx.has_bias = bias is not None
         ctx.relu = relu
-        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.save_for_backward(x, w, y if relu else None, packed_x)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        x, w, y, packed_x = ctx.saved_tensors
         lib = _lib.load()
         x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = ctx.params
         if ctx.relu:
@@ -155,18 +170,22 @@ class _ConvFunction(torch.autograd.Function):
         dy = dy.contiguous()
         p = _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, False, precision)
         dx = dw = db = None
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         with torch.cuda.device(dy.device):
-            if ctx.needs_input_grad[0]:
+            packed_dy = _pack_operand(lib, dy, p, 1) if need_dw else None
+            if need_dx:
                 dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
                 ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
-                _call(_conv_key("cpc_conv_dgrad", p), _conv_flops(p), lib.cpc_conv_dgrad, _ptr(dy), _ptr(w), _ptr(dx),
-                      ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
-            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                _call(_conv_key("cpc_conv_dgrad", p), _conv_flops(p), lib.cpc_conv_dgrad_ex, _ptr(dy), _ptr(w), _ptr(dx),
+                      ctypes.byref(p), _ptr(packed_dy), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+            if need_dw:
                 dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
                 db = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device) if ctx.has_bias else None
                 ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
-                _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad, _ptr(x), _ptr(dy), _ptr(dw),
-                      _ptr(db), ctypes.byref(p), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+                _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad_ex, _ptr(x), _ptr(dy), _ptr(dw),
+                      _ptr(db), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws),
+                      ws.numel() if ws is not None else 0, _stream())
         return dx, dw, db, None, None, None, None, None, None
 
 

@@ -7,6 +7,7 @@
 // channel counts >= 16 lives in conv_umma.cu and is selected by the dispatcher in this file.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace cpc {
@@ -15,20 +16,22 @@ namespace cpc {
 size_t umma_conv_workspace(const cpc_conv_params* p, int which);
 bool umma_conv_eligible(const cpc_conv_params* p, int which);
 int umma_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
-                     void* workspace, size_t workspace_bytes, cudaStream_t s);
+                     const void* pre, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int pack_split_launch(const float* x, __nv_bfloat16* out, long rows, int W, int Wp, int planes, int nrep, int w_mul,
+                      int rep_mul, int w_off, cudaStream_t s);
 
 size_t umma_wgrad_workspace(const cpc_conv_params* p);
 bool umma_wgrad_eligible(const cpc_conv_params* p);
-int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
-                      size_t workspace_bytes, cudaStream_t s);
+int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, const void* pre_x,
+                      const void* pre_dy, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 // conv_tall.cu: row-streaming kernels for kh x 1, stride-1, 32 -> 32 channel convolutions
 size_t tall_conv_workspace(const cpc_conv_params* p, int which);
 bool tall_conv_eligible(const cpc_conv_params* p, int which);
 int tall_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
-                     void* workspace, size_t workspace_bytes, cudaStream_t s);
-int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
-                      size_t workspace_bytes, cudaStream_t s);
+                     const void* pre, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, const void* pre_x,
+                      const void* pre_dy, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 // conv_smallk.cu: direct kernels for C_in * kh * kw <= 36 (forward and weight gradient)
 bool smallk_eligible(const cpc_conv_params* p, int which);
@@ -44,9 +47,9 @@ static bool smallk_path(const cpc_conv_params* p, int which) {
 size_t tall128_workspace(const cpc_conv_params* p, int which);
 bool tall128_eligible(const cpc_conv_params* p, int which);
 int tall128_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
-                        void* workspace, size_t workspace_bytes, cudaStream_t s);
-int tall128_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
-                         size_t workspace_bytes, cudaStream_t s);
+                        const void* pre, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int tall128_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, const void* pre_x,
+                         const void* pre_dy, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 // Debug switches (tests use them to A/B kernel families on one shape): CPC_FORCE_CUDA_CORE_CONV=1 selects the
 // fp32 CUDA-core kernels, CPC_NO_TALL_CONV=1 keeps tall convolutions on the generic tcgen05 kernel.
@@ -286,46 +289,106 @@ extern "C" size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which) 
     return 0;
 }
 
+// ---- caller-packed operands ---------------------------------------------------------------------------
+// Which kernel family serves (p, which): 0 tiled CUDA-core, 1 direct small-K, 2 tall 32ch, 3 tall 128, 4 generic tcgen05
+static int conv_family(const cpc_conv_params* p, int which) {
+    if ((which == 0 || which == 2) && smallk_path(p, which)) return 1;
+    if (const int tp = tall_path(p, which)) return tp == 1 ? 2 : 3;
+    return tensor_core_path(p, which) ? 4 : 0;
+}
+
+extern "C" size_t cpc_conv_packed_bytes(const cpc_conv_params* p, int operand) {
+    if (validate(p) != CPC_OK) return 0;
+    const size_t planes = p->precision == 1 ? 1 : 2;
+    const size_t Wp = (size_t)((p->w_out + 7) & ~7);
+    if (operand == 0) {
+        if (conv_family(p, 0) < 2 && conv_family(p, 2) < 2) return 0;
+        return align_up(planes * p->kw * p->batch * p->c_in * p->h_in * Wp * 2, 1024);
+    }
+    if (operand == 1) {
+        if (conv_family(p, 2) < 2) return 0;
+        return align_up(planes * p->batch * p->c_out * p->h_out * Wp * 2, 1024);
+    }
+    return 0;
+}
+
+extern "C" int cpc_conv_pack(const float* src, void* packed, const cpc_conv_params* p, int operand, void* stream) {
+    int st = validate(p);
+    if (st != CPC_OK) return st;
+    if (!src || !packed) return CPC_ERR_NULL;
+    if (cpc_conv_packed_bytes(p, operand) == 0) return CPC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return CPC_ERR_ALIGNMENT;   // TMA global base
+    if ((st = check_device()) != CPC_OK) return st;
+    const int planes = p->precision == 1 ? 1 : 2;
+    const int Wp = (p->w_out + 7) & ~7;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(packed);
+    if (operand == 0)
+        st = pack_split_launch(src, out, (long)p->batch * p->c_in * p->h_in, p->w_in, Wp, planes, p->kw, p->stride_w, 1,
+                               -p->pad_left, (cudaStream_t)stream);
+    else
+        st = pack_split_launch(src, out, (long)p->batch * p->c_out * p->h_out, p->w_out, Wp, planes, 1, 1, 0, 0,
+                               (cudaStream_t)stream);
+    if (st == CPC_OK) count_launch();
+    return st;
+}
+
 extern "C" int cpc_conv_fwd(const float* x, const float* w, const float* bias, float* y, const cpc_conv_params* p,
                             void* workspace, size_t workspace_bytes, void* stream) {
+    return cpc_conv_fwd_ex(x, w, bias, y, p, nullptr, workspace, workspace_bytes, stream);
+}
+extern "C" int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_params* p, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    return cpc_conv_dgrad_ex(dy, w, dx, p, nullptr, workspace, workspace_bytes, stream);
+}
+extern "C" int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    return cpc_conv_wgrad_ex(x, dy, dw, dbias, p, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cpc_conv_fwd_ex(const float* x, const float* w, const float* bias, float* y, const cpc_conv_params* p,
+                               const void* packed_x, void* workspace, size_t workspace_bytes, void* stream) {
     int st = validate(p);
     if (st != CPC_OK) return st;
     if (!x || !w || !y) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
-    if (smallk_path(p, 0)) return smallk_launch(0, x, w, bias, nullptr, y, p, (cudaStream_t)stream);
-    if (const int tp = tall_path(p, 0))
-        return tp == 1 ? tall_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream)
-                       : tall128_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream);
-    if (tensor_core_path(p, 0))
-        return umma_conv_launch(x, w, bias, y, p, 0, workspace, workspace_bytes, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (conv_family(p, 0)) {
+        case 1: return smallk_launch(0, x, w, bias, nullptr, y, p, s);
+        case 2: return tall_conv_launch(x, w, bias, y, p, 0, packed_x, workspace, workspace_bytes, s);
+        case 3: return tall128_conv_launch(x, w, bias, y, p, 0, packed_x, workspace, workspace_bytes, s);
+        case 4: return umma_conv_launch(x, w, bias, y, p, 0, packed_x, workspace, workspace_bytes, s);
+        default: break;
+    }
     ConvGeom g = make_geom(p);
     const int M = g.B * g.ohow, N = g.Cout, K = g.Cin * g.khkw;
     FwdA la{x, g, M, K};
     DenseRows lb{w, N, K};
     dim3 grid(ceil_div(M, TILE), ceil_div(N, TILE));
-    conv_fwd_kernel<<<grid, TILE_THREADS, 0, (cudaStream_t)stream>>>(la, lb, bias, y, p->relu);
+    conv_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(la, lb, bias, y, p->relu);
     CPC_LAUNCH_CHECK();
     count_launch();
     return CPC_OK;
 }
 
-extern "C" int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_params* p, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+extern "C" int cpc_conv_dgrad_ex(const float* dy, const float* w, float* dx, const cpc_conv_params* p, const void* packed_dy,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
     int st = validate(p);
     if (st != CPC_OK) return st;
     if (!dy || !w || !dx) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
-    if (const int tp = tall_path(p, 1))
-        return tp == 1 ? tall_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream)
-                       : tall128_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream);
-    if (tensor_core_path(p, 1))
-        return umma_conv_launch(dy, w, nullptr, dx, p, 1, workspace, workspace_bytes, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (conv_family(p, 1)) {
+        case 2: return tall_conv_launch(dy, w, nullptr, dx, p, 1, packed_dy, workspace, workspace_bytes, s);
+        case 3: return tall128_conv_launch(dy, w, nullptr, dx, p, 1, packed_dy, workspace, workspace_bytes, s);
+        case 4: return umma_conv_launch(dy, w, nullptr, dx, p, 1, packed_dy, workspace, workspace_bytes, s);
+        default: break;
+    }
     ConvGeom g = make_geom(p);
     const int M = g.B * g.hw, N = g.Cin, K = g.Cout * g.khkw;
     DgradA la{dy, g, M, K};
     DgradB lb{w, g, N, K};
     dim3 grid(ceil_div(M, TILE), ceil_div(N, TILE));
-    conv_dgrad_kernel<<<grid, TILE_THREADS, 0, (cudaStream_t)stream>>>(la, lb, dx);
+    conv_dgrad_kernel<<<grid, TILE_THREADS, 0, s>>>(la, lb, dx);
     CPC_LAUNCH_CHECK();
     count_launch();
     return CPC_OK;
@@ -340,27 +403,21 @@ static int launch_dbias(const float* dy, float* dbias, const ConvGeom& g, cudaSt
     return CPC_OK;
 }
 
-extern "C" int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int cpc_conv_wgrad_ex(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
+                                 const void* packed_x, const void* packed_dy, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
     int st = validate(p);
     if (st != CPC_OK) return st;
     if (!x || !dy || !dw) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
     ConvGeom g = make_geom(p);
     cudaStream_t s = (cudaStream_t)stream;
-    if (smallk_path(p, 2)) {
-        st = smallk_launch(2, x, nullptr, nullptr, dy, dw, p, s);
-        if (st != CPC_OK) return st;
-        return dbias ? launch_dbias(dy, dbias, g, s) : CPC_OK;
-    }
-    if (const int tp = tall_path(p, 2)) {
-        st = tp == 1 ? tall_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s)
-                     : tall128_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s);
-        if (st != CPC_OK) return st;
-        return dbias ? launch_dbias(dy, dbias, g, s) : CPC_OK;
-    }
-    if (tensor_core_path(p, 2)) {
-        st = umma_wgrad_launch(x, dy, dw, p, workspace, workspace_bytes, s);
+    const int fam = conv_family(p, 2);
+    if (fam != 0) {
+        if (fam == 1) st = smallk_launch(2, x, nullptr, nullptr, dy, dw, p, s);
+        else if (fam == 2) st = tall_wgrad_launch(x, dy, dw, p, packed_x, packed_dy, workspace, workspace_bytes, s);
+        else if (fam == 3) st = tall128_wgrad_launch(x, dy, dw, p, packed_x, packed_dy, workspace, workspace_bytes, s);
+        else st = umma_wgrad_launch(x, dy, dw, p, packed_x, packed_dy, workspace, workspace_bytes, s);
         if (st != CPC_OK) return st;
         return dbias ? launch_dbias(dy, dbias, g, s) : CPC_OK;
     }

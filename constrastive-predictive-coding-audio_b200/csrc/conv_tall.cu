@@ -421,7 +421,7 @@ static bool tall_act_tmap(CUtensorMap* t, const void* base, int B, int H, int Wp
 
 // which = 0: y = conv(x, w) + bias [relu];  which = 1: dx = conv_transpose(dy, w)
 int tall_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
-                     void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                     const void* pre, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     if (!tall_shape_ok(p)) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < tall_conv_workspace(p, which)) return CPC_ERR_WORKSPACE;
     const int B = p->batch, W = p->w_in, Wp = (W + 7) & ~7;
@@ -429,9 +429,9 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
     const int H_out = which == 0 ? p->h_out : p->h_in;
     const int P = which == 0 ? p->pad_top : p->kh - 1 - p->pad_top;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(ws);
+    const __nv_bfloat16* act = pre ? reinterpret_cast<const __nv_bfloat16*>(pre) : reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, H_src, W));
-    int st = pack_split_launch(in, act, (long)B * TL_C * H_src, W, Wp, 2, 1, 1, 1, 0, s);
+    int st = pre ? CPC_OK : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * TL_C * H_src, W, Wp, 2, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     tall_pack_weights_kernel<<<ceil_div(p->kh * TL_C * TL_C, 256), 256, 0, s>>>(w, wp, p->kh, which);
     CPC_LAUNCH_CHECK();
@@ -458,17 +458,19 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
     return CPC_OK;
 }
 
-int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
-                      size_t workspace_bytes, cudaStream_t s) {
+int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, const void* pre_x,
+                      const void* pre_dy, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     if (!tall_shape_ok(p)) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < tall_conv_workspace(p, 2)) return CPC_ERR_WORKSPACE;
     const int B = p->batch, W = p->w_in, Wp = (W + 7) & ~7;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, p->h_in, W));
-    int st = pack_split_launch(x, xp, (long)B * TL_C * p->h_in, W, Wp, 2, 1, 1, 1, 0, s);
+    const __nv_bfloat16* xp = pre_x ? reinterpret_cast<const __nv_bfloat16*>(pre_x) : reinterpret_cast<__nv_bfloat16*>(ws);
+    const __nv_bfloat16* dyp = pre_dy ? reinterpret_cast<const __nv_bfloat16*>(pre_dy)
+                                      : reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, p->h_in, W));
+    int st = pre_x ? CPC_OK : pack_split_launch(x, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * TL_C * p->h_in, W, Wp, 2, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
-    st = pack_split_launch(dy, dyp, (long)B * TL_C * p->h_out, W, Wp, 2, 1, 1, 1, 0, s);
+    st = pre_dy ? CPC_OK : pack_split_launch(dy, reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, p->h_in, W)),
+                                             (long)B * TL_C * p->h_out, W, Wp, 2, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     CUtensorMap tx, tdy;
     if (!tall_act_tmap(&tx, xp, B, p->h_in, Wp, 4)) return CPC_ERR_CUDA;

@@ -404,7 +404,7 @@ static bool t8_act_tmap(CUtensorMap* t, const void* base, int B, int C, int H, i
 }
 
 int tall128_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
-                        void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                        const void* pre, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     if (which > 1 || !tall128_eligible(p, which)) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < tall128_workspace(p, which)) return CPC_ERR_WORKSPACE;
     const int B = p->batch, W = p->w_in, Wp = (W + 7) & ~7;
@@ -413,9 +413,9 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
     const int H_out = which == 0 ? p->h_out : p->h_in;
     const int P = which == 0 ? p->pad_top : p->kh - 1 - p->pad_top;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(ws);
+    const __nv_bfloat16* act = pre ? reinterpret_cast<const __nv_bfloat16*>(pre) : reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, C, H_src, W));
-    int st = pack_split_launch(in, act, (long)B * C * H_src, W, Wp, 2, 1, 1, 1, 0, s);
+    int st = pre ? CPC_OK : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * C * H_src, W, Wp, 2, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     {
         const long total = (long)p->kh * (C / 64) * T8_N * 64;
@@ -447,17 +447,19 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
     return CPC_OK;
 }
 
-int tall128_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
-                         size_t workspace_bytes, cudaStream_t s) {
+int tall128_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, const void* pre_x,
+                         const void* pre_dy, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     if (!tall128_eligible(p, 2)) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < tall128_workspace(p, 2)) return CPC_ERR_WORKSPACE;
     const int B = p->batch, W = p->w_in, Wp = (W + 7) & ~7;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, T8_N, p->h_in, W));
-    int st = pack_split_launch(x, xp, (long)B * T8_N * p->h_in, W, Wp, 2, 1, 1, 1, 0, s);
+    const __nv_bfloat16* xp = pre_x ? reinterpret_cast<const __nv_bfloat16*>(pre_x) : reinterpret_cast<__nv_bfloat16*>(ws);
+    const __nv_bfloat16* dyp = pre_dy ? reinterpret_cast<const __nv_bfloat16*>(pre_dy)
+                                      : reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, T8_N, p->h_in, W));
+    int st = pre_x ? CPC_OK : pack_split_launch(x, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * T8_N * p->h_in, W, Wp, 2, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
-    st = pack_split_launch(dy, dyp, (long)B * T8_N * p->h_out, W, Wp, 2, 1, 1, 1, 0, s);
+    st = pre_dy ? CPC_OK : pack_split_launch(dy, reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, T8_N, p->h_in, W)),
+                                             (long)B * T8_N * p->h_out, W, Wp, 2, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     CUtensorMap tx, tdy;
     if (!t8_act_tmap(&tx, xp, B, T8_N, p->h_in, Wp, T8_N)) return CPC_ERR_CUDA;

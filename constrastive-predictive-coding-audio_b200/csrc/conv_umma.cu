@@ -40,6 +40,7 @@ struct UmmaConv {
     int h_mul, tap_h_mul, h_off;         // source row = h_mul*ph + tap_h_mul*i + h_off
     int out_H, out_W, oh_mul, oh_off, ow_mul, ow_off;        // output pixel = (oh_mul*ph + oh_off, ow_mul*pw + ow_off)
     int planes;                          // 2 = fp32-faithful split, 1 = bf16
+    int nrep;                            // replicas per plane in the packed operand (>= tw)
     int srcH;                            // rows of the source tensor (taps landing outside are all-zero)
     int relu, stages;
     const float* bias;
@@ -197,14 +198,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                                 const int tap = q / p.cin_chunks, c0 = (q - tap * p.cin_chunks) * KCHUNK;
                                 const int i = tap / p.tw, j = tap - i * p.tw;
                                 tma_load_5d(a_dst + a * (KCHUNK * 128), &tmap_a, &bars->full[stage], aw0[a],
-                                            aoh[a] + i * p.tap_h_mul, c0, ab[a], pl * p.tw + j);
+                                            aoh[a] + i * p.tap_h_mul, c0, ab[a], pl * p.nrep + j);
                             } else {
                                 for (int t = 0; t < p.tpc; ++t) {
                                     int tap = q * p.tpc + t;
                                     if (tap >= p.ntaps) tap = 0;        // phantom tap: its packed weights are zero
                                     const int i = tap / p.tw, j = tap - i * p.tw;
                                     tma_load_5d(a_dst + a * (KCHUNK * 128) + t * p.cin_eff * 128, &tmap_a, &bars->full[stage],
-                                                aw0[a], aoh[a] + i * p.tap_h_mul, 0, ab[a], pl * p.tw + j);
+                                                aw0[a], aoh[a] + i * p.tap_h_mul, 0, ab[a], pl * p.nrep + j);
                                 }
                             }
                         }
@@ -312,6 +313,8 @@ struct ConvProblem {
     int h_mul, tap_h_mul, h_off;                       // source row    = h_mul*ph + tap_h_mul*i + h_off
     int w_mul, rep_mul, w_off;                         // source column = w_mul*pw + rep_mul*j + w_off (baked into replicas)
     int out_H, out_W, oh_mul, oh_off, ow_mul, ow_off;  // destination pixel
+    // operand already packed by the caller / a sibling problem: [plane][pre_nrep][rows][pre_Wp], replica r as above
+    const __nv_bfloat16* pre; int pre_Wp, pre_nrep;
 };
 
 struct UmmaPlan {
@@ -336,13 +339,13 @@ static UmmaPlan plan_problem(const ConvProblem& c, int batch, int precision) {
     u.n_tile = co <= 128 ? co : 128;
     u.n_ntiles = co / u.n_tile;
     u.planes = precision == 1 ? 1 : 2;
-    u.Wp = (c.PW + 7) & ~7;                            // replicas are addressed by GEMM pixel column
+    u.Wp = c.pre ? c.pre_Wp : (c.PW + 7) & ~7;         // replicas are addressed by GEMM pixel column
     const int stage_bytes = u.planes * (A_PLANE_BYTES + u.n_tile * 128);
     u.stages = (SMEM_LIMIT - 2048) / stage_bytes;
     if (u.stages > 8) u.stages = 8;
     if (u.stages < 2) return u;
     u.smem_bytes = (size_t)u.stages * stage_bytes + sizeof(UmmaBarriers) + 1024;
-    u.act_bytes = align_up((size_t)u.planes * c.tm.tw * batch * ci * c.srcH * u.Wp * 2, 1024);
+    u.act_bytes = c.pre ? 0 : align_up((size_t)u.planes * c.tm.tw * batch * ci * c.srcH * u.Wp * 2, 1024);
     u.w_bytes = align_up((size_t)u.planes * u.n_chunks * co * KCHUNK * 2, 1024);
     u.ok = true;
     return u;
@@ -355,11 +358,13 @@ static int run_problem(const ConvProblem& c, const float* w, const float* bias, 
     if (!u.ok) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < u.act_bytes + u.w_bytes + 1024) return CPC_ERR_WORKSPACE;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(ws);
+    const __nv_bfloat16* act = c.pre ? c.pre : reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + u.act_bytes);
     const long rows = (long)B * c.in_ch * c.srcH;
+    const int nrep = c.pre ? c.pre_nrep : c.tm.tw;
     {
-        if (pack_split_launch(c.src, act, rows, c.srcW, u.Wp, u.planes, c.tm.tw, c.w_mul, c.rep_mul, c.w_off, s) != CPC_OK)
+        if (!c.pre && pack_split_launch(c.src, reinterpret_cast<__nv_bfloat16*>(ws), rows, c.srcW, u.Wp, u.planes, c.tm.tw,
+                                        c.w_mul, c.rep_mul, c.w_off, s) != CPC_OK)
             return CPC_ERR_CUDA;
         const long wtotal = (long)u.n_chunks * c.out_ch * KCHUNK;
         int wblocks = (int)((wtotal + 255) / 256);
@@ -372,7 +377,7 @@ static int run_problem(const ConvProblem& c, const float* w, const float* bias, 
     {
         // replica / plane index is the outermost dimension
         const uint64_t dims[5] = {(uint64_t)u.Wp, (uint64_t)c.srcH, (uint64_t)c.in_ch, (uint64_t)B,
-                                  (uint64_t)u.planes * c.tm.tw};
+                                  (uint64_t)u.planes * nrep};
         const uint64_t row_b = (uint64_t)u.Wp * 2;
         const uint64_t strides[4] = {row_b, row_b * c.srcH, row_b * c.srcH * c.in_ch, row_b * c.srcH * c.in_ch * B};
         const uint32_t box[5] = {ATOM, 1, (uint32_t)u.cin_eff, 1, 1};
@@ -391,14 +396,14 @@ static int run_problem(const ConvProblem& c, const float* w, const float* bias, 
     k.cin_chunks = u.cin_chunks; k.n_chunks = u.n_chunks;
     k.h_mul = c.h_mul; k.tap_h_mul = c.tap_h_mul; k.h_off = c.h_off;
     k.out_H = c.out_H; k.out_W = c.out_W; k.oh_mul = c.oh_mul; k.oh_off = c.oh_off; k.ow_mul = c.ow_mul; k.ow_off = c.ow_off;
-    k.planes = u.planes; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out; k.srcH = c.srcH;
+    k.planes = u.planes; k.nrep = nrep; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out; k.srcH = c.srcH;
     if (cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int n_tiles = ((k.n_atoms + 1) / 2) * k.n_ntiles;
     const int grid = n_tiles < 148 ? n_tiles : 148;
     umma_conv_kernel<<<grid, UM_THREADS, u.smem_bytes, s>>>(ta, tb, k);
     CPC_LAUNCH_CHECK();
-    count_launch(3);
+    count_launch(c.pre ? 2 : 3);
     return CPC_OK;
 }
 
@@ -455,6 +460,39 @@ bool umma_conv_eligible(const cpc_conv_params* p, int which) {
     return true;
 }
 
+// The data-gradient classes read dy through replicas  column w' -> dy[w' - r + w_off].  When every class has the
+// same w_off the replicas are packed ONCE (max tw replicas, widest pitch) and shared by all classes.
+struct DgradShare {
+    bool common;            // all classes agree on (w_mul = 1, w_off)
+    int n_classes, max_tw, max_pw, w_off;
+    size_t act_bytes;       // shared activation planes
+    size_t max_w_bytes;     // largest packed weight block of any class
+    size_t max_single;      // largest (act + w) of any class when packed per class
+};
+
+static DgradShare dgrad_share(const cpc_conv_params* p) {
+    DgradShare d{};
+    d.common = true;
+    bool first = true;
+    for (int rh = 0; rh < p->stride_h; ++rh)
+        for (int rw = 0; rw < p->stride_w; ++rw) {
+            ConvProblem c; bool taps;
+            if (!dgrad_problem(nullptr, p, rh, rw, c, taps) || !taps) continue;
+            UmmaPlan u = plan_problem(c, p->batch, p->precision);
+            ++d.n_classes;
+            if (first) { d.w_off = c.w_off; first = false; }
+            if (c.w_off != d.w_off || c.w_mul != 1) d.common = false;
+            if (c.tm.tw > d.max_tw) d.max_tw = c.tm.tw;
+            if (c.PW > d.max_pw) d.max_pw = c.PW;
+            if (u.w_bytes > d.max_w_bytes) d.max_w_bytes = u.w_bytes;
+            if (u.act_bytes + u.w_bytes > d.max_single) d.max_single = u.act_bytes + u.w_bytes;
+        }
+    const int planes = p->precision == 1 ? 1 : 2;
+    const int Wp = (d.max_pw + 7) & ~7;
+    d.act_bytes = align_up((size_t)planes * d.max_tw * p->batch * p->c_out * p->h_out * Wp * 2, 1024);
+    return d;
+}
+
 size_t umma_conv_workspace(const cpc_conv_params* p, int which) {
     if (!umma_conv_eligible(p, which)) return 0;
     size_t need = 0;
@@ -462,21 +500,26 @@ size_t umma_conv_workspace(const cpc_conv_params* p, int which) {
         UmmaPlan u = plan_problem(fwd_problem(nullptr, p), p->batch, p->precision);
         need = u.act_bytes + u.w_bytes;
     } else {
-        for (int rh = 0; rh < p->stride_h; ++rh)
-            for (int rw = 0; rw < p->stride_w; ++rw) {
-                ConvProblem c; bool taps;
-                if (!dgrad_problem(nullptr, p, rh, rw, c, taps) || !taps) continue;
-                UmmaPlan u = plan_problem(c, p->batch, p->precision);
-                if (u.act_bytes + u.w_bytes > need) need = u.act_bytes + u.w_bytes;
-            }
+        const DgradShare d = dgrad_share(p);
+        need = d.max_single;
+        if (d.common && d.act_bytes + d.max_w_bytes > need) need = d.act_bytes + d.max_w_bytes;
     }
-    return need + 1024;
+    return need + 2048;
 }
 
-// which = 0: y = conv(x, w) + bias ; which = 1: dx = conv_transpose(dy, w).   `in` is x or dy, `out` is y or dx.
+// Canonical caller-packed layouts (cpc_conv_pack):
+//   x : [plane][kw][B*Cin*H][round8(w_out)],  replica r column w' = x[stride_w * w' + r - pad_left]
+//   dy: [plane][1][B*Cout*OH][round8(w_out)]  (plain)
+// which = 0: y = conv(x, w) + bias ; which = 1: dx = conv_transpose(dy, w).   `in` is x or dy, `out` is y or dx;
+// `pre` is the caller-packed copy of `in` (or NULL).
 int umma_conv_launch(const float* in, const float* w, const float* bias, float* out, const cpc_conv_params* p, int which,
-                     void* workspace, size_t workspace_bytes, cudaStream_t s) {
-    if (which == 0) return run_problem(fwd_problem(in, p), w, bias, out, p, p->relu, workspace, workspace_bytes, s);
+                     const void* pre, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    const __nv_bfloat16* prep = reinterpret_cast<const __nv_bfloat16*>(pre);
+    if (which == 0) {
+        ConvProblem c = fwd_problem(in, p);
+        if (prep) { c.pre = prep; c.pre_Wp = (p->w_out + 7) & ~7; c.pre_nrep = p->kw; }
+        return run_problem(c, w, bias, out, p, p->relu, workspace, workspace_bytes, s);
+    }
     bool need_zero = false;
     for (int rh = 0; rh < p->stride_h; ++rh)
         for (int rw = 0; rw < p->stride_w; ++rw) {
@@ -486,11 +529,36 @@ int umma_conv_launch(const float* in, const float* w, const float* bias, float* 
     if (need_zero &&
         cudaMemsetAsync(out, 0, sizeof(float) * (size_t)p->batch * p->c_in * p->h_in * p->w_in, s) != cudaSuccess)
         return CPC_ERR_CUDA;
+    const DgradShare d = dgrad_share(p);
+    const int pre_Wp = (p->w_out + 7) & ~7;
+    // caller-packed plain dy serves every class iff no class needs a shifted replica
+    const bool use_pre = prep && d.common && d.max_tw == 1 && d.w_off == 0 && d.max_pw <= pre_Wp;
+    const __nv_bfloat16* shared = nullptr;
+    int shared_Wp = 0, shared_nrep = 0;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    size_t ws_bytes = workspace_bytes;
+    if (use_pre) {
+        shared = prep; shared_Wp = pre_Wp; shared_nrep = 1;
+    } else if (d.common && d.n_classes > 1) {
+        if (!workspace || workspace_bytes < d.act_bytes + d.max_w_bytes + 2048) return CPC_ERR_WORKSPACE;
+        uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+        shared_Wp = (d.max_pw + 7) & ~7;
+        shared_nrep = d.max_tw;
+        const int planes = p->precision == 1 ? 1 : 2;
+        if (pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(base), (long)p->batch * p->c_out * p->h_out, p->w_out,
+                              shared_Wp, planes, shared_nrep, 1, -1, d.w_off, s) != CPC_OK)
+            return CPC_ERR_CUDA;
+        count_launch();
+        shared = reinterpret_cast<const __nv_bfloat16*>(base);
+        ws = base + d.act_bytes;
+        ws_bytes = workspace_bytes - (size_t)(ws - reinterpret_cast<uint8_t*>(workspace));
+    }
     for (int rh = 0; rh < p->stride_h; ++rh)
         for (int rw = 0; rw < p->stride_w; ++rw) {
             ConvProblem c; bool taps;
             if (!dgrad_problem(in, p, rh, rw, c, taps) || !taps) continue;
-            const int st = run_problem(c, w, nullptr, out, p, 0, workspace, workspace_bytes, s);
+            if (shared) { c.pre = shared; c.pre_Wp = shared_Wp; c.pre_nrep = shared_nrep; }
+            const int st = run_problem(c, w, nullptr, out, p, 0, ws, ws_bytes, s);
             if (st != CPC_OK) return st;
         }
     return CPC_OK;
@@ -664,21 +732,25 @@ size_t umma_wgrad_workspace(const cpc_conv_params* p) {
 }
 bool umma_wgrad_eligible(const cpc_conv_params* p) { return make_wgrad_plan(p).ok; }
 
-int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* workspace,
-                      size_t workspace_bytes, cudaStream_t s) {
+int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv_params* p, const void* pre_x,
+                      const void* pre_dy, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     WgradPlan u = make_wgrad_plan(p);
     if (!u.ok) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < u.x_bytes + u.dy_bytes + 1024) return CPC_ERR_WORKSPACE;
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(ws + u.x_bytes);
+    const __nv_bfloat16* xp = pre_x ? reinterpret_cast<const __nv_bfloat16*>(pre_x) : reinterpret_cast<__nv_bfloat16*>(ws);
+    const __nv_bfloat16* dyp =
+        pre_dy ? reinterpret_cast<const __nv_bfloat16*>(pre_dy) : reinterpret_cast<__nv_bfloat16*>(ws + u.x_bytes);
     const int B = p->batch;
     {
         const long rows_x = (long)B * p->c_in * p->h_in;
-        if (pack_split_launch(x, xp, rows_x, p->w_in, u.Wp_x, u.planes, p->kw, p->stride_w, 1, -p->pad_left, s) != CPC_OK)
+        if (!pre_x && pack_split_launch(x, reinterpret_cast<__nv_bfloat16*>(ws), rows_x, p->w_in, u.Wp_x, u.planes, p->kw,
+                                        p->stride_w, 1, -p->pad_left, s) != CPC_OK)
             return CPC_ERR_CUDA;
         const long rows_dy = (long)B * p->c_out * p->h_out;
-        if (pack_split_launch(dy, dyp, rows_dy, p->w_out, u.Wp_dy, u.planes, 1, 1, 0, 0, s) != CPC_OK) return CPC_ERR_CUDA;
+        if (!pre_dy && pack_split_launch(dy, reinterpret_cast<__nv_bfloat16*>(ws + u.x_bytes), rows_dy, p->w_out, u.Wp_dy,
+                                         u.planes, 1, 1, 0, 0, s) != CPC_OK)
+            return CPC_ERR_CUDA;
     }
     CUtensorMap tx, tdy;
     {

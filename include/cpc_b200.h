@@ -123,6 +123,22 @@ int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_pa
 int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Optional operand caching.  The tensor-core kernels read bf16 hi/lo planes of their activation operand; by
+ * default every call re-packs its fp32 inputs into the workspace.  A caller that keeps tensors across calls (an
+ * autograd Function keeps x from forward to backward, and uses dy for both gradients) can pack each operand
+ * once with cpc_conv_pack() and hand the result to the *_ex entry points (a NULL packed pointer = pack
+ * internally; the fp32 tensor must always be passed too, some kernel families read it directly).
+ *   operand 0: x   operand 1: dy.   cpc_conv_packed_bytes() == 0: this configuration does not use a packed copy.
+ *   `packed` must be 16-byte aligned (it becomes a TMA global base address). */
+size_t cpc_conv_packed_bytes(const cpc_conv_params* p, int operand);
+int cpc_conv_pack(const float* src, void* packed, const cpc_conv_params* p, int operand, void* stream);
+int cpc_conv_fwd_ex(const float* x, const float* w, const float* bias, float* y, const cpc_conv_params* p,
+                    const void* packed_x, void* workspace, size_t workspace_bytes, void* stream);
+int cpc_conv_dgrad_ex(const float* dy, const float* w, float* dx, const cpc_conv_params* p, const void* packed_dy,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int cpc_conv_wgrad_ex(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
+                      const void* packed_x, const void* packed_dy, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 2b. Fused BatchNorm2d + ReLU (+ centre-cropped residual add + ReLU), forward and backward.
  *    Replaces nn.BatchNorm2d / nn.ReLU after each conv of ScalogramEncoderBlock (scalogram_model.py:399-431),

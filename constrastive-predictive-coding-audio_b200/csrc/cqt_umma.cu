@@ -22,11 +22,12 @@
 namespace cpc {
 using namespace umma;
 
-constexpr int CQ_THREADS = 256;
+constexpr int CQ_THREADS = 384;                        // 4 control warps + 2 x 4 epilogue warps
+constexpr int CQ_ACC_COLS = 256;                       // TMEM columns per accumulator buffer (two buffers)
 constexpr int CQ_SLAB_ROWS = 256;
 constexpr int CQ_SLAB_PLANE = CQ_SLAB_ROWS * 128;        // 32 KB: one column half, one plane
-constexpr int CQ_BSTAGES = 4;
-constexpr int CQ_MAX_SETS = 4;
+constexpr int CQ_BSTAGES = 5;
+constexpr int CQ_MAX_SETS = 8;
 
 struct CqGroup {
     int K, off, n_g, bin_lo, n_chunks, w_row0;           // w_row0: first row of the group in the packed filters
@@ -48,10 +49,10 @@ struct CqtUmma {
 };
 
 struct __align__(8) CqBarriers {
-    uint64_t bfull[CQ_BSTAGES], bempty[CQ_BSTAGES], slab_full, slab_empty, acc_full, acc_empty, sfull[2], sempty[2];
+    uint64_t bfull[CQ_BSTAGES], bempty[CQ_BSTAGES], slab_full, slab_empty, acc_full[2], acc_empty[2], sfull[2], sempty[2];
     uint32_t tmem_base;
     int tile_id[2];
-    float exch[2][4][32];
+    float exch[2][2][4][32];                         // [epilogue warp set][parity][warp][bin]
 };
 
 // x (B, pitch) fp32 -> bf16 [plane][b][S*hop] (zeros past the item)
@@ -112,7 +113,22 @@ __device__ __forceinline__ void cq_tile(const CqtUmma& p, int tile, int& set, in
     blk = r - b * p.n_blocks;
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// atan2 to ~2e-7 rad: octant reduction + the cephes atanf kernel (|z| <= tan(pi/8)), fast divisions.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = mx > 0.f ? __fdividef(mn, mx) : 0.f;               // in [0, 1]
+    float base = 0.f;
+    if (t > 0.41421356f) { base = 0.78539816f; t = __fdividef(t - 1.f, t + 1.f); }
+    const float z = t * t;
+    float r = fmaf(fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f) * z, t, t);
+    r += base;
+    if (ay > ax) r = 1.57079632679f - r;
+    if (x < 0.f) r = 3.14159265359f - r;
+    return y < 0.f ? -r : r;
+}
 
 __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                 const __grid_constant__ CUtensorMap tmap_w,
@@ -132,9 +148,12 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
         for (int s = 0; s < CQ_BSTAGES; ++s) { mbar_init(&bars->bfull[s], 1); mbar_init(&bars->bempty[s], 1); }
         mbar_init(&bars->slab_full, 1);
         mbar_init(&bars->slab_empty, 1);
-        mbar_init(&bars->acc_full, 1);
-        mbar_init(&bars->acc_empty, 4);
-        for (int s = 0; s < 2; ++s) { mbar_init(&bars->sfull[s], 1); mbar_init(&bars->sempty[s], 5); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->acc_full[s], 1);
+            mbar_init(&bars->acc_empty[s], 8);
+            mbar_init(&bars->sfull[s], 1);
+            mbar_init(&bars->sempty[s], 9);
+        }
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
@@ -187,12 +206,13 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                 if (tile < 0) break;
                 int set, b, blk;
                 cq_tile(p, tile, set, b, blk);
-                mbar_wait(&bars->acc_empty, (tn & 1) ^ 1);
+                const uint32_t buf = tn & 1;
+                mbar_wait(&bars->acc_empty[buf], ((tn >> 1) & 1) ^ 1);
                 mbar_wait(&bars->slab_full, tn & 1);
                 tc_fence_after();
                 for (int gi = 0; gi < p.set_count[set]; ++gi) {
                     const CqGroup& g = p.g[p.set_first[set] + gi];
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(gi * p.NP);
+                    const uint32_t d_tmem = tmem_base + buf * CQ_ACC_COLS + (uint32_t)(gi * p.NP);
                     for (int c = 0; c < g.n_chunks; ++c, ++bn) {
                         const int stage = bn % CQ_BSTAGES;
                         mbar_wait(&bars->bfull[stage], (bn / CQ_BSTAGES) & 1);
@@ -214,13 +234,14 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                     }
                 }
                 tc_commit(&bars->slab_empty);
-                tc_commit(&bars->acc_full);
+                tc_commit(&bars->acc_full[buf]);
                 ++tn;
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue: (re, im) -> output format =====
-        const int ew = warp & 3;
+        const int ew = warp & 3;                                               // TMEM lane quarter
+        const int eset = (warp - 4) >> 2;                                      // warp set 0 / 1: even / odd groups
         const int r = ew * 32 + lane;
         const float kPi = 3.14159265358979323846f;
         uint32_t tn = 0, xb = 0;
@@ -234,10 +255,11 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             int set, b, blk;
             cq_tile(p, tile, set, b, blk);
             const int t = blk * p.fpb + r;                                     // frame of this thread
-            mbar_wait(&bars->acc_full, tn & 1);
+            const uint32_t buf = tn & 1;
+            mbar_wait(&bars->acc_full[buf], (tn >> 1) & 1);
             tc_fence_after();
-            const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
-            for (int gi = 0; gi < p.set_count[set]; ++gi) {
+            const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * CQ_ACC_COLS;
+            for (int gi = eset; gi < p.set_count[set]; gi += 2) {
                 const CqGroup& g = p.g[p.set_first[set] + gi];
                 for (int j0 = 0; j0 < g.n_g; j0 += 32) {
                     uint32_t re[32], im[32];
@@ -260,8 +282,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                             for (int j = 0; j < 32; ++j)
                                 if (j < nb) {
                                     const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
-                                    const float a = sqrtf(x * x + y * y);
-                                    float amp = (logf(a * a + p.eps) + p.log_offset) * p.norm;
+                                    float amp = (__logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
                                     if (p.power != 1.f) amp = powf(amp, p.power);
                                     p.out[((size_t)b * p.F + g.bin_lo + j0 + j) * p.To + t] = amp;
                                 }
@@ -270,13 +291,13 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                         // phase difference needs frame t - 1: previous lane, or lane 31 of the previous warp
                         float ph[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) ph[j] = atan2f(__uint_as_float(im[j]), __uint_as_float(re[j]));
-                        float* ex = &bars->exch[xb & 1][0][0];
+                        for (int j = 0; j < 32; ++j) ph[j] = fast_atan2(__uint_as_float(im[j]), __uint_as_float(re[j]));
+                        float* ex = &bars->exch[eset][xb & 1][0][0];
                         if (lane == 31) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) ex[ew * 32 + j] = ph[j];
                         }
-                        epi_bar();
+                        epi_bar(1 + eset);
                         ++xb;
                         const bool emit = r >= 1 && t < p.T;
                         const int to = t - 1;
@@ -287,8 +308,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                             if (emit && j < nb) {
                                 const int f = g.bin_lo + j0 + j;
                                 const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
-                                const float a = sqrtf(x * x + y * y);
-                                float amp = (logf(a * a + p.eps) + p.log_offset) * p.norm;
+                                float amp = (__logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
                                 float pd = ph[j] - prev + __ldg(p.phase_fixed + f);
                                 if (pd > kPi) pd -= 2.f * kPi;
                                 if (pd < -kPi) pd += 2.f * kPi;
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty);
+            if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
             ++tn;
         }
     }
@@ -396,7 +416,7 @@ int cqt_umma_launch(const float* x, const float* weights, const float* phase_fix
     {
         long total = 0;
         for (int g = 0; g < u.n_tensor_groups; ++g) total += k.g[g].K;
-        const int max_per_set = 512 / u.NP;
+        const int max_per_set = CQ_ACC_COLS / u.NP;
         const long target = (total + 2) / 3;
         int g = 0;
         k.n_sets = 0;

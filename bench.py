@@ -108,6 +108,7 @@ def workload_config(n_gpus):
                         "InfoNCE linear/all-steps K=16, full train step incl. Adam (BASELINE configs[1])",
             "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus, "samples_per_item": 97024,
             "sample_rate": SR, "parallelism": "dp%d" % n_gpus, "negatives": "per-GPU",
+            "submission": "whole step captured in one CUDA graph (cpc_b200.GraphedTrainStep)",
             "l2": "activations (>300 MB per layer) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -154,22 +155,36 @@ def run_ours(args):
         model=model, dataset=None, device=dev, regularization=tc["regularization"],
         score_over_all_timesteps=tc["score_over_all_timesteps"], score_function=tc["score_function"],
         preprocessing=pre, prediction_steps=tc["prediction_steps"], verbose=False)
-    optimizer = torch.optim.Adam(model.parameters(), lr=tc["learning_rate"])
-    reducer = ddp.GradientBucketReducer(model) if world > 1 else None
+    optimizer = torch.optim.Adam(model.parameters(), lr=tc["learning_rate"], capturable=True)
+    use_graph = not args.no_graph
+    reducer = ddp.GradientBucketReducer(model) if (world > 1 and not use_graph) else None
     model.train()
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_batches = [(0.1 * torch.randn(b, length, generator=g)).pin_memory() for _ in range(2)]
     dev_batches = [h.to(dev) for h in host_batches]
 
-    def step(batch):
+    def eager_step(batch):
         loss, max_score = trainer.loss_on_batch(batch)
         model.zero_grad(set_to_none=True)
         loss.backward()
         if reducer is not None:
             reducer.finish()
+        elif world > 1:
+            ddp.allreduce_gradients([p for p in model.parameters() if p.requires_grad], world)
         optimizer.step()
         return loss, max_score
+
+    graphed, launches_per_step = None, None
+    if use_graph:
+        # the whole step (forward, backward, Adam) is captured once and replayed; count our launches per step while
+        # capturing (a replay issues no host-side launch calls)
+        _lib.reset_launch_count()
+        graphed = cpc_b200.GraphedTrainStep(trainer, optimizer, (b, length), warmup=3)
+        launches_per_step = _lib.launch_count() // 4            # 3 eager warm-up steps + the captured one
+
+    def step(batch):
+        return graphed(batch) if graphed is not None else eager_step(batch)
 
     def barrier():
         if world > 1:
@@ -197,14 +212,15 @@ def run_ours(args):
     clocks.start()
     _lib.reset_launch_count()
     ms_dev = timed(lambda i: step(dev_batches[i % 2]), args.steps)
-    launches = _lib.launch_count()
+    launches = launches_per_step * args.steps if graphed is not None else _lib.launch_count()
     clk = clocks.stop()
 
     # end to end through the public API: pinned host batch -> device, full step, loss + max score read back
     last = {}
 
     def e2e_step(i):
-        batch = host_batches[i % 2].to(dev, non_blocking=True)
+        # pinned host batch -> device (inside the graphed step it lands directly in the static input buffer)
+        batch = host_batches[i % 2] if graphed is not None else host_batches[i % 2].to(dev, non_blocking=True)
         loss, mx = step(batch)
         last["v"] = torch.stack([loss.detach(), mx.detach()]).tolist()
     e2e_step(0)
@@ -214,7 +230,7 @@ def run_ours(args):
     prof = ops.KernelProfiler()
     with prof:
         for i in range(max(2, min(args.steps, 4))):
-            step(dev_batches[i % 2])
+            eager_step(dev_batches[i % 2])
     torch.cuda.synchronize()
     top = prof.summary()
 
@@ -255,6 +271,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="submit kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -18,7 +18,7 @@ from .encoders import (AudioEncoder, Conv1d, Conv2d, Conv2dSeparable, ScalogramE
                        ScalogramEncoderBlock, ScalogramResidualEncoder, cqt_default_dict,
                        encoder_default_dict, scalogram_encoder_default_dict)
 from .ar_models import AttentionModel, AudioGRUModel, ConvolutionalArBlock, ConvolutionalArModel  # noqa: F401
-from .trainer import (ContrastiveEstimationTrainer, DeterministicSampler, difference_score_function,  # noqa: F401
+from .trainer import (ContrastiveEstimationTrainer, DeterministicSampler, GraphedTrainStep, difference_score_function,  # noqa: F401
                       linear_score_function, softplus_score_function)
 from .sampler import FileBatchSampler, SyntheticAudioDataset                  # noqa: F401
 from . import configs, ddp                                                    # noqa: F401

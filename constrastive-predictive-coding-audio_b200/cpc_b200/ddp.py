@@ -49,6 +49,37 @@ def broadcast_parameters(module, src=0):
         dist.broadcast(t.data, src=src)
 
 
+def allreduce_gradients(params, world, bucket_mb=64.0, group=None):
+    """Synchronous variant used after a CUDA-graph replay (the graph holds forward + backward only): average the
+    .grad buffers across ranks in flat buckets, in place."""
+    if world == 1 or not dist.is_initialized():
+        return
+    limit = int(bucket_mb * 1024 * 1024)
+    bucket, size = [], 0
+
+    def flush():
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        offset = 0
+        for g in bucket:
+            n = g.numel()
+            g.copy_(flat[offset:offset + n].view_as(g))
+            offset += n
+
+    for p in params:
+        if p.grad is None:
+            continue
+        bucket.append(p.grad)
+        size += p.grad.numel() * p.grad.element_size()
+        if size >= limit:
+            flush()
+            bucket, size = [], 0
+    flush()
+
+
 class GradientBucketReducer:
     """Averages ``.grad`` across ranks.  Parameters are packed into buckets of ~``bucket_mb`` in reverse
     registration order (the order autograd produces them); when the last gradient of a bucket has been

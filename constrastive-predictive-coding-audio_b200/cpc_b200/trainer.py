@@ -212,6 +212,73 @@ class ContrastiveEstimationTrainer:
         return total_losses, total_accurate, total_score, mutual_information_lb
 
 
+class GraphedTrainStep:
+    """One full training step (preprocessing -> model -> fused InfoNCE -> backward -> optimizer) captured once into a
+    CUDA graph and replayed: the ~380 kernel launches of a step are submitted with one call, so the GPU never waits
+    for Python between kernels.  Everything the step touches lives at fixed addresses (the static input batch, the
+    parameters, their .grad buffers, the optimizer state and every workspace come from the graph's private pool).
+
+        step = GraphedTrainStep(trainer, optimizer, (B, L))      # optimizer must be capturable (Adam(capturable=True))
+        loss, max_score = step(batch)                            # batch: (B, L) device or pinned-host tensor
+
+    With more than one rank the gradient all-reduce and the optimizer step run eagerly after the replayed
+    forward/backward graph (NCCL work is not captured)."""
+
+    def __init__(self, trainer, optimizer, batch_shape, warmup=3):
+        self.trainer, self.optimizer = trainer, optimizer
+        self.world = trainer.world
+        dev = trainer.device
+        self.static_batch = torch.zeros(batch_shape, dtype=torch.float32, device=dev)
+        self.params = [p for p in trainer.model.parameters() if p.requires_grad]
+        # Warm-up steps outside the capture create the optimizer state, cuDNN plans and allocator blocks the capture
+        # must not contain; they run on a scratch copy of the training state, which is restored afterwards so that
+        # building the graph leaves model and optimizer exactly as they were.
+        modules = [trainer.model] + ([trainer.preprocessing] if trainer.preprocessing is not None else [])
+        tensors = [t for m in modules for t in list(m.parameters()) + list(m.buffers())]
+        saved = [t.detach().clone() for t in tensors]
+        saved_state = {p: {k: v.detach().clone() for k, v in optimizer.state.get(p, {}).items() if torch.is_tensor(v)}
+                       for p in self.params}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.no_grad():
+            for t, s in zip(tensors, saved):
+                t.copy_(s)
+            for p in self.params:
+                for k, v in optimizer.state.get(p, {}).items():
+                    if torch.is_tensor(v):
+                        old = saved_state[p].get(k)
+                        v.copy_(old) if old is not None else v.zero_()
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            loss, max_score = trainer.loss_on_batch(self.static_batch)
+            loss.backward()
+            if self.world == 1:
+                optimizer.step()
+            self.loss, self.max_score = loss.detach(), max_score.detach()
+
+    def _eager_step(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss, _ = self.trainer.loss_on_batch(self.static_batch)
+        loss.backward()
+        if self.world > 1:
+            ddp.allreduce_gradients(self.params, self.world)
+        self.optimizer.step()
+
+    def __call__(self, batch):
+        self.static_batch.copy_(batch, non_blocking=True)
+        self.graph.replay()
+        if self.world > 1:
+            ddp.allreduce_gradients(self.params, self.world)
+            self.optimizer.step()
+        return self.loss, self.max_score
+
+
 class DeterministicSampler(torch.utils.data.Sampler):
     """contrastive_estimation_training.py:363-382."""
 

@@ -608,3 +608,47 @@ def test_training_steps_cqt_resnet_match_reference_train(cpc):
     log, snaps, lr = _replay_trainer(cpc, g, model, pre, seed=3, steps=3, regularization=0.25, score_over_all_timesteps=True,
                                      score_function=cpc.linear_score_function, prediction_steps=3)
     _check_against_snapshots(g, log, snaps, lr, 5 * TOL)
+
+
+def test_cuda_graph_step_reproduces_eager_steps(cpc):
+    """GraphedTrainStep (one captured CUDA graph per step) against the same steps submitted eagerly."""
+    def make():
+        torch.manual_seed(5)
+        cfg = small_resnet_cfg()
+        cfg['blocks'][2] = dict(cfg['blocks'][2], kernel_size_1=(30, 2), pooling_1=1, ceil_pooling=False)
+        cfg['blocks'][1] = dict(cfg['blocks'][1], kernel_size_2=(35, 1))
+        pre = cpc.PreprocessingModule(dict(cpc.cqt_default_dict), phase=True)
+        enc = cpc.ScalogramResidualEncoder(cfg, preprocessing_module=pre)
+        ar = cpc.ConvolutionalArModel({'kernel_sizes': [3, 3], 'channel_count': [24, 16, 16], 'stride': [1, 1],
+                                       'pooling': [1, 2], 'bias': True, 'batch_norm': True, 'residual': False,
+                                       'activation_register': None})
+        model = cpc.AudioPredictiveCodingModel(enc, ar, enc_size=24, ar_size=16, visible_steps=10, prediction_steps=3)
+        model.to(DEV).train()
+        pre.to(DEV)
+        trainer = cpc.ContrastiveEstimationTrainer(model=model, dataset=None, device=torch.device(DEV), regularization=0.1,
+                                                   score_over_all_timesteps=True,
+                                                   score_function=cpc.linear_score_function, preprocessing=pre,
+                                                   prediction_steps=3, verbose=False)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+        return model, trainer, opt
+    gen = torch.Generator().manual_seed(9)
+    model, trainer, opt = make()
+    batches = [0.1 * torch.randn(4, model.item_length, generator=gen) for _ in range(3)]
+    eager = []
+    for x in batches:
+        loss, _ = trainer.loss_on_batch(x.to(DEV))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        eager.append(loss.item())
+    model2, trainer2, opt2 = make()
+    step = cpc.GraphedTrainStep(trainer2, opt2, (4, model2.item_length), warmup=2)
+    graphed = [step(x.pin_memory())[0].item() for x in batches]
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) < 1e-4 * max(1.0, abs(a)), (eager, graphed)
+    # conv biases in front of a batch norm have zero true gradient: Adam turns their rounding noise (atomics order)
+    # into lr-sized steps, so they are not comparable between two runs of ANY implementation
+    noise_only = bn_shadowed_biases(model.state_dict().keys())
+    for (n, p), (_, q) in zip(model.named_parameters(), model2.named_parameters()):
+        if n not in noise_only:
+            assert rel_err(q, p) < 1e-4, n

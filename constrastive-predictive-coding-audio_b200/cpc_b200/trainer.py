@@ -221,8 +221,8 @@ class GraphedTrainStep:
         step = GraphedTrainStep(trainer, optimizer, (B, L))      # optimizer must be capturable (Adam(capturable=True))
         loss, max_score = step(batch)                            # batch: (B, L) device or pinned-host tensor
 
-    With more than one rank the gradient all-reduce and the optimizer step run eagerly after the replayed
-    forward/backward graph (NCCL work is not captured)."""
+    With more than one rank the step is two graphs (forward + backward + gradient flattening | un-flattening +
+    optimizer) with one eagerly submitted NCCL all-reduce of the flat gradient buffer between them."""
 
     def __init__(self, trainer, optimizer, batch_shape, warmup=3):
         self.trainer, self.optimizer = trainer, optimizer
@@ -254,13 +254,28 @@ class GraphedTrainStep:
                         v.copy_(old) if old is not None else v.zero_()
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
+        self.update_graph = None
         optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
             loss, max_score = trainer.loss_on_batch(self.static_batch)
             loss.backward()
             if self.world == 1:
                 optimizer.step()
+            else:                                                # all gradients in one flat buffer for ONE all-reduce
+                grads = [p.grad for p in self.params if p.grad is not None]
+                self.flat = torch.cat([g.reshape(-1) for g in grads])
             self.loss, self.max_score = loss.detach(), max_score.detach()
+        if self.world > 1:
+            # second graph (same memory pool): averaged gradients back into .grad, then the optimizer step.
+            # The NCCL all-reduce between the two replays is the only eagerly submitted operation of a step.
+            self.update_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.update_graph, pool=self.graph.pool()):
+                self.flat.div_(self.world)
+                offset = 0
+                for g in grads:
+                    g.copy_(self.flat[offset:offset + g.numel()].view_as(g))
+                    offset += g.numel()
+                optimizer.step()
 
     def _eager_step(self):
         self.optimizer.zero_grad(set_to_none=True)
@@ -274,8 +289,8 @@ class GraphedTrainStep:
         self.static_batch.copy_(batch, non_blocking=True)
         self.graph.replay()
         if self.world > 1:
-            ddp.allreduce_gradients(self.params, self.world)
-            self.optimizer.step()
+            torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM)
+            self.update_graph.replay()
         return self.loss, self.max_score
 
 

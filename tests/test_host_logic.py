@@ -174,6 +174,14 @@ total.backward()
 for p, q in zip(model.parameters(), ref.parameters()):
     assert torch.allclose(p.grad, q.grad, atol=1e-6), (p.grad - q.grad).abs().max()
 assert launched == len(red.buckets), (launched, len(red.buckets))
+# the synchronous helper used around CUDA-graph replays gives the same averages
+red.remove()
+model.zero_grad(set_to_none=True)
+loss = ((model(mine[0]) - mine[1]) ** 2).mean()
+loss.backward()
+ddp.allreduce_gradients([p for p in model.parameters()], world, bucket_mb=0.0005)
+for p, q in zip(model.parameters(), ref.parameters()):
+    assert torch.allclose(p.grad, q.grad, atol=1e-6), (p.grad - q.grad).abs().max()
 dist.barrier()
 print("RANK_OK", rank)
 '''

@@ -129,6 +129,8 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import cpc_b200

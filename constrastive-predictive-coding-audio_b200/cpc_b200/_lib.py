@@ -14,7 +14,7 @@ CQT_MAX_GROUPS = 16
 CQT_COMPLEX, CQT_LOGPOW, CQT_LOGPOW_PHASE = 0, 1, 2
 SCORE_LINEAR, SCORE_SOFTPLUS = 0, 1
 INFONCE_OUT_FLOATS = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CqtParams(ctypes.Structure):
@@ -70,6 +70,7 @@ SIGNATURES = {
     "cpc_conv_fwd": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_dgrad": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_wgrad": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
+    "cpc_conv_kernel_family": (ctypes.c_int, [ctypes.POINTER(ConvParams), ctypes.c_int]),
     "cpc_conv_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvParams), ctypes.c_int]),
     "cpc_conv_pack": (ctypes.c_int, [_P, _P, ctypes.POINTER(ConvParams), ctypes.c_int, _P]),
     "cpc_conv_fwd_ex": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, _P, ctypes.c_size_t, _P]),

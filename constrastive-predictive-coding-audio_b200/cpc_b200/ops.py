@@ -92,9 +92,15 @@ def _call(key, flops, fn, *args, nbytes=0.0):
     _lib.check(status, key.split(" ")[0])
 
 
+CONV_FAMILIES = {0: "conv_tiled_cuda_core", 1: "conv_small_k_direct", 2: "tall_conv_tcgen05_32ch", 3: "tall_conv_tcgen05_128ch",
+                 4: "conv_implicit_gemm_tcgen05"}
+
+
 def _conv_key(tag, p):
-    return "%s b%d %dx%dx%d->%dx%dx%d k%dx%d s%dx%d" % (tag, p.batch, p.c_in, p.h_in, p.w_in, p.c_out, p.h_out,
-                                                       p.w_out, p.kh, p.kw, p.stride_h, p.stride_w)
+    which = {"cpc_conv_fwd": 0, "cpc_conv_dgrad": 1, "cpc_conv_wgrad": 2}[tag]
+    fam = CONV_FAMILIES.get(_lib.load().cpc_conv_kernel_family(ctypes.byref(p), which), "?")
+    return "%s b%d %dx%dx%d->%dx%dx%d k%dx%d s%dx%d [%s]" % (tag, p.batch, p.c_in, p.h_in, p.w_in, p.c_out, p.h_out,
+                                                            p.w_out, p.kh, p.kw, p.stride_h, p.stride_w, fam)
 
 
 def _conv_flops(p):

@@ -297,6 +297,11 @@ static int conv_family(const cpc_conv_params* p, int which) {
     return tensor_core_path(p, which) ? 4 : 0;
 }
 
+extern "C" int cpc_conv_kernel_family(const cpc_conv_params* p, int which) {
+    if (validate(p) != CPC_OK || which < 0 || which > 2) return -1;
+    return conv_family(p, which);
+}
+
 extern "C" size_t cpc_conv_packed_bytes(const cpc_conv_params* p, int operand) {
     if (validate(p) != CPC_OK) return 0;
     const size_t planes = p->precision == 1 ? 1 : 2;

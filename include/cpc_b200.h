@@ -123,6 +123,11 @@ int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_pa
 int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Which kernel family serves this configuration (for profiling / reporting; which: 0 fwd, 1 dgrad, 2 wgrad):
+ * 0 tiled fp32 CUDA-core GEMM, 1 direct small-K kernel, 2 row-streaming tcgen05 (32 -> 32 channels, conv_tall.cu),
+ * 3 row-streaming tcgen05 (128 output channels, conv_tall128.cu), 4 generic implicit-GEMM tcgen05; -1 bad params. */
+int cpc_conv_kernel_family(const cpc_conv_params* p, int which);
+
 /* Optional operand caching.  The tensor-core kernels read bf16 hi/lo planes of their activation operand; by
  * default every call re-packs its fp32 inputs into the workspace.  A caller that keeps tensors across calls (an
  * autograd Function keeps x from forward to backward, and uses dy for both gradients) can pack each operand

@@ -113,6 +113,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
     affine[2 * c + 1] = b - g * rstd * mean;
 }
 
+// All streaming kernels below are two-phase per thread: issue every load of the thread's BN_PER_THREAD elements
+// first (independent, predicated), then compute and store -- one load in flight per thread is latency-bound.
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ affine,
                                                              const float* __restrict__ res, float* __restrict__ out,
                                                              BnGeom g) {
@@ -123,20 +125,28 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
     float* po = out + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
     const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
+    float xv[BN_PER_THREAD], rv[BN_PER_THREAD];
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
         const int i = i0 + u * BN_THREADS;
-        if (i < g.HW) {
-            float v = fmaf(__ldg(px + i), sc, sh);
-            if (g.relu) v = fmaxf(v, 0.f);
-            if (pr) {
-                int h, w;
-                g.d_w.divmod(i, h, w);
-                v += __ldg(pr + (size_t)h * g.RW + w);
-                if (g.outer_relu) v = fmaxf(v, 0.f);
-            }
-            po[i] = v;
+        xv[u] = i < g.HW ? __ldg(px + i) : 0.f;
+        rv[u] = 0.f;
+        if (pr && i < g.HW) {
+            int h, w;
+            g.d_w.divmod(i, h, w);
+            rv[u] = __ldg(pr + (size_t)h * g.RW + w);
         }
+    }
+#pragma unroll
+    for (int u = 0; u < BN_PER_THREAD; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        float v = fmaf(xv[u], sc, sh);
+        if (g.relu) v = fmaxf(v, 0.f);
+        if (pr) {
+            v += rv[u];
+            if (g.outer_relu) v = fmaxf(v, 0.f);
+        }
+        if (i < g.HW) po[i] = v;
     }
 }
 
@@ -168,19 +178,28 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     const float* pd = dout + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
     const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
+    float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[BN_PER_THREAD];
+    const bool need_res = pr != nullptr && g.outer_relu;
+#pragma unroll
+    for (int u = 0; u < BN_PER_THREAD; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        const bool in = i < g.HW;
+        xv[u] = in ? __ldg(px + i) : 0.f;
+        dv[u] = in ? __ldg(pd + i) : 0.f;
+        rv[u] = 0.f;
+        if (need_res && in) {
+            int h, w;
+            g.d_w.divmod(i, h, w);
+            rv[u] = __ldg(pr + (size_t)h * g.RW + w);
+        }
+    }
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
         const int i = i0 + u * BN_THREADS;
         if (i < g.HW) {
-            float resv = 0.f;
-            if (pr && g.outer_relu) {
-                int h, w;
-                g.d_w.divmod(i, h, w);
-                resv = __ldg(pr + (size_t)h * g.RW + w);
-            }
             float xhat, g1;
-            const float g2 = bn_grad_in(__ldg(pd + i), __ldg(px + i), mean, rstd, gam, bet, pr != nullptr, resv, g, xhat, g1);
+            const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, rv[u], g, xhat, g1);
             s += g2;
             q = fmaf(g2, xhat, q);
         }
@@ -222,17 +241,32 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     const float* pr = res ? res + roff : nullptr;
     float* pdr = d_res ? d_res + roff : nullptr;
     const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
+    float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[BN_PER_THREAD];
+    int ro[BN_PER_THREAD];                                           // offset inside the residual plane
+    const bool need_res = pr != nullptr && g.outer_relu;
+#pragma unroll
+    for (int u = 0; u < BN_PER_THREAD; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        const bool in = i < g.HW;
+        xv[u] = in ? __ldg(px + i) : 0.f;
+        dv[u] = in ? __ldg(pd + i) : 0.f;
+        rv[u] = 0.f;
+        ro[u] = 0;
+        if ((pr || pdr) && in) {
+            int h, w;
+            g.d_w.divmod(i, h, w);
+            ro[u] = h * g.RW + w;
+            if (need_res) rv[u] = __ldg(pr + ro[u]);
+        }
+    }
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
         const int i = i0 + u * BN_THREADS;
         if (i < g.HW) {
-            int h = 0, w = 0;
-            if (pr || pdr) g.d_w.divmod(i, h, w);
-            const float resv = (pr && g.outer_relu) ? __ldg(pr + (size_t)h * g.RW + w) : 0.f;
             float xhat, g1;
-            const float g2 = bn_grad_in(__ldg(pd + i), __ldg(px + i), mean, rstd, gam, bet, pr != nullptr, resv, g, xhat, g1);
+            const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, rv[u], g, xhat, g1);
             pdx[i] = k * (g2 - m1 - xhat * m2);
-            if (pdr) pdr[(size_t)h * g.RW + w] = g1;
+            if (pdr) pdr[ro[u]] = g1;
         }
     }
 }

@@ -42,6 +42,7 @@ struct UmmaConv {
     int planes;                          // 2 = fp32-faithful split, 1 = bf16
     int nrep;                            // replicas per plane in the packed operand (>= tw)
     int srcH;                            // rows of the source tensor (taps landing outside are all-zero)
+    int w_resident;                      // 1: all packed weight chunks live in shared memory for the whole kernel
     int relu, stages;
     const float* bias;
     float* y;
@@ -142,7 +143,7 @@ __device__ __forceinline__ bool umma_chunk_live(const UmmaConv& p, int q, int ro
 }
 
 struct __align__(8) UmmaBarriers {
-    uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
+    uint64_t full[8], empty[8], acc_full[2], acc_empty[2], wfull;
     uint32_t tmem_base;
 };
 
@@ -152,8 +153,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_plane_bytes = p.n_tile * 128;
-    const int stage_bytes = p.planes * (A_PLANE_BYTES + b_plane_bytes);
-    UmmaBarriers* bars = reinterpret_cast<UmmaBarriers*>(smem + (size_t)p.stages * stage_bytes);
+    // weights-resident mode: [all chunks: planes x n_tile x 128 B][A-only stages]; else [stages of A + B]
+    const int w_chunk_bytes = p.planes * b_plane_bytes;
+    const int w_res_bytes = p.w_resident ? p.n_chunks * w_chunk_bytes : 0;
+    const int stage_bytes = p.planes * A_PLANE_BYTES + (p.w_resident ? 0 : w_chunk_bytes);
+    uint8_t* w_res = smem;
+    uint8_t* stages_base = smem + w_res_bytes;
+    UmmaBarriers* bars = reinterpret_cast<UmmaBarriers*>(stages_base + (size_t)p.stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_mtiles = (p.n_atoms + 1) >> 1;
     const int n_tiles = n_mtiles * p.n_ntiles;
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
         prefetch_tmap(&tmap_b);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 4); }
+        mbar_init(&bars->wfull, 1);
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
@@ -172,48 +179,64 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int mtile = tile / p.n_ntiles, ntile = tile - mtile * p.n_ntiles;
-                int ab[2], aoh[2], aw0[2];
-                for (int a = 0; a < 2; ++a) {
-                    const int atom = mtile * 2 + a;            // beyond n_atoms -> batch index OOB -> zero fill
-                    const int row = atom / p.AW;
-                    aw0[a] = (atom - row * p.AW) * ATOM;
-                    ab[a] = row / p.PH;
-                    aoh[a] = (row - ab[a] * p.PH) * p.h_mul + p.h_off;
-                }
-                const bool may_skip = umma_tile_may_skip(p, aoh[0], aoh[1]);
-                for (int q = 0; q < p.n_chunks; ++q) {
-                    if (may_skip && !umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
+        // ===== TMA producer: the whole warp runs the loop in lockstep and the loads of one stage are issued by
+        // different lanes (one load each), so the per-load index arithmetic runs in parallel instead of on one thread =====
+        if (p.w_resident) {                                     // every tile of this CTA uses the same (only) N tile
+            if (lane == 0) mbar_expect_tx(&bars->wfull, (uint32_t)w_res_bytes);
+            __syncwarp();
+            for (int l = lane; l < p.n_chunks * p.planes; l += 32) {
+                const int q = l / p.planes, pl = l - q * p.planes;
+                tma_load_4d(w_res + q * w_chunk_bytes + pl * b_plane_bytes, &tmap_b, &bars->wfull, 0, 0, q, pl);
+            }
+        }
+        const int taps_per_load = p.cin_eff == KCHUNK ? 1 : p.tpc;
+        const int n_a_loads = p.planes * 2 * taps_per_load;     // (plane, atom, tap-in-chunk)
+        const int n_loads = n_a_loads + (p.w_resident ? 0 : p.planes);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mtile = tile / p.n_ntiles, ntile = tile - mtile * p.n_ntiles;
+            int ab[2], aoh[2], aw0[2];
+            for (int a = 0; a < 2; ++a) {
+                const int atom = mtile * 2 + a;                 // beyond n_atoms -> batch index OOB -> zero fill
+                const int row = atom / p.AW;
+                aw0[a] = (atom - row * p.AW) * ATOM;
+                ab[a] = row / p.PH;
+                aoh[a] = (row - ab[a] * p.PH) * p.h_mul + p.h_off;
+            }
+            const bool may_skip = umma_tile_may_skip(p, aoh[0], aoh[1]);
+            for (int q = 0; q < p.n_chunks; ++q) {
+                if (may_skip && !umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
+                if (lane == 0) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    uint8_t* st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
-                    for (int pl = 0; pl < p.planes; ++pl) {
-                        uint8_t* a_dst = st + pl * A_PLANE_BYTES;
-                        for (int a = 0; a < 2; ++a) {
-                            if (p.cin_eff == KCHUNK) {
-                                const int tap = q / p.cin_chunks, c0 = (q - tap * p.cin_chunks) * KCHUNK;
-                                const int i = tap / p.tw, j = tap - i * p.tw;
-                                tma_load_5d(a_dst + a * (KCHUNK * 128), &tmap_a, &bars->full[stage], aw0[a],
-                                            aoh[a] + i * p.tap_h_mul, c0, ab[a], pl * p.nrep + j);
-                            } else {
-                                for (int t = 0; t < p.tpc; ++t) {
-                                    int tap = q * p.tpc + t;
-                                    if (tap >= p.ntaps) tap = 0;        // phantom tap: its packed weights are zero
-                                    const int i = tap / p.tw, j = tap - i * p.tw;
-                                    tma_load_5d(a_dst + a * (KCHUNK * 128) + t * p.cin_eff * 128, &tmap_a, &bars->full[stage],
-                                                aw0[a], aoh[a] + i * p.tap_h_mul, 0, ab[a], pl * p.nrep + j);
-                                }
-                            }
+                }
+                __syncwarp();
+                uint8_t* st = stages_base + (size_t)stage * stage_bytes;
+                for (int l = lane; l < n_loads; l += 32) {
+                    if (l < n_a_loads) {
+                        const int t = l % taps_per_load;
+                        const int a = (l / taps_per_load) & 1;
+                        const int pl = l / (2 * taps_per_load);
+                        uint8_t* a_dst = st + pl * A_PLANE_BYTES + a * (KCHUNK * 128);
+                        if (p.cin_eff == KCHUNK) {
+                            const int tap = q / p.cin_chunks, c0 = (q - tap * p.cin_chunks) * KCHUNK;
+                            const int i = tap / p.tw, j = tap - i * p.tw;
+                            tma_load_5d(a_dst, &tmap_a, &bars->full[stage], aw0[a], aoh[a] + i * p.tap_h_mul, c0, ab[a],
+                                        pl * p.nrep + j);
+                        } else {
+                            int tap = q * p.tpc + t;
+                            if (tap >= p.ntaps) tap = 0;        // phantom tap: its packed weights are zero
+                            const int i = tap / p.tw, j = tap - i * p.tw;
+                            tma_load_5d(a_dst + t * p.cin_eff * 128, &tmap_a, &bars->full[stage], aw0[a],
+                                        aoh[a] + i * p.tap_h_mul, 0, ab[a], pl * p.nrep + j);
                         }
+                    } else {
+                        const int pl = l - n_a_loads;
                         tma_load_4d(st + p.planes * A_PLANE_BYTES + pl * b_plane_bytes, &tmap_b, &bars->full[stage], 0,
                                     ntile * p.n_tile, q, pl);
                     }
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -222,6 +245,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
             const uint32_t idesc = make_idesc_bf16(128, p.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t acc_phase = 0;
+            if (p.w_resident) { mbar_wait(&bars->wfull, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 mbar_wait(&bars->acc_empty[buf], acc_phase ^ 1);
                 tc_fence_after();
@@ -239,8 +263,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                     if (may_skip && !umma_chunk_live(p, q, aoh[0], aoh[1])) continue;
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
-                    const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t b0 = st + p.planes * A_PLANE_BYTES;
+                    const uint32_t st = smem_u32(stages_base + (size_t)stage * stage_bytes);
+                    const uint32_t b0 = p.w_resident ? smem_u32(w_res + q * w_chunk_bytes) : st + p.planes * A_PLANE_BYTES;
                     const int ncombo = p.planes == 2 ? 3 : 1;
                     for (int cb = 0; cb < ncombo; ++cb) {
                         const uint32_t a_addr = st + (cb == 2 ? A_PLANE_BYTES : 0);          // (hi,hi) (hi,lo) (lo,hi)
@@ -319,7 +343,7 @@ struct ConvProblem {
 
 struct UmmaPlan {
     bool ok;
-    int Wp, cin_eff, cin_chunks, tpc, n_chunks, n_tile, n_ntiles, planes, stages;
+    int Wp, cin_eff, cin_chunks, tpc, n_chunks, n_tile, n_ntiles, planes, stages, w_resident;
     size_t act_bytes, w_bytes, smem_bytes;
 };
 
@@ -340,11 +364,16 @@ static UmmaPlan plan_problem(const ConvProblem& c, int batch, int precision) {
     u.n_ntiles = co / u.n_tile;
     u.planes = precision == 1 ? 1 : 2;
     u.Wp = c.pre ? c.pre_Wp : (c.PW + 7) & ~7;         // replicas are addressed by GEMM pixel column
-    const int stage_bytes = u.planes * (A_PLANE_BYTES + u.n_tile * 128);
-    u.stages = (SMEM_LIMIT - 2048) / stage_bytes;
+    int stage_bytes = u.planes * (A_PLANE_BYTES + u.n_tile * 128);
+    // all weight chunks fit next to >= 3 activation-only stages: keep them resident (every tile re-reads them otherwise)
+    const long w_all = (long)u.n_chunks * u.planes * u.n_tile * 128;
+    u.w_resident = u.n_ntiles == 1 && w_all + 3L * u.planes * A_PLANE_BYTES <= SMEM_LIMIT - 2048;
+    long avail = SMEM_LIMIT - 2048;
+    if (u.w_resident) { stage_bytes = u.planes * A_PLANE_BYTES; avail -= w_all; }
+    u.stages = (int)(avail / stage_bytes);
     if (u.stages > 8) u.stages = 8;
     if (u.stages < 2) return u;
-    u.smem_bytes = (size_t)u.stages * stage_bytes + sizeof(UmmaBarriers) + 1024;
+    u.smem_bytes = (size_t)(u.w_resident ? w_all : 0) + (size_t)u.stages * stage_bytes + sizeof(UmmaBarriers) + 1024;
     u.act_bytes = c.pre ? 0 : align_up((size_t)u.planes * c.tm.tw * batch * ci * c.srcH * u.Wp * 2, 1024);
     u.w_bytes = align_up((size_t)u.planes * u.n_chunks * co * KCHUNK * 2, 1024);
     u.ok = true;
@@ -396,7 +425,7 @@ static int run_problem(const ConvProblem& c, const float* w, const float* bias, 
     k.cin_chunks = u.cin_chunks; k.n_chunks = u.n_chunks;
     k.h_mul = c.h_mul; k.tap_h_mul = c.tap_h_mul; k.h_off = c.h_off;
     k.out_H = c.out_H; k.out_W = c.out_W; k.oh_mul = c.oh_mul; k.oh_off = c.oh_off; k.ow_mul = c.ow_mul; k.ow_off = c.ow_off;
-    k.planes = u.planes; k.nrep = nrep; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out; k.srcH = c.srcH;
+    k.planes = u.planes; k.nrep = nrep; k.w_resident = u.w_resident; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out; k.srcH = c.srcH;
     if (cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int n_tiles = ((k.n_atoms + 1) / 2) * k.n_ntiles;

@@ -652,22 +652,27 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_wgrad_kernel(const __grid_
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int q = q_begin; q < q_end; ++q) {
-                const int row = q / p.AW;
-                const int w0 = (q - row * p.AW) * ATOM;
-                const int b = row / p.OH, oh = row - b * p.OH;
+        // whole warp in lockstep; lanes 0 .. 2*planes-1 issue one TMA load each (x / dy, per plane)
+        int stage = 0; uint32_t phase = 0;
+        for (int q = q_begin; q < q_end; ++q) {
+            const int row = q / p.AW;
+            const int w0 = (q - row * p.AW) * ATOM;
+            const int b = row / p.OH, oh = row - b * p.OH;
+            if (lane == 0) {
                 mbar_wait(&bars->empty[stage], phase ^ 1);
-                uint8_t* st = smem + (size_t)stage * stage_bytes;
                 mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
-                for (int pl = 0; pl < p.planes; ++pl) {
-                    tma_load_5d(st + pl * A_BYTES, &tmap_x, &bars->full[stage], w0, oh * p.sh + i0 - p.pt, c0, b, pl * p.kw + j);
-                    tma_load_5d(st + p.planes * A_BYTES + pl * b_bytes, &tmap_dy, &bars->full[stage], w0, oh,
-                                ntile * p.n_tile, b, pl);
-                }
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            uint8_t* st = smem + (size_t)stage * stage_bytes;
+            if (lane < 2 * p.planes) {
+                const int pl = lane >> 1;
+                if ((lane & 1) == 0)
+                    tma_load_5d(st + pl * A_BYTES, &tmap_x, &bars->full[stage], w0, oh * p.sh + i0 - p.pt, c0, b, pl * p.kw + j);
+                else
+                    tma_load_5d(st + p.planes * A_BYTES + pl * b_bytes, &tmap_dy, &bars->full[stage], w0, oh, ntile * p.n_tile,
+                                b, pl);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
         if (lane == 0) {

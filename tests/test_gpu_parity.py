@@ -652,3 +652,34 @@ def test_cuda_graph_step_reproduces_eager_steps(cpc):
     for (n, p), (_, q) in zip(model.named_parameters(), model2.named_parameters()):
         if n not in noise_only:
             assert rel_err(q, p) < 1e-4, n
+
+
+@pytest.mark.parametrize("name", ["e24", "e25", "e20"])
+def test_experiment_configs_train_one_step(cpc, name):
+    """The reference's experiment dicts (conv AR, per-step scoring, attention AR) drive the B200 path unchanged:
+    setup_model -> trainer -> one optimisation step at the full item length, small batch."""
+    exp = cpc.configs.experiment(name)
+    tc = exp["training_config"]
+    torch.manual_seed(0)
+    model, pre, _ = cpc.configs.setup_model(exp["cqt_config"], exp["encoder_config"], exp["ar_model_config"], tc,
+                                            device=torch.device(DEV))
+    assert model.item_length == 97024
+    trainer = cpc.ContrastiveEstimationTrainer(model=model, dataset=None, device=torch.device(DEV),
+                                               regularization=tc["regularization"],
+                                               score_over_all_timesteps=tc["score_over_all_timesteps"],
+                                               score_function=tc["score_function"], preprocessing=pre,
+                                               prediction_steps=tc["prediction_steps"], verbose=False)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    model.train()
+    x = 0.1 * torch.randn(8, model.item_length, generator=torch.Generator().manual_seed(2))
+    losses = []
+    for _ in range(2):
+        loss, max_score = trainer.loss_on_batch(x.to(DEV))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(math.isfinite(v) for v in losses), losses
+    n = 8 * tc["prediction_steps"] if tc["score_over_all_timesteps"] else 8
+    assert losses[0] < 3.0 * math.log(n) + 60.0             # untrained model: within sight of the uniform-softmax loss
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())

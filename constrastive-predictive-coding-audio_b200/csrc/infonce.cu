@@ -14,7 +14,24 @@
 //           dP += G Zc and dZc += G^T P with fp32 atomics.  No B*K x B*K tensor ever reaches HBM.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace cpc {
+
+// infonce_umma.cu: tcgen05 path (>= 128 candidates per softmax, E % 64 == 0)
+bool nce_umma_eligible(const cpc_infonce_params* p, int which);
+size_t nce_umma_workspace(const cpc_infonce_params* p, int which);
+int nce_umma_fwd(const float* pred, const float* targets, float* out, float* lse, const cpc_infonce_params* p,
+                 void* workspace, size_t workspace_bytes, cudaStream_t s);
+int nce_umma_bwd(const float* pred, const float* targets, const float* lse, const float* grad_loss, float* d_pred,
+                 float* d_targets, const cpc_infonce_params* p, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+// CPC_NO_TENSOR_INFONCE=1 keeps everything on the CUDA-core kernels (A/B switch for tests)
+static bool nce_tensor_path(const cpc_infonce_params* p, int which) {
+    const char* e = std::getenv("CPC_NO_TENSOR_INFONCE");
+    if (e && e[0] == '1') return false;
+    return nce_umma_eligible(p, which);
+}
 
 struct NceGeom {
     int B, K, E, all, kind;
@@ -455,10 +472,13 @@ using namespace cpc;
 
 extern "C" size_t cpc_infonce_workspace_bytes(const cpc_infonce_params* p, int which) {
     if (nce_validate(p) != CPC_OK) return 0;
-    if (which == 1) return 0;
+    if (which == 1) return nce_umma_eligible(p, 1) ? nce_umma_workspace(p, 1) : 0;
     const NceGeom g = nce_geom(p);
-    const size_t fwd = nce_ws(g, nullptr).bytes;
-    if (which == 0) return fwd;
+    size_t fwd = nce_ws(g, nullptr).bytes;
+    if (which == 0) {
+        if (nce_umma_eligible(p, 0) && nce_umma_workspace(p, 0) > fwd) fwd = nce_umma_workspace(p, 0);
+        return fwd;
+    }
     // validate: forward scratch + lse + 4 scalars + per-(column tile, row) arg-max partials
     const size_t rows = (size_t)ceil_div(g.C, TILE) * g.nprob * g.R;
     return fwd + align_up(sizeof(float) * (size_t)g.ncols, 256) + 256 + 2 * align_up(sizeof(float) * rows, 256);
@@ -471,9 +491,10 @@ extern "C" int cpc_infonce_fwd(const float* pred, const float* targets, float* o
     if (!pred || !targets || !out || !lse) return CPC_ERR_NULL;
     NceGeom g = nce_geom(p);
     NceWs w = nce_ws(g, workspace);
-    if (!workspace || workspace_bytes < w.bytes) return CPC_ERR_WORKSPACE;
+    if (!workspace || workspace_bytes < cpc_infonce_workspace_bytes(p, 0)) return CPC_ERR_WORKSPACE;
     if ((st = check_device()) != CPC_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
+    if (nce_tensor_path(p, 0)) return nce_umma_fwd(pred, targets, out, lse, p, workspace, workspace_bytes, s);
     dim3 grid(ceil_div(g.C, TILE), g.nrowtiles);
     nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta, nullptr, nullptr);
     CPC_LAUNCH_CHECK();
@@ -488,13 +509,16 @@ extern "C" int cpc_infonce_fwd(const float* pred, const float* targets, float* o
 extern "C" int cpc_infonce_bwd(const float* pred, const float* targets, const float* lse, const float* grad_loss,
                                float* d_pred, float* d_targets, const cpc_infonce_params* p, void* workspace,
                                size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     int st = nce_validate(p);
     if (st != CPC_OK) return st;
     if (!pred || !targets || !lse || !grad_loss || !d_pred || !d_targets) return CPC_ERR_NULL;
     if ((st = check_device()) != CPC_OK) return st;
     NceGeom g = nce_geom(p);
     cudaStream_t s = (cudaStream_t)stream;
+    if (nce_tensor_path(p, 1)) {
+        if (!workspace || workspace_bytes < nce_umma_workspace(p, 1)) return CPC_ERR_WORKSPACE;
+        return nce_umma_bwd(pred, targets, lse, grad_loss, d_pred, d_targets, p, workspace, workspace_bytes, s);
+    }
     const size_t n = sizeof(float) * (size_t)g.B * g.K * g.E;
     if (cudaMemsetAsync(d_pred, 0, n, s) != cudaSuccess) return CPC_ERR_CUDA;
     if (cudaMemsetAsync(d_targets, 0, n, s) != cudaSuccess) return CPC_ERR_CUDA;

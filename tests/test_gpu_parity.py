@@ -461,6 +461,37 @@ def test_infonce_matches_oracle_native_sizes_and_strided_targets(cpc, b, k, e, a
             assert abs(loss0.item() - loss.item()) < 1e-6
 
 
+@pytest.mark.parametrize("b,k,e,all_steps", [(256, 4, 256, False), (200, 3, 128, False), (64, 16, 512, True),
+                                             (40, 8, 64, True), (150, 4, 320, True), (129, 1, 64, False)])
+def test_infonce_tensor_core_path_matches_oracle_and_cuda_core_path(cpc, b, k, e, all_steps):
+    """tcgen05 InfoNCE (>= 128 candidates, E % 64 == 0) against the fp64 oracle and against the CUDA-core kernels."""
+    import os
+    gen = torch.Generator().manual_seed(b + 7 * k)
+    pred = torch.randn(b, k, e, generator=gen) * (2.0 / math.sqrt(e))
+    z = torch.randn(b, e, k + 3, generator=gen)
+    for kind in ("linear", "softplus"):
+        want_loss, want_max, want_dp, want_dz = O.infonce_with_grads(pred, z[:, :, -k:], all_steps, kind, 0.0)
+        res = {}
+        for flag in ("0", "1"):
+            os.environ["CPC_NO_TENSOR_INFONCE"] = flag
+            try:
+                pg = pred.clone().to(DEV).requires_grad_(True)
+                zg = z.clone().to(DEV).requires_grad_(True)
+                loss, mx, _, mean_s = cpc.ops.infonce(pg, zg[:, :, -k:], all_steps, kind, 0.0)
+                (2.0 * loss).backward()
+                res[flag] = (loss.item(), mx.item(), mean_s.item(), pg.grad.clone(), zg.grad.clone())
+            finally:
+                os.environ["CPC_NO_TENSOR_INFONCE"] = "0"
+        for flag in ("0", "1"):
+            loss, mx, mean_s, dp, dz = res[flag]
+            assert abs(loss - float(want_loss)) < TOL * max(1.0, abs(float(want_loss))), (flag, kind)
+            assert abs(mx - float(want_max)) < TOL * max(1.0, abs(float(want_max))), (flag, kind)
+            assert rel_err(dp, 2.0 * want_dp) < TOL, (flag, kind)
+            assert rel_err(dz[:, :, -k:], 2.0 * want_dz) < TOL, (flag, kind)
+        assert abs(res["0"][2] - res["1"][2]) < 1e-4 * max(1.0, abs(res["1"][2]))
+        assert rel_err(res["0"][3], res["1"][3]) < 1e-4 and rel_err(res["0"][4], res["1"][4]) < 1e-4
+
+
 def test_infonce_full_size_property(cpc):
     """Sweep corner the reference cannot materialise (N = 4096 candidates, K = 8): loss of a perfectly
     predictable batch -> ~0 and of an uninformative one -> log N."""

@@ -466,6 +466,9 @@ bool nce_umma_eligible(const cpc_infonce_params* p, int which) {
     if (p->precision != 0 || p->enc % 64 != 0 || p->enc < 64 || p->enc > 4096) return false;
     const long bp = p->all_steps ? (long)p->batch * p->steps : p->batch;
     if (bp < 128 || bp > (1 << 24)) return false;                          // tiny problems are latency-bound either way
+    // one CTA per 128 owner rows: a single all-steps problem needs >= 20 row tiles to fill the machine better than
+    // the CUDA-core kernel does (measured cross-over, tools/infonce_sweep.py); per-step mode has K problems
+    if (p->all_steps && bp < 2560) return false;
     if (p->regularization != 0.f) {
         if (which == 1) return false;                                       // regulariser gradient: CUDA-core kernel
         if (!p->all_steps || 128 % p->steps != 0) return false;            // forward needs whole K-groups inside a tile

@@ -461,8 +461,8 @@ def test_infonce_matches_oracle_native_sizes_and_strided_targets(cpc, b, k, e, a
             assert abs(loss0.item() - loss.item()) < 1e-6
 
 
-@pytest.mark.parametrize("b,k,e,all_steps", [(256, 4, 256, False), (200, 3, 128, False), (64, 16, 512, True),
-                                             (40, 8, 64, True), (150, 4, 320, True), (129, 1, 64, False)])
+@pytest.mark.parametrize("b,k,e,all_steps", [(256, 4, 256, False), (200, 3, 128, False), (170, 16, 128, True),
+                                             (330, 8, 64, True), (129, 1, 64, False)])
 def test_infonce_tensor_core_path_matches_oracle_and_cuda_core_path(cpc, b, k, e, all_steps):
     """tcgen05 InfoNCE (>= 128 candidates, E % 64 == 0) against the fp64 oracle and against the CUDA-core kernels."""
     import os

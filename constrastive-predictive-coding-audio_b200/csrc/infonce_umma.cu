@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) nce_umma_final_kernel(const float* __rest
 
 // ---- backward -----------------------------------------------------------------------------------------------
 struct __align__(8) NuBwdBarriers {
-    uint64_t full[NU_BSTAGES], empty[NU_BSTAGES], s_full, s_empty, g_full, g_empty, acc_full;
+    uint64_t full[NU_BSTAGES], empty[NU_BSTAGES], s_full[2], s_empty[2], g_full, g_empty, acc_full;
     uint32_t tmem_base;
     float lse_s[2][128];                          // target lse of the current other-tile, double-buffered by tile parity
 };
@@ -291,8 +291,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
         prefetch_tmap(&tmap_owner);
         prefetch_tmap(&tmap_other);
         for (int s = 0; s < NU_BSTAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->s_empty, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->s_full[b], 1); mbar_init(&bars->s_empty[b], 4); }
         mbar_init(&bars->g_full, 4);
         mbar_init(&bars->g_empty, 1);
         mbar_init(&bars->acc_full, 1);
@@ -306,9 +305,10 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
 
     if (warp == 0) {
         if (lane == 0) {
+            // order of ring uses (the MMA issuer consumes in the same order): P1(0), then per tile st: P1(st+1), P3(st)
             uint32_t n = 0;
-            for (int st = 0; st < g.nT; ++st) {
-                for (int q = 0; q < g.EC; ++q, ++n) {                         // phase 1: S = owner . other^T over E
+            auto phase1 = [&](int st) {                                      // S = owner . other^T over E
+                for (int q = 0; q < g.EC; ++q, ++n) {
                     const int stage = n % NU_BSTAGES;
                     mbar_wait(&bars->empty[stage], ((n / NU_BSTAGES) & 1) ^ 1);
                     mbar_expect_tx(&bars->full[stage], 2 * NU_TILE);
@@ -316,6 +316,10 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                     tma_load_4d(sp, &tmap_owner, &bars->full[stage], q * 64, ot * 128, prob, 0);
                     tma_load_4d(sp + NU_TILE, &tmap_other, &bars->full[stage], q * 64, st * 128, prob, 0);
                 }
+            };
+            phase1(0);
+            for (int st = 0; st < g.nT; ++st) {
+                if (st + 1 < g.nT) phase1(st + 1);
                 for (int a = 0; a < e_chunks; ++a, ++n) {                    // phase 3: other rows, E slice chunk a
                     const int stage = n % NU_BSTAGES;
                     mbar_wait(&bars->empty[stage], ((n / NU_BSTAGES) & 1) ^ 1);
@@ -331,8 +335,10 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
             const uint32_t idesc_g = make_idesc_bf16(128, 64, 0, 1);         // acc: A = G K-major, B = other MN-major
             const uint32_t gs_addr = smem_u32(gs);
             uint32_t n = 0;
-            for (int st = 0; st < g.nT; ++st) {
-                mbar_wait(&bars->s_empty, (st & 1) ^ 1);                     // epilogue finished reading the previous S
+            // S is double-buffered (TMEM columns 0-127 / 128-255): the score GEMM of tile st+1 overlaps the epilogue of st
+            auto phase1 = [&](int st) {
+                const uint32_t buf = st & 1;
+                mbar_wait(&bars->s_empty[buf], ((st >> 1) & 1) ^ 1);         // epilogue finished reading this S buffer
                 tc_fence_after();
                 for (int q = 0; q < g.EC; ++q, ++n) {
                     const int stage = n % NU_BSTAGES;
@@ -345,12 +351,16 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                         const uint32_t b_addr = b0 + (cb == 1 ? 128 * 128 : 0);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_bf16(tmem_base, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024),
-                                     idesc_s, (uint32_t)(q | cb | k));
+                            mma_bf16(tmem_base + buf * 128, make_smem_desc(a_addr + k * 32, 16, 1024),
+                                     make_smem_desc(b_addr + k * 32, 16, 1024), idesc_s, (uint32_t)(q | cb | k));
                     }
                     tc_commit(&bars->empty[stage]);
                 }
-                tc_commit(&bars->s_full);
+                tc_commit(&bars->s_full[buf]);
+            };
+            phase1(0);
+            for (int st = 0; st < g.nT; ++st) {
+                if (st + 1 < g.nT) phase1(st + 1);
                 mbar_wait(&bars->g_full, st & 1);                            // G tile written (and fenced) by the epilogue warps
                 tc_fence_after();
                 for (int a = 0; a < e_chunks; ++a, ++n) {
@@ -358,7 +368,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                     mbar_wait(&bars->full[stage], (n / NU_BSTAGES) & 1);
                     tc_fence_after();
                     const uint32_t b0 = smem_u32(ring + stage * 2 * NU_TILE + NU_TILE);
-                    const uint32_t d_tmem = tmem_base + 128 + (uint32_t)a * 64;
+                    const uint32_t d_tmem = tmem_base + 256 + (uint32_t)a * 64;
 #pragma unroll
                     for (int cb = 0; cb < 3; ++cb) {                         // (G hi, X hi) (G hi, X lo) (G lo, X hi)
                         const uint32_t ga = gs_addr + (cb == 2 ? NU_TILE : 0);           // lo plane of G
@@ -390,13 +400,13 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                 const int c = st * 128 + rl;
                 bars->lse_s[st & 1][rl] = c < g.Bp ? __ldg(p.lse + (size_t)prob * g.Bp + c) : 0.f;
             }
-            mbar_wait(&bars->s_full, st & 1);
+            mbar_wait(&bars->s_full[st & 1], (st >> 1) & 1);
             tc_fence_after();
             mbar_wait(&bars->g_empty, (st & 1) ^ 1);                         // previous G tile consumed by the MMAs
             asm volatile("bar.sync 1, 128;" ::: "memory");                  // lse_s visible to all epilogue threads
             for (int n0 = 0; n0 < 128; n0 += 32) {
                 uint32_t raw[32];
-                tmem_ld32(lane_base + n0, raw);
+                tmem_ld32(lane_base + (uint32_t)((st & 1) * 128 + n0), raw);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
             tc_fence_before();
             fence_proxy_async();                                             // generic-proxy smem writes -> tensor core
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&bars->g_full); mbar_arrive(&bars->s_empty); }
+            if (lane == 0) { mbar_arrive(&bars->g_full); mbar_arrive(&bars->s_empty[st & 1]); }
         }
         // flush the accumulator: rows = owner rows, columns = E slice
         mbar_wait(&bars->acc_full, 0);
@@ -434,7 +444,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
         for (int a = 0; a < e_chunks; ++a)
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
-                tmem_ld32(lane_base + 128 + (uint32_t)(a * 64 + h * 32), raw);
+                tmem_ld32(lane_base + 256 + (uint32_t)(a * 64 + h * 32), raw);
                 tmem_ld_wait();
                 if (!own_ok) continue;
                 const int e0 = (es * 4 + a) * 64 + h * 32;

@@ -84,6 +84,7 @@ struct __align__(8) NuFwdBarriers {
 };
 
 // per-CTA partials: [cta][0] sum over its columns of (lse - diag), [1] max score, [2] sum of scores, [3] regulariser
+template <int KIND, bool REG>
 __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_fwd_kernel(const __grid_constant__ CUtensorMap tmap_z,
                                                                     const __grid_constant__ CUtensorMap tmap_p,
                                                                     const NuGeom g, float* __restrict__ lse,
@@ -161,40 +162,46 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_fwd_kernel(const __gri
             mbar_wait(&bars->acc_full[buf], (rt >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 128;
+            const int n_valid = min(128, g.Bp - rt * 128);                   // prediction rows of this tile inside the problem
             for (int n0 = 0; n0 < 128; n0 += 32) {
                 uint32_t raw[32];
                 tmem_ld32(taddr + n0, raw);
                 tmem_ld_wait();
-                if (col_ok) {
-                    float v[32];
-                    float bmax = -INFINITY;
+                if (!col_ok || n0 >= n_valid) continue;
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int r = rt * 128 + n0 + j;
-                        float s = __uint_as_float(raw[j]);
-                        if (g.kind == CPC_SCORE_SOFTPLUS) s = nu_softplus(s);
-                        const bool ok = r < g.Bp;
-                        v[j] = ok ? s : -INFINITY;
-                        if (ok) {
-                            bmax = fmaxf(bmax, s);
-                            vsum += s;
-                            if (r == c) diag = s;
-                            if (g.lambda != 0.f) {                           // all-steps only: groups of K rows = one item d
-                                grp += s;
-                                if ((r + 1) % g.K == 0) { const float a = grp * inv_k; reg += a * a; grp = 0.f; }
-                            }
-                        }
-                    }
-                    if (bmax > -INFINITY) {
-                        vmax = fmaxf(vmax, bmax);
-                        const float mn = fmaxf(m, bmax);
-                        float acc = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc += __expf(v[j] - mn);      // exp(-inf) = 0 for masked rows
-                        ssum = ssum * __expf(m - mn) + acc;
-                        m = mn;
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const float u = __uint_as_float(raw[j]);
+                    v[j] = KIND == CPC_SCORE_SOFTPLUS ? nu_softplus(u) : u;
                 }
+                if (n0 + 32 > n_valid) {                                     // ragged last batch: mask the rows outside
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (n0 + j >= n_valid) v[j] = -INFINITY;
+                }
+                if (rt == ct && n0 == (cl & 96)) {                           // the tile on the diagonal holds S[c, c]
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j == (cl & 31)) diag = v[j];
+                }
+                float bmax = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) bmax = fmaxf(bmax, v[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vsum += v[j] > -INFINITY ? v[j] : 0.f;
+                if (REG) {                                                   // groups of K consecutive rows = one item d
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < n_valid) {
+                            grp += v[j];
+                            if ((rt * 128 + n0 + j + 1) % g.K == 0) { const float a = grp * inv_k; reg += a * a; grp = 0.f; }
+                        }
+                }
+                vmax = fmaxf(vmax, bmax);
+                const float mn = fmaxf(m, bmax);
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc += __expf(v[j] - mn);              // exp(-inf) = 0 for masked rows
+                ssum = ssum * __expf(m - mn) + acc;
+                m = mn;
             }
             tc_fence_before();
             __syncwarp();
@@ -271,6 +278,7 @@ struct NuBwd {
     float* out;                   // d_targets (B,E,K) contiguous or d_pred (B,K,E) contiguous
 };
 
+template <int KIND>
 __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __grid_constant__ CUtensorMap tmap_owner,
                                                                     const __grid_constant__ CUtensorMap tmap_other,
                                                                     const NuBwd p) {
@@ -404,28 +412,40 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
             tc_fence_after();
             mbar_wait(&bars->g_empty, (st & 1) ^ 1);                         // previous G tile consumed by the MMAs
             asm volatile("bar.sync 1, 128;" ::: "memory");                  // lse_s visible to all epilogue threads
+            const int n_valid = min(128, g.Bp - st * 128);                   // rows of the other operand inside the problem
+            const float* lrow = bars->lse_s[st & 1];
             for (int n0 = 0; n0 < 128; n0 += 32) {
                 uint32_t raw[32];
                 tmem_ld32(lane_base + (uint32_t)((st & 1) * 128 + n0), raw);
                 tmem_ld_wait();
+                float gv[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float u = __uint_as_float(raw[j]);
+                    const float sc = KIND == CPC_SCORE_SOFTPLUS ? nu_softplus(u) : u;
+                    const float l = p.owner_is_target ? lse_own : lrow[n0 + j];
+                    gv[j] = w_ce * __expf(sc - l);
+                }
+                if (st == ot && n0 == (rl & 96)) {                           // - w on the diagonal element
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j == (rl & 31)) gv[j] -= w_ce;
+                }
+                if (KIND == CPC_SCORE_SOFTPLUS) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) gv[j] *= nu_sigmoid(__uint_as_float(raw[j]));
+                }
+                if (!own_ok || n0 + 32 > n_valid) {                          // rows outside the problem contribute nothing
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (!own_ok || n0 + j >= n_valid) gv[j] = 0.f;
+                }
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                     __align__(16) __nv_bfloat16 hi[8];
                     __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int nloc = n0 + j8 * 8 + j;
-                        const int xrow = st * 128 + nloc;                    // row of the other operand
-                        const float u = __uint_as_float(raw[j8 * 8 + j]);
-                        const float s = p.g.kind == CPC_SCORE_SOFTPLUS ? nu_softplus(u) : u;
-                        float gv = 0.f;
-                        if (own_ok && xrow < g.Bp) {
-                            const float l = p.owner_is_target ? lse_own : bars->lse_s[st & 1][nloc];
-                            gv = w_ce * (__expf(s - l) - (xrow == orow ? 1.f : 0.f));
-                            if (p.g.kind == CPC_SCORE_SOFTPLUS) gv *= nu_sigmoid(u);
-                        }
-                        hi[j] = __float2bfloat16_rn(gv);
-                        lo[j] = __float2bfloat16_rn(gv - __bfloat162float(hi[j]));
+                        hi[j] = __float2bfloat16_rn(gv[j8 * 8 + j]);
+                        lo[j] = __float2bfloat16_rn(gv[j8 * 8 + j] - __bfloat162float(hi[j]));
                     }
                     const int nchunk = n0 / 8 + j8;                          // 16-byte chunk index along K (0..15)
                     uint8_t* dst = grow + (nchunk >> 3) * (128 * 128) + (((nchunk & 7) ^ (rl & 7)) << 4);
@@ -476,9 +496,9 @@ bool nce_umma_eligible(const cpc_infonce_params* p, int which) {
     if (p->precision != 0 || p->enc % 64 != 0 || p->enc < 64 || p->enc > 4096) return false;
     const long bp = p->all_steps ? (long)p->batch * p->steps : p->batch;
     if (bp < 128 || bp > (1 << 24)) return false;                          // tiny problems are latency-bound either way
-    // one CTA per 128 owner rows: a single all-steps problem needs >= 20 row tiles to fill the machine better than
+    // one CTA per 128 owner rows: a single all-steps problem needs >= 8 row tiles to beat
     // the CUDA-core kernel does (measured cross-over, tools/infonce_sweep.py); per-step mode has K problems
-    if (p->all_steps && bp < 2560) return false;
+    if (p->all_steps && bp < 1024) return false;
     if (p->regularization != 0.f) {
         if (which == 1) return false;                                       // regulariser gradient: CUDA-core kernel
         if (!p->all_steps || 128 % p->steps != 0) return false;            // forward needs whole K-groups inside a tile
@@ -533,10 +553,16 @@ int nce_umma_fwd(const float* pred, const float* targets, float* out, float* lse
     CUtensorMap tz, tp;
     if (!nu_tmap(&tz, zp, g) || !nu_tmap(&tp, pp, g)) return CPC_ERR_CUDA;
     const int smem_bytes = NU_FSTAGES * 2 * NU_TILE + (int)sizeof(NuFwdBarriers) + 1024;
-    if (cudaFuncSetAttribute(nce_umma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
-        return CPC_ERR_CUDA;
     const int ncta = g.nprob * g.nT;
-    nce_umma_fwd_kernel<<<ncta, NU_THREADS, smem_bytes, s>>>(tz, tp, g, lse, partials);
+    auto launch = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return CPC_ERR_CUDA;
+        kern<<<ncta, NU_THREADS, smem_bytes, s>>>(tz, tp, g, lse, partials);
+        return CPC_OK;
+    };
+    const bool soft = g.kind == CPC_SCORE_SOFTPLUS, reg = g.lambda != 0.f;
+    st = soft ? (reg ? launch(nce_umma_fwd_kernel<CPC_SCORE_SOFTPLUS, true>) : launch(nce_umma_fwd_kernel<CPC_SCORE_SOFTPLUS, false>))
+              : (reg ? launch(nce_umma_fwd_kernel<CPC_SCORE_LINEAR, true>) : launch(nce_umma_fwd_kernel<CPC_SCORE_LINEAR, false>));
+    if (st != CPC_OK) return st;
     CPC_LAUNCH_CHECK();
     nce_umma_final_kernel<<<1, 256, 0, s>>>(partials, ncta, g, out);
     CPC_LAUNCH_CHECK();
@@ -557,17 +583,20 @@ int nce_umma_bwd(const float* pred, const float* targets, const float* lse, cons
     CUtensorMap tz, tp;
     if (!nu_tmap(&tz, zp, g) || !nu_tmap(&tp, pp, g)) return CPC_ERR_CUDA;
     const int smem_bytes = NU_BSTAGES * 2 * NU_TILE + 2 * NU_TILE + (int)sizeof(NuBwdBarriers) + 1024;
-    if (cudaFuncSetAttribute(nce_umma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
-        return CPC_ERR_CUDA;
     NuBwd k{};
     k.g = g; k.lse = lse; k.grad_loss = grad_loss;
     k.n_slices = ceil_div(g.EC, 4);
     const int grid = g.nprob * g.nT * k.n_slices;
-    k.owner_is_target = 1; k.out = d_targets;
-    nce_umma_bwd_kernel<<<grid, NU_THREADS, smem_bytes, s>>>(tz, tp, k);
-    CPC_LAUNCH_CHECK();
-    k.owner_is_target = 0; k.out = d_pred;
-    nce_umma_bwd_kernel<<<grid, NU_THREADS, smem_bytes, s>>>(tp, tz, k);
+    auto launch = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return CPC_ERR_CUDA;
+        k.owner_is_target = 1; k.out = d_targets;
+        kern<<<grid, NU_THREADS, smem_bytes, s>>>(tz, tp, k);
+        k.owner_is_target = 0; k.out = d_pred;
+        kern<<<grid, NU_THREADS, smem_bytes, s>>>(tp, tz, k);
+        return CPC_OK;
+    };
+    st = g.kind == CPC_SCORE_SOFTPLUS ? launch(nce_umma_bwd_kernel<CPC_SCORE_SOFTPLUS>) : launch(nce_umma_bwd_kernel<CPC_SCORE_LINEAR>);
+    if (st != CPC_OK) return st;
     CPC_LAUNCH_CHECK();
     count_launch(4);
     return CPC_OK;

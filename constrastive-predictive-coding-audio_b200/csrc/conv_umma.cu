@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+        {
             const uint32_t idesc = make_idesc_bf16(128, p.n_tile, /*A MN-major*/ 1, /*B K-major*/ 0);
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t acc_phase = 0;
@@ -266,20 +266,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                     const uint32_t st = smem_u32(stages_base + (size_t)stage * stage_bytes);
                     const uint32_t b0 = p.w_resident ? smem_u32(w_res + q * w_chunk_bytes) : st + p.planes * A_PLANE_BYTES;
                     const int ncombo = p.planes == 2 ? 3 : 1;
-                    for (int cb = 0; cb < ncombo; ++cb) {
-                        const uint32_t a_addr = st + (cb == 2 ? A_PLANE_BYTES : 0);          // (hi,hi) (hi,lo) (lo,hi)
-                        const uint32_t b_addr = b0 + (cb == 1 ? b_plane_bytes : 0);
+                    if (elect_one()) {
+                        for (int cb = 0; cb < ncombo; ++cb) {
+                            const uint32_t a_addr = st + (cb == 2 ? A_PLANE_BYTES : 0);      // (hi,hi) (hi,lo) (lo,hi)
+                            const uint32_t b_addr = b0 + (cb == 1 ? b_plane_bytes : 0);
+                            // descriptors advance by a constant per K step: +16 K-rows of 128 B (A, MN-major), +32 B (B)
+                            const uint64_t ad0 = make_smem_desc(a_addr, KCHUNK * 128, 1024);
+                            const uint64_t bd0 = make_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-                        for (int k = 0; k < KCHUNK / 16; ++k) {
-                            const uint64_t ad = make_smem_desc(a_addr + k * (16 * 128), KCHUNK * 128, 1024);
-                            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-                            mma_bf16(d_tmem, ad, bd, idesc, (q | cb | k) != 0);
+                            for (int k = 0; k < KCHUNK / 16; ++k)
+                                mma_bf16(d_tmem, ad0 + (uint64_t)(k * ((16 * 128) >> 4)), bd0 + (uint64_t)(k * (32 >> 4)), idesc,
+                                         (q | cb | k) != 0);
                         }
+                        tc_commit(&bars->empty[stage]);       // frees the smem stage once these MMAs retire
                     }
-                    tc_commit(&bars->empty[stage]);           // frees the smem stage once these MMAs retire
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&bars->acc_full[buf]);               // accumulator complete -> epilogue
+                if (elect_one()) tc_commit(&bars->acc_full[buf]);              // accumulator complete -> epilogue
+                __syncwarp();
                 if (++buf == 2) { buf = 0; acc_phase ^= 1; }
             }
         }

@@ -41,6 +41,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a fully converged warp.  Single-thread roles (MMA issue, TMA issue) run their loops with the WHOLE
+// warp and elect a lane only for the issuing instruction: the loop state then stays warp-uniform, so ptxas keeps
+// descriptors / addresses in uniform registers instead of converting per-thread values (R2UR + retry loops).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -193,16 +193,19 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues.  An N = 64 MMA occupies the tensor pipe for
+        // only 32 cycles, so the issue path is kept to one 64-bit add per descriptor =====
+        {
             const uint32_t idesc = make_idesc_bf16(128, p.NP, 0, 0);
             const uint32_t slab_addr = smem_u32(slab);
+            const uint32_t hop_shift = p.hop == 64 ? 6 : 7;                  // hop is 64 or 128
             uint32_t bn = 0, tn = 0;
             for (uint32_t i = 0;; ++i) {
                 const int slot = i & 1;
                 mbar_wait(&bars->sfull[slot], (i >> 1) & 1);
                 const int tile = *reinterpret_cast<volatile int*>(&bars->tile_id[slot]);
-                mbar_arrive(&bars->sempty[slot]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->sempty[slot]);
                 if (tile < 0) break;
                 int set, b, blk;
                 cq_tile(p, tile, set, b, blk);
@@ -217,24 +220,30 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                         const int stage = bn % CQ_BSTAGES;
                         mbar_wait(&bars->bfull[stage], (bn / CQ_BSTAGES) & 1);
                         tc_fence_after();
-                        const int so = g.off + c * 64;                         // sample offset of this tap chunk
-                        const int m = so / p.hop, half = (so - m * p.hop) >> 6;
+                        const uint32_t so = (uint32_t)(g.off + c * 64);        // sample offset of this tap chunk
+                        const uint32_t m = so >> hop_shift, half = (so & (p.hop - 1)) >> 6;
                         const uint32_t a_hi = slab_addr + half * 2 * CQ_SLAB_PLANE + m * 128;
                         const uint32_t b_hi = smem_u32(b_ring + stage * b_stage);
+                        if (elect_one()) {
+                            const uint64_t a_d_hi = cq_desc(a_hi, p.base_offset), a_d_lo = cq_desc(a_hi + CQ_SLAB_PLANE, p.base_offset);
+                            const uint64_t b_d_hi = make_smem_desc(b_hi, 16, 1024), b_d_lo = make_smem_desc(b_hi + p.NP * 128, 16, 1024);
 #pragma unroll
-                        for (int cb = 0; cb < 3; ++cb) {                       // (hi,hi) (hi,lo) (lo,hi)
-                            const uint32_t a_addr = a_hi + (cb == 2 ? CQ_SLAB_PLANE : 0);
-                            const uint32_t b_addr = b_hi + (cb == 1 ? p.NP * 128 : 0);
+                            for (int cb = 0; cb < 3; ++cb) {                   // (hi,hi) (hi,lo) (lo,hi)
+                                const uint64_t ad = cb == 2 ? a_d_lo : a_d_hi, bd = cb == 1 ? b_d_lo : b_d_hi;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                mma_bf16(d_tmem, cq_desc(a_addr + k * 32, p.base_offset), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
-                                         (uint32_t)(c | cb | k));
+                                for (int k = 0; k < 4; ++k)                    // +32 B per K step = +2 in the address field
+                                    mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)(c | cb | k));
+                            }
+                            tc_commit(&bars->bempty[stage]);
                         }
-                        tc_commit(&bars->bempty[stage]);
+                        __syncwarp();
                     }
                 }
-                tc_commit(&bars->slab_empty);
-                tc_commit(&bars->acc_full[buf]);
+                if (elect_one()) {
+                    tc_commit(&bars->slab_empty);
+                    tc_commit(&bars->acc_full[buf]);
+                }
+                __syncwarp();
                 ++tn;
             }
         }

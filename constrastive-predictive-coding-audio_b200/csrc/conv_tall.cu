@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues; descriptors advance by constant adds =====
+        {
             const uint32_t idesc = make_idesc_bf16(128, 128, /*A MN-major*/ 1, /*B K-major*/ 0);
             const uint32_t w_base = smem_u32(w_ring);
             uint32_t v = 0, acc_phase = 0;
@@ -158,31 +158,37 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
                     const uint32_t phase = (v / TL_S) & 1;
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
-                    if (j >= j_lo) {
-                        const uint32_t a_addr = smem_u32(a_ring + stage * TL_ASTAGE);
-                        for (int g = 0; g < TL_R / 4; ++g) {
-                            const int t_hi = j - 4 * g;                        // newest tap of the group (row 4g)
-                            const bool live = t_hi >= 0 && t_hi - 3 < p.kh;    // any tap inside [0, kh)
-                            if (j != j_lo && !live) continue;                  // first step initialises every group
-                            const int start = (4 * g + TL_T - (int)(v % TL_T)) % TL_T;     // slot of tap j - 4g
-                            const uint32_t b_addr = w_base + start * TL_SLOT;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)g * 128;
-#pragma unroll
-                            for (int cb = 0; cb < 3; ++cb) {                   // (hi,hi) (hi,lo) (lo,hi)
-                                const uint32_t a_off = cb == 2 ? 32 * 128 : 0;
-                                const uint32_t b_off = cb == 1 ? 64 : 0;
-#pragma unroll
-                                for (int k = 0; k < 2; ++k) {
-                                    const uint64_t ad = make_smem_desc(a_addr + a_off + k * (16 * 128), 64 * 128, 1024);
-                                    const uint64_t bd = make_smem_desc(b_addr + b_off + k * 32, 16, 1024);
-                                    mma_bf16(d_tmem, ad, bd, idesc, (j != j_lo || cb != 0 || k != 0) ? 1u : 0u);
-                                }
+                    if (elect_one()) {
+                        if (j >= j_lo) {
+                            // A (MN-major): hi plane rows 0..31, lo plane rows 32..63, 16 K-rows (2 KB) per K step
+                            const uint64_t a_hi = make_smem_desc(smem_u32(a_ring + stage * TL_ASTAGE), 64 * 128, 1024);
+                            const uint64_t a_lo = a_hi + (uint64_t)((32 * 128) >> 4);
+                            const uint32_t accum0 = j != j_lo ? 1u : 0u;
+                            const int vslot = (int)(v % TL_T);
+                            for (int g = 0; g < TL_R / 4; ++g) {
+                                const int t_hi = j - 4 * g;                    // newest tap of the group (row 4g)
+                                const bool live = t_hi >= 0 && t_hi - 3 < p.kh;    // any tap inside [0, kh)
+                                if (j != j_lo && !live) continue;              // first step initialises every group
+                                int start = 4 * g + TL_T - vslot;              // slot of tap j - 4g
+                                if (start >= TL_T) start -= TL_T;
+                                // B (K-major): [hi c0..31 | lo c0..31] per 128-byte row, 32 B per K step
+                                const uint64_t b_hi = make_smem_desc(w_base + start * TL_SLOT, 16, 1024);
+                                const uint64_t b_lo = b_hi + (uint64_t)(64 >> 4);
+                                const uint32_t d_tmem = tmem_base + (uint32_t)g * 128;
+                                mma_bf16(d_tmem, a_hi, b_hi, idesc, accum0);                                   // hi * hi
+                                mma_bf16(d_tmem, a_hi + (uint64_t)((16 * 128) >> 4), b_hi + 2, idesc, 1u);
+                                mma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);                                       // hi * lo
+                                mma_bf16(d_tmem, a_hi + (uint64_t)((16 * 128) >> 4), b_lo + 2, idesc, 1u);
+                                mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);                                       // lo * hi
+                                mma_bf16(d_tmem, a_lo + (uint64_t)((16 * 128) >> 4), b_hi + 2, idesc, 1u);
                             }
                         }
+                        tc_commit(&bars->empty[stage]);
                     }
-                    tc_commit(&bars->empty[stage]);
+                    __syncwarp();
                 }
-                tc_commit(&bars->acc_full);
+                if (elect_one()) tc_commit(&bars->acc_full);
+                __syncwarp();
                 acc_phase ^= 1;
             }
         }

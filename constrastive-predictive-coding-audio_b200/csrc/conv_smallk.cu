@@ -104,19 +104,20 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const float* __restrict_
         if (co0 + c < g.Cout) yo[(size_t)c * g.ohow] = relu ? fmaxf(acc[c], 0.f) : acc[c];
 }
 
-// grid (pixel chunks of SW_ITERS * 32 pixels, B, Cout / 32); block 256 = 8 warps, warp w owns channels 4w..4w+3
+// grid (pixel chunks of SW_ITERS * 32 pixels, B, Cout / 32); block = 32 / CPW warps, warp w owns channels CPW*w .. +CPW-1
+// (CPW = 8 while the CPW x KT accumulators fit in registers: every x tap loaded is then reused by 8 channels)
 constexpr int SW_ITERS = 32;
-template <int KT>
-__global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                         float* __restrict__ dw, SmallGeom g, int interior) {
+template <int KT, int CPW>
+__global__ void __launch_bounds__(32 * (32 / CPW)) small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                     float* __restrict__ dw, SmallGeom g, int interior) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int toff[KT];
     small_tap_offsets<KT>(g, toff);
     const int b = blockIdx.y;
-    const int co = blockIdx.z * 32 + warp * 4;
-    float acc[4][KT];
+    const int co = blockIdx.z * 32 + warp * CPW;
+    float acc[CPW][KT];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < CPW; ++c)
 #pragma unroll
         for (int k = 0; k < KT; ++k) acc[c][k] = 0.f;
     const int p_begin = blockIdx.x * (SW_ITERS * 32);
@@ -126,16 +127,16 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restric
         if (pix >= g.ohow) break;                                   // later iterations are out of range for every lane >= this one
         float v[KT];
         small_gather<KT>(x, g, toff, interior != 0, b, pix, v);
-        float d[4];
+        float d[CPW];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) d[c] = co + c < g.Cout ? __ldg(dyb + (size_t)c * g.ohow + pix) : 0.f;
+        for (int c = 0; c < CPW; ++c) d[c] = co + c < g.Cout ? __ldg(dyb + (size_t)c * g.ohow + pix) : 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < CPW; ++c)
 #pragma unroll
             for (int k = 0; k < KT; ++k) acc[c][k] = fmaf(d[c], v[k], acc[c][k]);
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < CPW; ++c)
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
             const float s = warp_sum(acc[c][k]);
@@ -160,7 +161,8 @@ static void small_launch(int which, const float* x, const float* w, const float*
         small_fwd_kernel<KT><<<grid, 256, 0, s>>>(x, w, bias, out, g, relu, interior);
     } else {
         dim3 grid(ceil_div(g.ohow, SW_ITERS * 32), g.B, ceil_div(g.Cout, 32));
-        small_wgrad_kernel<KT><<<grid, 256, 0, s>>>(x, dy, out, g, interior);
+        constexpr int CPW = KT <= 18 ? 8 : 4;
+        small_wgrad_kernel<KT, CPW><<<grid, 32 * (32 / CPW), 0, s>>>(x, dy, out, g, interior);
     }
 }
 

@@ -158,7 +158,8 @@ def run_ours(args):
         model=model, dataset=None, device=dev, regularization=tc["regularization"],
         score_over_all_timesteps=tc["score_over_all_timesteps"], score_function=tc["score_function"],
         preprocessing=pre, prediction_steps=tc["prediction_steps"], verbose=False)
-    optimizer = torch.optim.Adam(model.parameters(), lr=tc["learning_rate"], capturable=True)
+    trainer.optimizer = tc["optimizer"]                        # torch.optim.Adam in the reference's config
+    optimizer = trainer.make_optimizer(tc["learning_rate"])     # -> cpc_b200.optim.Adam (one kernel per step)
     use_graph = not args.no_graph
     reducer = ddp.GradientBucketReducer(model) if (world > 1 and not use_graph) else None
     model.train()

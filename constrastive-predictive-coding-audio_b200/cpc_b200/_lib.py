@@ -14,7 +14,7 @@ CQT_MAX_GROUPS = 16
 CQT_COMPLEX, CQT_LOGPOW, CQT_LOGPOW_PHASE = 0, 1, 2
 SCORE_LINEAR, SCORE_SOFTPLUS = 0, 1
 INFONCE_OUT_FLOATS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CqtParams(ctypes.Structure):
@@ -56,6 +56,11 @@ class InfoNceParams(ctypes.Structure):
                 ("precision", ctypes.c_int32)]
 
 
+class AdamParams(ctypes.Structure):
+    _fields_ = [("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
+                ("weight_decay", ctypes.c_float), ("grad_scale", ctypes.c_float), ("maximize", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); exactly the symbols include/cpc_b200.h declares
 _P = ctypes.c_void_p
 SIGNATURES = {
@@ -85,6 +90,7 @@ SIGNATURES = {
     "cpc_infonce_fwd": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(InfoNceParams), _P, ctypes.c_size_t, _P]),
     "cpc_infonce_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(InfoNceParams), _P, ctypes.c_size_t, _P]),
     "cpc_infonce_validate": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(InfoNceParams), _P, ctypes.c_size_t, _P]),
+    "cpc_adam_step": (ctypes.c_int, [ctypes.c_int32, _P, _P, _P, _P, _P, _P, ctypes.POINTER(AdamParams), _P]),
 }
 
 _lib = None

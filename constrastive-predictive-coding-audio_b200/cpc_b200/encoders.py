@@ -61,7 +61,7 @@ class MaxPool2d(nn.MaxPool2d):
         k = self.kernel_size if isinstance(self.kernel_size, int) else None
         stride = self.stride if isinstance(self.stride, int) else None
         if (k is not None and stride == k and self.padding == 0 and self.dilation == 1 and not self.return_indices
-                and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32):
+                and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and not ops.second_order_enabled()):
             return ops.max_pool2d(x, k, self.ceil_mode)
         return super().forward(x)
 
@@ -303,7 +303,7 @@ class ScalogramEncoderBlock(nn.Module):
 
     def forward(self, x, outer_relu=False):
         """``outer_relu``: also apply the ReLU the encoder puts between blocks (scalogram_model.py:523-527)."""
-        if not self._taps_attached():
+        if not self._taps_attached() and not ops.second_order_enabled():
             fused = self._forward_fused(x, outer_relu)
             if fused is not None:
                 return fused

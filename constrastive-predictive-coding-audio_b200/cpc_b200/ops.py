@@ -3,9 +3,11 @@
 PyTorch is plumbing here: it owns the device buffers and the stream; all arithmetic happens inside
 libcpc_b200.so.  Every op raises on non-CUDA tensors -- there is no CPU path.
 """
+import contextlib
 import ctypes
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -23,6 +25,27 @@ def set_default_precision(name):
 
 def get_default_precision():
     return _default_precision
+
+
+# Second-order mode (the Wasserstein gradient penalty, contrastive_estimation_training.py:144-155, differentiates
+# d(sum scores)/d(scalogram) once more): convolutions stay on the B200 kernels -- their backward is then recorded
+# as differentiable dgrad / wgrad Functions -- while the fused BN+ReLU and max-pool Functions, whose backward
+# kernels have no second derivative, step aside for the literal module sequence.
+_second_order = False
+
+
+@contextlib.contextmanager
+def second_order(enabled=True):
+    global _second_order
+    previous, _second_order = _second_order, bool(enabled)
+    try:
+        yield
+    finally:
+        _second_order = previous
+
+
+def second_order_enabled():
+    return _second_order
 
 
 def _require_cuda(*tensors):
@@ -174,6 +197,13 @@ class _ConvFunction(torch.autograd.Function):
         if ctx.relu:
             dy = dy * (y > 0).to(dy.dtype)
         dy = dy.contiguous()
+        if torch.is_grad_enabled():
+            # backward under create_graph=True: record dgrad / wgrad as differentiable nodes
+            geom = (x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision)
+            dx = _ConvDgradFunction.apply(dy, w, geom) if ctx.needs_input_grad[0] else None
+            dw = _ConvWgradFunction.apply(x, dy, geom) if ctx.needs_input_grad[1] else None
+            db = dy.sum(dim=(0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+            return dx, dw, db, None, None, None, None, None, None
         p = _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, False, precision)
         dx = dw = db = None
         need_dx = ctx.needs_input_grad[0]
@@ -193,6 +223,69 @@ class _ConvFunction(torch.autograd.Function):
                       _ptr(db), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws),
                       ws.numel() if ws is not None else 0, _stream())
         return dx, dw, db, None, None, None, None, None, None
+
+
+class _ConvDgradFunction(torch.autograd.Function):
+    """dx = conv_transpose(dy, w) as a differentiable node (bilinear in dy and w):
+    d/d(dy) = conv_fwd(g, w),  d/d(w) = wgrad(x := g, dy)."""
+
+    @staticmethod
+    def forward(ctx, dy, w, geom):
+        _require_cuda(dy, w)
+        lib = _lib.load()
+        x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = geom
+        dy, w = dy.contiguous(), w.contiguous()
+        p = _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, False, precision)
+        dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
+        ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
+        with torch.cuda.device(dy.device):
+            _call(_conv_key("cpc_conv_dgrad", p), _conv_flops(p), lib.cpc_conv_dgrad_ex, _ptr(dy), _ptr(w), _ptr(dx),
+                  ctypes.byref(p), _ptr(None), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+        ctx.geom = geom
+        ctx.save_for_backward(dy, w)
+        return dx
+
+    @staticmethod
+    def backward(ctx, g):
+        dy, w = ctx.saved_tensors
+        x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = ctx.geom
+        g = g.contiguous()
+        g_dy = (_ConvFunction.apply(g, w, None, stride, pad_top, pad_left, out_hw, False, precision)
+                if ctx.needs_input_grad[0] else None)
+        g_w = _ConvWgradFunction.apply(g, dy, ctx.geom) if ctx.needs_input_grad[1] else None
+        return g_dy, g_w, None
+
+
+class _ConvWgradFunction(torch.autograd.Function):
+    """dw = wgrad(x, dy) as a differentiable node (bilinear in x and dy):
+    d/d(x) = conv_transpose(dy, g),  d/d(dy) = conv_fwd(x, g)."""
+
+    @staticmethod
+    def forward(ctx, x, dy, geom):
+        _require_cuda(x, dy)
+        lib = _lib.load()
+        x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = geom
+        x, dy = x.contiguous(), dy.contiguous()
+        p = _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, False, precision)
+        dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
+        ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
+        with torch.cuda.device(dy.device):
+            _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad_ex, _ptr(x), _ptr(dy), _ptr(dw),
+                  _ptr(None), ctypes.byref(p), _ptr(None), _ptr(None), _ptr(ws), ws.numel() if ws is not None else 0,
+                  _stream())
+        ctx.geom = geom
+        ctx.save_for_backward(x, dy)
+        return dw
+
+    @staticmethod
+    def backward(ctx, g):
+        x, dy = ctx.saved_tensors
+        x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = ctx.geom
+        g = g.contiguous()
+        g_x = _ConvDgradFunction.apply(dy, g, ctx.geom) if ctx.needs_input_grad[0] else None
+        g_dy = (_ConvFunction.apply(x, g, None, stride, pad_top, pad_left, out_hw, False, precision)
+                if ctx.needs_input_grad[1] else None)
+        return g_x, g_dy, None
 
 
 def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), extra_top=0, relu=False, precision=None):
@@ -271,6 +364,7 @@ class _BnReluFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable                                         # second-order mode uses the literal modules instead
     def backward(ctx, dout):
         x, gamma, beta, save_mean, save_rstd, residual = ctx.saved_tensors
         lib = _lib.load()
@@ -342,6 +436,7 @@ class _MaxPoolFunction(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         lib = _lib.load()
@@ -410,6 +505,7 @@ class _InfoNceFunction(torch.autograd.Function):
         return loss, max_score, loss_noreg, mean_score
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_loss, _g1, _g2, _g3):
         pred, targets, lse = ctx.saved_tensors
         lib = _lib.load()

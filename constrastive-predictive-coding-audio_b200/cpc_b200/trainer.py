@@ -16,7 +16,7 @@ import torch.nn.functional as F
 import torch.optim
 import torch.utils.data
 
-from . import ddp, ops
+from . import ddp, ops, optim
 from .sampler import FileBatchSampler
 
 
@@ -96,11 +96,10 @@ class ContrastiveEstimationTrainer:
             # reads that gradient; without the penalty the first layer's data gradient is dead work, so it is
             # not requested here (identical losses and parameter gradients).
             batch.requires_grad = bool(self.wasserstein_gradient_penalty)
-        predicted_z, targets, _, _ = self.model(batch)
         kind = _FUSED_KINDS.get(self.score_function)
         if self.wasserstein_gradient_penalty:
-            raise NotImplementedError("wasserstein_gradient_penalty needs double backward through the encoder; "
-                                      "the B200 conv kernels do not provide it yet (DESIGN.md, 'next')")
+            return self._loss_with_gradient_penalty(batch, kind)
+        predicted_z, targets, _, _ = self.model(batch)
         if kind is not None:
             loss, max_score, _, _ = ops.infonce(predicted_z, targets, self.score_over_all_timesteps, kind,
                                                 self.regularization)
@@ -110,10 +109,40 @@ class ContrastiveEstimationTrainer:
                                                          self.score_over_all_timesteps, self.regularization)
         return loss, max_score
 
+    def _loss_with_gradient_penalty(self, batch, kind):
+        """:144-158: loss + factor * mean((||d sum(scores) / d scalogram||_2 over channels - 1)^2).  The penalty is
+        differentiated a second time by loss.backward(), so the encoder runs in second-order mode: convolutions on the
+        B200 kernels with differentiable dgrad / wgrad nodes, BN / ReLU / pooling as the literal modules.  The InfoNCE
+        term still goes through the fused kernels; only the penalty's sum(scores) uses the materialised scores."""
+        with ops.second_order():
+            predicted_z, targets, _, _ = self.model(batch)
+            scores = self.score_function(predicted_z, targets)
+            if not self.score_over_all_timesteps:
+                scores = torch.diagonal(scores, dim1=1, dim2=3).permute(0, 2, 1).contiguous()
+            if kind is not None:
+                loss, max_score, _, _ = ops.infonce(predicted_z, targets, self.score_over_all_timesteps, kind,
+                                                    self.regularization)
+            else:
+                loss, max_score = reference_loss_from_scores(self.score_function(predicted_z, targets),
+                                                             predicted_z.shape[0], self.prediction_steps,
+                                                             self.score_over_all_timesteps, self.regularization)
+            batch_grad = torch.autograd.grad(outputs=torch.sum(scores), inputs=batch, create_graph=True,
+                                             retain_graph=True, only_inputs=True)
+            penalty = ((batch_grad[0].norm(2, dim=1) - 1) ** 2).mean() * self.gradient_penalty_factor
+        return loss + penalty, max_score
+
+    def make_optimizer(self, lr, **kwargs):
+        """``self.optimizer(self.model.parameters(), lr=lr)`` (:84); the stock ``torch.optim.Adam`` class is replaced
+        by the single-kernel ``cpc_b200.optim.Adam`` (same arithmetic and state_dict) when the model is on a GPU."""
+        cls = self.optimizer
+        if cls is torch.optim.Adam and all(p.is_cuda for p in self.model.parameters()):
+            cls = optim.Adam
+        return cls(self.model.parameters(), lr=lr, **kwargs)
+
     def train(self, batch_size=32, epochs=10, lr=0.0001, continue_training_at_step=0, num_workers=1, max_steps=None,
               profile=False):
         self.model.train()
-        optimizer = self.optimizer(self.model.parameters(), lr=lr)
+        optimizer = self.make_optimizer(lr)
         sampler = FileBatchSampler(index_count_per_file=self.dataset.get_example_count_per_file(),
                                    batch_size=batch_size, file_batch_size=self.file_batch_size, drop_last=True)
         dataloader = torch.utils.data.DataLoader(self.dataset, batch_sampler=sampler, num_workers=num_workers,
@@ -262,20 +291,32 @@ class GraphedTrainStep:
             if self.world == 1:
                 optimizer.step()
             else:                                                # all gradients in one flat buffer for ONE all-reduce
-                grads = [p.grad for p in self.params if p.grad is not None]
-                self.flat = torch.cat([g.reshape(-1) for g in grads])
+                with_grad = [p for p in self.params if p.grad is not None]
+                grads = [p.grad for p in with_grad]
+                # every segment starts on a 16-byte boundary (vector loads in the optimizer kernel)
+                pieces, offsets, offset = [], [], 0
+                for g in grads:
+                    offsets.append(offset)
+                    pieces.append(g.reshape(-1))
+                    offset += g.numel()
+                    if offset % 4:
+                        pieces.append(torch.zeros(4 - offset % 4, dtype=g.dtype, device=g.device))
+                        offset += 4 - offset % 4
+                self.flat = torch.cat(pieces)
             self.loss, self.max_score = loss.detach(), max_score.detach()
         if self.world > 1:
             # second graph (same memory pool): averaged gradients back into .grad, then the optimizer step.
             # The NCCL all-reduce between the two replays is the only eagerly submitted operation of a step.
             self.update_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.update_graph, pool=self.graph.pool()):
-                self.flat.div_(self.world)
-                offset = 0
-                for g in grads:
-                    g.copy_(self.flat[offset:offset + g.numel()].view_as(g))
-                    offset += g.numel()
-                optimizer.step()
+                views = {p: self.flat[o:o + g.numel()].view_as(g) for p, g, o in zip(with_grad, grads, offsets)}
+                if isinstance(optimizer, optim.Adam):            # reads the summed gradients in place, scaled by 1/W
+                    optimizer.step(flat_grads=views, grad_scale=1.0 / self.world)
+                else:
+                    self.flat.div_(self.world)
+                    for p, g in zip(with_grad, grads):
+                        g.copy_(views[p])
+                    optimizer.step()
 
     def _eager_step(self):
         self.optimizer.zero_grad(set_to_none=True)

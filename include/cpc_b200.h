@@ -232,6 +232,27 @@ int cpc_infonce_bwd(const float* pred, const float* targets, const float* lse, c
 int cpc_infonce_validate(const float* pred, const float* targets, float* metrics,
                          const cpc_infonce_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 5. Adam update of all parameter tensors (torch.optim.Adam semantics, amsgrad off) in one pass.
+ *    Replaces optimizer.step() of ContrastiveEstimationTrainer.train
+ *    (contrastive_estimation_training.py:162; optimizer class from the ctor, :41,59).
+ *    params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors device pointers (fp32, contiguous,
+ *    numel[i] elements each).  step_state: 4 device floats owned by the caller; [0] is the step count t
+ *    (0 before the first update; advanced by every call, so CUDA-graph replays keep counting), [1..2]
+ *    are scratch (bias corrections of the current step).
+ *      g = grad_scale * grad (+ weight_decay * p);  m += (1-beta1)(g-m);  v = beta2 v + (1-beta2) g^2
+ *      p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cpc_adam_params {
+    float lr, beta1, beta2, eps, weight_decay;
+    float grad_scale;       /* 1/world_size when grads hold the all-reduced SUM, else 1 */
+    int32_t maximize;
+} cpc_adam_params;
+
+int cpc_adam_step(int32_t n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                  void* const* exp_avg_sq, const int64_t* numel, float* step_state,
+                  const cpc_adam_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -208,6 +208,38 @@ def golden_trainer_cqt(ref):
     np.savez_compressed(os.path.join(OUT, "trainer_cqt.npz"), **out)
 
 
+def golden_trainer_gp(ref):
+    """Reference training steps with wasserstein_gradient_penalty=True (contrastive_estimation_training.py:144-155):
+    the penalty differentiates d(sum scores)/d(scalogram) a second time through encoder and AR model."""
+    sm, am = ref["scalogram_model"], ref["audio_model"]
+    cet = ref["contrastive_estimation_training"]
+    out = {}
+    for tag, all_steps, fn in (("a", True, cet.linear_score_function), ("p", False, cet.softplus_score_function)):
+        torch.manual_seed(4)
+        cfg = small_resnet_cfg(ref)
+        cfg['blocks'][2] = dict(cfg['blocks'][2], kernel_size_1=(30, 2), pooling_1=1, ceil_pooling=False)
+        cfg['blocks'][1] = dict(cfg['blocks'][1], kernel_size_2=(35, 1))
+        pre = sm.PreprocessingModule(dict(sm.cqt_default_dict), phase=True)
+        enc = sm.ScalogramResidualEncoder(cfg, preprocessing_module=pre)
+        ar = am.ConvolutionalArModel({'kernel_sizes': [3, 3], 'channel_count': [24, 16, 16], 'stride': [1, 1],
+                                      'pooling': [1, 2], 'bias': True, 'batch_norm': True, 'residual': False,
+                                      'activation_register': None})
+        model = am.AudioPredictiveCodingModel(enc, ar, enc_size=24, ar_size=16, visible_steps=10, prediction_steps=3)
+        g = torch.Generator().manual_seed(77)
+        items = 0.1 * torch.randn(8, model.item_length, generator=g)
+        lr = 1e-4
+        logger, snaps = run_reference_trainer(ref, model, ListDataset(items), pre, steps=2, batch_size=4, lr=lr, seed=5,
+                                              regularization=0.25, score_over_all_timesteps=all_steps,
+                                              score_function=fn, prediction_steps=3,
+                                              wasserstein_gradient_penalty=True, gradient_penalty_factor=10.)
+        out.update({tag + ".items": items.numpy(), tag + ".losses": np.array(logger.losses),
+                    tag + ".max_scores": np.array(logger.scores), tag + ".lr": np.array(lr),
+                    tag + ".batch_size": np.array(4), tag + ".item_length": np.array(model.item_length)})
+        for i, s in enumerate(snaps):
+            out.update({"%s.s%d.%s" % (tag, i, k): v for k, v in s.items()})
+    np.savez_compressed(os.path.join(OUT, "trainer_gp.npz"), **out)
+
+
 class StoredPairModel(torch.nn.Module):
     """A 'model' whose parameters ARE (pred, targets): lets the reference trainer's own loss code and
     autograd produce loss / gradients for arbitrary (pred, targets)."""
@@ -336,6 +368,7 @@ def main():
     golden_trainer_raw(ref)
     golden_trainer_cqt(ref)
     golden_validate(ref)
+    golden_trainer_gp(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -29,7 +29,7 @@ def main():
         model=model, dataset=None, device=dev, regularization=tc["regularization"],
         score_over_all_timesteps=tc["score_over_all_timesteps"], score_function=tc["score_function"],
         preprocessing=pre, prediction_steps=tc["prediction_steps"], verbose=False)
-    opt = torch.optim.Adam(model.parameters(), lr=tc["learning_rate"])
+    opt = cpc_b200.optim.Adam(model.parameters(), lr=tc["learning_rate"])
     model.train()
     g = torch.Generator().manual_seed(1234)
     x = (0.1 * torch.randn(args.batch, model.item_length, generator=g)).to(dev)

@@ -1,7 +1,7 @@
 """cpc_b200 -- B200-native (sm_100a) implementation of the CPC-audio training hot path.
 
 Public surface mirrors the reference's modules:
-    frontend : CQT, PhaseDifference, PreprocessingModule
+    frontend : CQT, InverseCQT, PhaseDifference, PhaseAccumulation, PreprocessingModule
     encoders : AudioEncoder, ScalogramEncoder, ScalogramEncoderBlock, ScalogramResidualEncoder
     model    : AudioPredictiveCodingModel, ActivationRegister, ActivationWriter
     ar_models: AudioGRUModel, ConvolutionalArModel, AttentionModel        (stock PyTorch, caller-side)
@@ -12,7 +12,7 @@ Public surface mirrors the reference's modules:
     ops      : conv1d / conv2d / infonce / cqt_frontend autograd functions over the C-ABI
 """
 from . import _lib, ops                                                        # noqa: F401
-from .frontend import CQT, PhaseDifference, PreprocessingModule               # noqa: F401
+from .frontend import CQT, InverseCQT, PhaseAccumulation, PhaseDifference, PreprocessingModule  # noqa: F401
 from .model import (ActivationRegister, ActivationWriter, AudioPredictiveCodingModel,  # noqa: F401
                     cuda0_writing_condition, load_to_cpu, num_parameters)
 from .encoders import (AudioEncoder, Conv1d, Conv2d, Conv2dSeparable, ScalogramEncoder,  # noqa: F401

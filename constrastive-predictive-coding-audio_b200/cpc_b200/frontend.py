@@ -12,6 +12,7 @@ import math
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib, ops
 
@@ -138,14 +139,97 @@ class CQT(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def _check_frozen(self):
-        if self._trainable and torch.is_grad_enabled():
-            raise NotImplementedError("trainable CQT (gradient w.r.t. the filterbank) is not implemented in the "
-                                      "B200 kernels yet; see DESIGN.md 'next'")
+    def needs_autograd(self, x):
+        """True when a gradient must flow through the transform: a trainable filterbank (``trainable_cqt``) or an
+        input that requires grad (dreaming: audio-input optimisation, dreaming/dreaming_calculation.py:169,265)."""
+        return torch.is_grad_enabled() and (self._trainable or x.requires_grad)
+
+    def forward_differentiable(self, x):
+        """constant_q_transform.py:161-172 literally, every group through the conv kernels (forward, dgrad towards
+        the audio, wgrad towards the filters; second derivatives by composition).  The fused single-launch kernel is
+        forward-only and serves the frozen transform."""
+        real, imag = [], []
+        for size, conv in zip(self.conv_kernel_sizes, self.conv_modules):
+            offset = (self.conv_kernel_sizes[0] - size) // 2
+            y = ops.conv1d(x[:, :, offset:x.shape[2] - (offset + 1)], conv.weight, None, stride=self.hop_length)
+            r, i = torch.chunk(y, 2, dim=1)
+            real.append(r)
+            imag.append(i)
+        return torch.stack([torch.cat(real, dim=1), torch.cat(imag, dim=1)], dim=3)
 
     def forward(self, x):
-        self._check_frozen()
+        if self.needs_autograd(x):
+            return self.forward_differentiable(x)
         return ops.cqt_frontend(x, self.packed_weights(), self.kernel_plan(), _lib.CQT_COMPLEX)
+
+
+class InverseCQT(nn.Module):
+    """constant_q_transform.py:180-260: complex CQT coefficients (N, n_bins, T, 2) -> complex signal (N, L, 2), one
+    ConvTranspose1d per octave group on the conv data-gradient kernels.  Same attributes and state_dict keys
+    (``conv_modules.{i}.weight`` of shape (n_g, 2, K_g)).  (The reference's forward applies ``.view`` to a permuted
+    tensor at :253, which raises in current PyTorch; the intended reshape is what runs here.)"""
+
+    def __init__(self, sr=16000, fmin=30, n_bins=256, bins_per_octave=32, filter_scale=1., hop_length=128,
+                 trainable=False):
+        super().__init__()
+        self.sr, self.fmin, self.n_bins = sr, fmin, n_bins
+        self.bins_per_octave, self.filter_scale, self.hop_length = bins_per_octave, filter_scale, hop_length
+        bank, lengths = constant_q_filterbank(sr, fmin, n_bins, bins_per_octave, filter_scale)
+        self.cqt_filter_lengths = lengths
+        self.conv_kernel_sizes, self.conv_index_ranges = octave_groups(lengths)
+        width = bank.shape[-1]
+        self.conv_modules = nn.ModuleList()
+        for size, rng in zip(self.conv_kernel_sizes, self.conv_index_ranges):
+            crop = (width - size) // 2
+            part = bank[rng.start:rng.stop, crop:width - crop]
+            weight = torch.stack([torch.from_numpy(part.real.copy()), torch.from_numpy(part.imag.copy())], dim=1).float()
+            conv = nn.ConvTranspose1d(weight.shape[0], 2, size, bias=False, stride=hop_length, padding=size // 2)
+            conv.weight = nn.Parameter(weight, requires_grad=False)
+            self.conv_modules.append(conv)
+        self._trainable = False
+        self.trainable = trainable
+
+    @property
+    def trainable(self):
+        return self._trainable
+
+    @trainable.setter
+    def trainable(self, value):
+        for p in self.parameters():
+            p.requires_grad = value
+        self._trainable = value
+
+    def forward(self, x):
+        result = 0
+        n = x.shape[0]
+        for size, rng, conv in zip(self.conv_kernel_sizes, self.conv_index_ranges, self.conv_modules):
+            band = x[:, rng.start:rng.stop]                                      # (N, n_g, T, 2)
+            p, t = band.shape[1], band.shape[2]
+            band = band.permute(3, 0, 1, 2).reshape(2 * n, p, t)                 # real parts first, then imaginary
+            result = result + ops.conv_transpose1d(band, conv.weight, stride=self.hop_length, padding=size // 2)
+        result = result.view(2, n, 2, -1)
+        return torch.stack([result[0, :, 0] - result[1, :, 0], result[0, :, 1] + result[1, :, 1]], dim=2)
+
+
+class PhaseAccumulation(nn.Module):
+    """constant_q_transform.py:294-313: inverse of PhaseDifference (cumulative phase from scaled differences).
+    ``start_phase`` is (1, n_bins, 1) as in the reference, so it concatenates with batch-1 inputs only (:311)."""
+
+    def __init__(self, sr=16000, fmin=30, n_bins=256, bins_per_octave=32, hop_length=128):
+        super().__init__()
+        freqs = cqt_frequencies(n_bins, fmin, bins_per_octave)
+        fixed = (((1.0 * freqs * hop_length / sr) + 0.5) % 1 - 0.5) * 2 * np.pi
+        # a plain attribute in the reference (not in its state_dict): non-persistent buffer here so .to() moves it
+        self.register_buffer("fixed_phase_diff", torch.from_numpy(fixed).float().view(1, -1, 1), persistent=False)
+        scaling = torch.from_numpy(1 / np.log(freqs)).float().view(1, -1, 1)
+        self.scaling = nn.Parameter(scaling, requires_grad=False)
+        self.start_phase = nn.Parameter(torch.zeros_like(scaling), requires_grad=False)
+
+    def forward(self, x):
+        x = (x / self.scaling) - self.fixed_phase_diff
+        x = torch.cat([self.start_phase, x], dim=2)
+        x = torch.cumsum(x, dim=2)
+        return x % (2 * np.pi) - np.pi
 
 
 class PhaseDifference(nn.Module):
@@ -203,7 +287,8 @@ class PreprocessingModule(nn.Module):
     def forward(self, x):
         if self.cqt is None:
             return x
-        self.cqt._check_frozen()
+        if self.cqt.needs_autograd(x):
+            return self._forward_differentiable(x)
         pool_t = 1 if self.pooling is None else int(self.pooling[1])
         if self.phase_diff is not None:
             y = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW_PHASE,
@@ -214,5 +299,20 @@ class PreprocessingModule(nn.Module):
             y = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW, pool_t=pool_t,
                                  eps=self.offset, log_offset=self.log_offset, norm=self.normalization_factor,
                                  power=self.output_power)
+        self.output = y
+        return y
+
+    def _forward_differentiable(self, x):
+        """scalogram_model.py:75-102 term by term on top of the differentiable CQT (autograd needs the complex
+        coefficients); same values as the fused kernel."""
+        z = self.cqt.forward_differentiable(x)
+        if self.phase_diff is not None:
+            amp = torch.log(torch.pow(abs(z[:, :, 1:]), 2) + self.offset) + self.log_offset
+            y = torch.stack([amp, self.phase_diff(angle(z))], dim=1)
+        else:
+            y = torch.log(torch.pow(abs(z), 2) + self.offset).unsqueeze(1) + self.log_offset
+        if self.pooling is not None:
+            y = F.max_pool2d(y, self.pooling)
+        y = (y * self.normalization_factor) ** self.output_power
         self.output = y
         return y

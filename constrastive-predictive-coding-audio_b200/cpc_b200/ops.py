@@ -313,6 +313,21 @@ def conv1d(x, weight, bias=None, stride=1, padding=0, relu=False, precision=None
     return y.squeeze(2)
 
 
+def conv_transpose1d(x, weight, stride=1, padding=0, precision=None):
+    """F.conv_transpose1d(x, weight, stride=stride, padding=padding) (no bias, no output padding): x (N, C_in, T),
+    weight (C_in, C_out, K) -> (N, C_out, (T-1)*stride - 2*padding + K).  It IS the data gradient of the conv1d
+    with that weight, so it runs on the dgrad kernels (InverseCQT, constant_q_transform.py:233-236)."""
+    n, c_in, t = x.shape
+    if weight.shape[0] != c_in:
+        raise ValueError("channel mismatch: input has %d channels, weight expects %d" % (c_in, weight.shape[0]))
+    c_out, k = weight.shape[1], weight.shape[2]
+    length = (t - 1) * stride - 2 * padding + k
+    if length <= 0:
+        raise ValueError("conv_transpose1d output would be empty")
+    geom = ((n, c_out, 1, length), (c_in, c_out, 1, k), (1, stride), 0, padding, (1, t), precision or _default_precision)
+    return _ConvDgradFunction.apply(x.unsqueeze(2), weight.unsqueeze(2), geom).squeeze(2)
+
+
 # --------------------------------------------------------------------------------------------------
 # fused BatchNorm2d + ReLU (+ cropped residual add + ReLU)
 # --------------------------------------------------------------------------------------------------

@@ -93,6 +93,54 @@ def golden_cqt(ref):
     np.savez_compressed(os.path.join(OUT, "cqt.npz"), **out)
 
 
+def golden_cqt_grad(ref):
+    """Gradients THROUGH the front end: d/d(audio) and d/d(filterbank) of the trainable CQT and
+    of the phase scalogram, plus InverseCQT and PhaseAccumulation outputs (constant_q_transform.py:155-260, 294-313).
+    A small filterbank (8 kHz, 96 bins, hop 64) keeps the fixture small."""
+    sm = ref["scalogram_model"]
+    cq = ref["constant_q_transform"]
+    g = torch.Generator().manual_seed(4321)
+    kw = dict(sr=8000, fmin=55, n_bins=96, bins_per_octave=24, filter_scale=0.5, hop_length=64)
+    cqt = cq.CQT(trainable=True, **kw)
+    x = (0.1 * torch.randn(2, 1, cqt.conv_kernel_sizes[0] + 1 + 64 * 6 + 11, generator=g)).requires_grad_(True)
+    z = cqt(x)
+    gz = torch.randn(z.shape, generator=g)
+    (z * gz).sum().backward()
+    out = {"x": x.detach().numpy(), "z": z.detach().numpy(), "gz": gz.numpy(), "gx": x.grad.numpy(),
+           "kernel_sizes": np.array(cqt.conv_kernel_sizes)}
+    for i, conv in enumerate(cqt.conv_modules):
+        out["gw%d" % i] = conv.weight.grad.numpy()
+    # phase scalogram of a trainable front end: loss = <y, gy>, gradient w.r.t. the audio and the filters
+    d = {'sample_rate': 8000, 'fmin': 55, 'n_bins': 96, 'bins_per_octave': 24, 'filter_scale': 0.5, 'hop_length': 64,
+         'trainable_cqt': True}
+    pre = sm.PreprocessingModule(d, phase=True, offset_zero=True, output_power=1., pooling=[1, 2], scaling=3.)
+    x2 = (0.1 * torch.randn(2, 1, x.shape[2], generator=g)).requires_grad_(True)
+    y = pre(x2)
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    out.update({"x2": x2.detach().numpy(), "y2": y.detach().numpy(), "gy2": gy.numpy(), "gx2": x2.grad.numpy()})
+    for i, conv in enumerate(pre.cqt.conv_modules):
+        out["g2w%d" % i] = conv.weight.grad.numpy()
+    # InverseCQT.forward itself raises on this torch (view of a permuted tensor, constant_q_transform.py:253), so the
+    # fixture applies the reference module's OWN ConvTranspose1d layers with that line's view replaced by reshape
+    icqt = cq.InverseCQT(**kw)
+    zi = torch.randn(2, 96, 5, 2, generator=g)
+    result = 0
+    for i, conv in enumerate(icqt.conv_modules):
+        band = zi[:, icqt.conv_index_ranges[i]]
+        n, p_, t, c = band.shape
+        result = result + conv(band.permute(3, 0, 1, 2).reshape(c * n, p_, t))
+    result = result.view(2, n, 2, -1)
+    out["icqt_in"] = zi.numpy()
+    out["icqt_out"] = torch.stack([result[0, :, 0] - result[1, :, 0], result[0, :, 1] + result[1, :, 1]],
+                                  dim=2).detach().numpy()
+    acc = cq.PhaseAccumulation(sr=8000, fmin=55, n_bins=96, bins_per_octave=24, hop_length=64)
+    ph = torch.randn(1, 96, 7, generator=g)                     # start_phase is (1, F, 1): batch 1 only (:311)
+    out["acc_in"] = ph.numpy()
+    out["acc_out"] = acc(ph).detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "cqt_grad.npz"), **out)
+
+
 def golden_audio_encoder(ref):
     am = ref["audio_model"]
     torch.manual_seed(0)
@@ -369,6 +417,7 @@ def main():
     golden_trainer_cqt(ref)
     golden_validate(ref)
     golden_trainer_gp(ref)
+    golden_cqt_grad(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -46,6 +46,23 @@ def test_abi_rejects_bad_arguments_before_touching_the_device(built_lib):
     c.kernel_size[0], c.bin_lo[0], c.bin_hi[0] = 128, 0, 4
     assert lib.cpc_cqt_fwd(None, None, None, None, None, ctypes.byref(c), None, 0, None) == -1  # frames overrun input
     assert lib.cpc_conv_fwd(None, None, None, None, None, None, 0, None) == -7
+    a = _lib.AdamParams(1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, 0)
+    assert lib.cpc_adam_step(0, None, None, None, None, None, None, ctypes.byref(a), None) == -7  # no step counter
+    a.beta2 = 1.5
+    state = (ctypes.c_float * 4)()
+    assert lib.cpc_adam_step(0, None, None, None, None, None, state, ctypes.byref(a), None) == -1  # beta out of range
+
+
+def test_phase_accumulation_matches_reference_golden():
+    """constant_q_transform.py:294-313 (plain tensor arithmetic, no kernel): values and state_dict keys."""
+    import cpc_b200
+    g = load_golden("cqt_grad.npz")
+    acc = cpc_b200.PhaseAccumulation(sr=8000, fmin=55, n_bins=96, bins_per_octave=24, hop_length=64)
+    assert set(acc.state_dict()) == {"scaling", "start_phase"}
+    out = acc(torch.from_numpy(g["acc_in"]))
+    want = torch.from_numpy(g["acc_out"])
+    d = torch.remainder(out - want + np.pi, 2 * np.pi) - np.pi            # compare on the circle (mod 2 pi wrap)
+    assert float(d.abs().max()) < 1e-4
 
 
 def test_no_cpu_fallback(built_lib):
@@ -57,6 +74,12 @@ def test_no_cpu_fallback(built_lib):
         cpc_b200.ops.infonce(torch.zeros(2, 2, 4), torch.zeros(2, 4, 2), True)
     with pytest.raises(cpc_b200._lib.CpcError):
         cpc_b200.CQT(filter_scale=0.5)(torch.zeros(1, 1, 20000))
+    with pytest.raises(cpc_b200._lib.CpcError):                           # differentiable path: same rule
+        cpc_b200.CQT(filter_scale=0.5, trainable=True)(torch.zeros(1, 1, 20000))
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.zeros(8)
+    with pytest.raises(cpc_b200._lib.CpcError):
+        cpc_b200.optim.Adam([p]).step()
 
 
 def test_audio_encoder_known_answers():

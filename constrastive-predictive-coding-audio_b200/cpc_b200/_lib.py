@@ -57,8 +57,8 @@ class InfoNceParams(ctypes.Structure):
 
 
 class AdamParams(ctypes.Structure):
-    _fields_ = [("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
-                ("weight_decay", ctypes.c_float), ("grad_scale", ctypes.c_float), ("maximize", ctypes.c_int32)]
+    _fields_ = [("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double),
+                ("weight_decay", ctypes.c_double), ("grad_scale", ctypes.c_float), ("maximize", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); exactly the symbols include/cpc_b200.h declares

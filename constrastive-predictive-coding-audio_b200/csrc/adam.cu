@@ -25,26 +25,29 @@ struct AdamTable {
 };
 
 // state[0] = t (advanced here), state[1] = lr / (1 - beta1^t), state[2] = 1 / sqrt(1 - beta2^t)
-__global__ void adam_tick_kernel(float* state, float lr, float beta1, float beta2) {
+__global__ void adam_tick_kernel(float* state, double lr, double beta1, double beta2) {
     const double t = (double)state[0] + 1.0;
     state[0] = (float)t;
-    state[1] = (float)((double)lr / (1.0 - pow((double)beta1, t)));
-    state[2] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, t)));
+    state[1] = (float)(lr / (1.0 - pow(beta1, t)));
+    state[2] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
 }
 
+// hyper-parameters rounded to fp32 once, on the host
+struct AdamScalars { float beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay, grad_scale; int maximize; };
+
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float step_size, float inv_bc2_sqrt,
-                                         const cpc_adam_params& a) {
+                                         const AdamScalars& a) {
     g *= a.grad_scale;
     if (a.maximize) g = -g;
     if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
-    m = fmaf(1.f - a.beta1, g - m, m);
-    v = fmaf(1.f - a.beta2, g * g, a.beta2 * v);
+    m = fmaf(a.one_minus_beta1, g - m, m);
+    v = fmaf(a.one_minus_beta2, g * g, a.beta2 * v);
     const float denom = fmaf(sqrtf(v), inv_bc2_sqrt, a.eps);
     p -= step_size * (m / denom);
 }
 
 __global__ void __launch_bounds__(256) adam_update_kernel(const __grid_constant__ AdamTable tab,
-                                                         const float* __restrict__ state, const cpc_adam_params a) {
+                                                         const float* __restrict__ state, const AdamScalars a) {
     // which tensor does this block work on? (block_start is ascending; <= 48 entries in the constant bank)
     int lo = 0, hi = tab.count - 1;
     while (lo < hi) {
@@ -100,7 +103,7 @@ extern "C" int cpc_adam_step(int32_t n_tensors, void* const* params, const void*
                              void* const* exp_avg_sq, const int64_t* numel, float* step_state,
                              const cpc_adam_params* a, void* stream) {
     if (!a || !step_state || (n_tensors > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !numel))) return CPC_ERR_NULL;
-    if (n_tensors < 0 || !(a->beta1 >= 0.f && a->beta1 < 1.f) || !(a->beta2 >= 0.f && a->beta2 < 1.f) || !(a->eps >= 0.f))
+    if (n_tensors < 0 || !(a->beta1 >= 0. && a->beta1 < 1.) || !(a->beta2 >= 0. && a->beta2 < 1.) || !(a->eps >= 0.))
         return CPC_ERR_BAD_SHAPE;
     for (int i = 0; i < n_tensors; ++i) {
         if (numel[i] < 0 || numel[i] > (int64_t)1 << 30) return CPC_ERR_BAD_SHAPE;
@@ -112,6 +115,8 @@ extern "C" int cpc_adam_step(int32_t n_tensors, void* const* params, const void*
     const int st = check_device();
     if (st != CPC_OK) return st;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const AdamScalars sc{(float)a->beta2, (float)(1.0 - a->beta1), (float)(1.0 - a->beta2), (float)a->eps,
+                         (float)a->weight_decay, a->grad_scale, a->maximize};
     adam_tick_kernel<<<1, 1, 0, s>>>(step_state, a->lr, a->beta1, a->beta2);
     CPC_LAUNCH_CHECK();
     count_launch();
@@ -134,7 +139,7 @@ extern "C" int cpc_adam_step(int32_t n_tensors, void* const* params, const void*
         }
         if (tab.count == 0) break;
         tab.block_start[tab.count] = blocks;
-        adam_update_kernel<<<blocks, 256, 0, s>>>(tab, step_state, *a);
+        adam_update_kernel<<<blocks, 256, 0, s>>>(tab, step_state, sc);
         CPC_LAUNCH_CHECK();
         count_launch();
     }

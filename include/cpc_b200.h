@@ -244,7 +244,8 @@ int cpc_infonce_validate(const float* pred, const float* targets, float* metrics
  *      p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct cpc_adam_params {
-    float lr, beta1, beta2, eps, weight_decay;
+    double lr, beta1, beta2, eps, weight_decay;   /* doubles, as the Python optimizer holds them: 1 - beta is
+                                                     formed in double and rounded once, like torch does */
     float grad_scale;       /* 1/world_size when grads hold the all-reduced SUM, else 1 */
     int32_t maximize;
 } cpc_adam_params;

@@ -247,36 +247,26 @@ def test_tall_conv_full_size_agrees_with_generic_kernel(cpc, geom):
     (128, 34, 156, 256, 3, 3, 2),      # block 2 conv_a: output rows of 77 pixels
     (256, 16, 77, 256, 15, 1, 1),      # block 2 conv_b: output rows of 77 pixels, 2 rows
 ])
-def test_narrow_atoms_agree_with_64_pixel_atoms(cpc, geom):
-    """The generic tcgen05 conv tiles every image row with MN-major atoms of 64, 32 or 16 pixels (SWIZZLE_128B / 64B /
-    32B operand layouts), whichever pads the row least.  BASELINE-size geometry, B = 4: forward, dgrad and wgrad with
-    each atom width (CPC_ATOM_W) and the automatic choice -- same arithmetic, different tiling -- and the forward
-    against torch in float64."""
-    import os
+def test_generic_conv_full_size_matches_torch(cpc, geom):
+    """BASELINE-size geometry (B = 2) of the three arch-7 layers on the generic tcgen05 kernels -- rows of 156 / 77
+    pixels, i.e. ragged 64-pixel atoms, stride-2 replicas, four dgrad parity classes: forward, data gradient and
+    weight gradient against torch's conv2d in float64."""
     cin, h, w_, cout, kh, kw, st = geom
     gen = torch.Generator().manual_seed(6)
-    x = torch.randn(4, cin, h, w_, generator=gen).to(DEV)
-    wt = (torch.randn(cout, cin, kh, kw, generator=gen) / math.sqrt(cin * kh * kw)).to(DEV)
-    bias = torch.randn(cout, generator=gen).to(DEV)
-    outs = []
-    for flag in ("64", "32", "16", None):
-        if flag is None:
-            os.environ.pop("CPC_ATOM_W", None)
-        else:
-            os.environ["CPC_ATOM_W"] = flag
-        try:
-            xg, wg, bg = (t.clone().requires_grad_(True) for t in (x, wt, bias))
-            y = cpc.ops.conv2d(xg, wg, bg, (st, st), (0, 0))
-            gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(7)).to(DEV)
-            (y * gy).sum().backward()
-            outs.append((y.detach(), xg.grad, wg.grad, bg.grad))
-        finally:
-            os.environ.pop("CPC_ATOM_W", None)
-    for other in outs[1:]:
-        for a, b in zip(outs[0], other):
-            assert rel_err(b, a) < 5e-5
-    want = F.conv2d(x.double().cpu(), wt.double().cpu(), bias.double().cpu(), stride=st)
-    assert rel_err(outs[-1][0], want) < 5e-5
+    x = torch.randn(2, cin, h, w_, generator=gen)
+    wt = torch.randn(cout, cin, kh, kw, generator=gen) / math.sqrt(cin * kh * kw)
+    bias = torch.randn(cout, generator=gen)
+    xr, wr, br = (t.clone().double().requires_grad_(True) for t in (x, wt, bias))
+    want = F.conv2d(xr, wr, br, stride=st)
+    gy = torch.randn(want.shape, generator=gen)
+    (want * gy.double()).sum().backward()
+    xg, wg, bg = (t.clone().to(DEV).requires_grad_(True) for t in (x, wt, bias))
+    got = cpc.ops.conv2d(xg, wg, bg, (st, st), (0, 0))
+    assert rel_err(got, want) < 5e-5
+    (got * gy.to(DEV)).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < 5e-5
+    assert rel_err(wg.grad, wr.grad) < TOL
+    assert rel_err(bg.grad, br.grad) < TOL
 
 
 UMMA_STRIDED_CASES = [

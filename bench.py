@@ -126,7 +126,7 @@ def run_reference(args):
                                                                   "batch %d per step" % CPU_SAMPLE_BATCH),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -318,10 +318,34 @@ def run_ours(args):
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "kernel_families": [{k: f[k] for k in ("family", "share", "ms", "launches", "tflops", "gbs")} for f in fam_list],
             "kernels": top[:24]}
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries loaded later write banners to file descriptor 1 (NCCL
+    prints "NCCL version ..." there at communicator creation).  Keep a private duplicate of the real stdout for the
+    result line and point descriptor 1 (and sys.stdout) at stderr for everything else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -207,52 +207,61 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
                 tma_load_4d(w_res + q * w_chunk_bytes + pl * b_plane_bytes, &tmap_b, &bars->wfull, 0, 0, q, pl);
             }
         }
+        // Each lane owns ONE load of a stage -- (plane, atom, tap-in-chunk) of the activations or one weight plane --
+        // decoded once here; inside the chunk loop the (tap row, tap column, channel chunk) of chunk q advance
+        // incrementally.  The loop must stay short: a single warp retires roughly one dependent instruction per
+        // 6-8 cycles and a chunk's MMAs last only ~770 cycles (ncu: runtime integer divisions here made the producer
+        // the bottleneck of every launch of this kernel).
         const int taps_per_load = p.cin_eff == KCHUNK ? 1 : p.tpc;
-        const int n_a_loads = p.planes * 2 * taps_per_load;     // (plane, atom, tap-in-chunk)
+        const int n_a_loads = p.planes * 2 * taps_per_load;     // <= 2 * 2 * 4 = 16
         const int n_loads = n_a_loads + (p.w_resident ? 0 : p.planes);
+        const bool is_a = lane < n_a_loads, is_b = !is_a && lane < n_loads;
+        const int my_t = is_a ? lane % taps_per_load : 0;
+        const int my_a = is_a ? (lane / taps_per_load) & 1 : 0;
+        const int my_pl = is_a ? lane / (2 * taps_per_load) : lane - n_a_loads;
+        const uint32_t my_off = is_a ? (uint32_t)(my_pl * A_PLANE_BYTES + my_a * (KCHUNK * 128) + my_t * p.cin_eff * 128)
+                                     : (uint32_t)(p.planes * A_PLANE_BYTES + my_pl * b_plane_bytes);
+        const int my_rep = my_pl * p.nrep;
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int mtile = tile / p.n_ntiles, ntile = tile - mtile * p.n_ntiles;
-            int ab[2], aoh[2], aw0[2];
+            int aoh[2], my_b = 0, my_w0 = 0, my_row = 0;
             for (int a = 0; a < 2; ++a) {
                 const int atom = mtile * 2 + a;                 // beyond n_atoms -> batch index OOB -> zero fill
                 const int row = atom / p.AW;
-                aw0[a] = (atom - row * p.AW) * ATOM;
-                ab[a] = row / p.PH;
-                aoh[a] = (row - ab[a] * p.PH) * p.h_mul + p.h_off;
+                const int b = row / p.PH;
+                aoh[a] = (row - b * p.PH) * p.h_mul + p.h_off;
+                if (a == my_a) { my_b = b; my_w0 = (atom - row * p.AW) * ATOM; my_row = aoh[a]; }
             }
             int q_begin, q_end;
             umma_live_chunks(p, aoh[0], aoh[1], q_begin, q_end);
+            // chunk q_begin: full-chunk mode -> (tap, channel chunk cc); shared-chunk mode -> this lane's tap q*tpc + t
+            int ti, tj, cc = 0;
+            {
+                const int tap0 = p.cin_eff == KCHUNK ? q_begin / p.cin_chunks : q_begin * p.tpc + my_t;
+                if (p.cin_eff == KCHUNK) cc = q_begin - tap0 * p.cin_chunks;
+                ti = tap0 / p.tw; tj = tap0 - ti * p.tw;
+            }
             for (int q = q_begin; q < q_end; ++q) {
                 if (lane == 0) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
                 }
                 __syncwarp();
-                uint8_t* st = stages_base + (size_t)stage * stage_bytes;
-                for (int l = lane; l < n_loads; l += 32) {
-                    if (l < n_a_loads) {
-                        const int t = l % taps_per_load;
-                        const int a = (l / taps_per_load) & 1;
-                        const int pl = l / (2 * taps_per_load);
-                        uint8_t* a_dst = st + pl * A_PLANE_BYTES + a * (KCHUNK * 128);
-                        if (p.cin_eff == KCHUNK) {
-                            const int tap = q / p.cin_chunks, c0 = (q - tap * p.cin_chunks) * KCHUNK;
-                            const int i = tap / p.tw, j = tap - i * p.tw;
-                            tma_load_5d(a_dst, &tmap_a, &bars->full[stage], aw0[a], aoh[a] + i * p.tap_h_mul, c0, ab[a],
-                                        pl * p.nrep + j);
-                        } else {
-                            int tap = q * p.tpc + t;
-                            if (tap >= p.ntaps) tap = 0;        // phantom tap: its packed weights are zero
-                            const int i = tap / p.tw, j = tap - i * p.tw;
-                            tma_load_5d(a_dst + t * p.cin_eff * 128, &tmap_a, &bars->full[stage], aw0[a],
-                                        aoh[a] + i * p.tap_h_mul, 0, ab[a], pl * p.nrep + j);
-                        }
-                    } else {
-                        const int pl = l - n_a_loads;
-                        tma_load_4d(st + p.planes * A_PLANE_BYTES + pl * b_plane_bytes, &tmap_b, &bars->full[stage], 0,
-                                    ntile * p.n_tile, q, pl);
-                    }
+                uint8_t* dst = stages_base + (size_t)stage * stage_bytes + my_off;
+                if (is_a) {
+                    // a phantom tap (beyond the kernel, last shared chunk) re-reads tap 0: its packed weights are zero
+                    const bool phantom = ti >= p.th;
+                    tma_load_5d(dst, &tmap_a, &bars->full[stage], my_w0, my_row + (phantom ? 0 : ti * p.tap_h_mul),
+                                cc * KCHUNK, my_b, my_rep + (phantom ? 0 : tj));
+                } else if (is_b) {
+                    tma_load_4d(dst, &tmap_b, &bars->full[stage], 0, ntile * p.n_tile, q, my_pl);
+                }
+                if (p.cin_eff == KCHUNK) {
+                    if (++cc == p.cin_chunks) { cc = 0; if (++tj == p.tw) { tj = 0; ++ti; } }
+                } else {
+                    tj += p.tpc;
+                    while (tj >= p.tw) { tj -= p.tw; ++ti; }
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -677,10 +686,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_wgrad_kernel(const __grid_
     if (warp == 0) {
         // whole warp in lockstep; lanes 0 .. 2*planes-1 issue one TMA load each (x / dy, per plane)
         int stage = 0; uint32_t phase = 0;
+        // (item, output row, 64-pixel atom) of chunk q advance incrementally: no divisions in the loop
+        int wa, b, oh;
+        {
+            const int row = q_begin / p.AW;
+            wa = q_begin - row * p.AW;
+            b = row / p.OH; oh = row - b * p.OH;
+        }
         for (int q = q_begin; q < q_end; ++q) {
-            const int row = q / p.AW;
-            const int w0 = (q - row * p.AW) * ATOM;
-            const int b = row / p.OH, oh = row - b * p.OH;
+            const int w0 = wa * ATOM;
             if (lane == 0) {
                 mbar_wait(&bars->empty[stage], phase ^ 1);
                 mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
@@ -695,6 +709,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_wgrad_kernel(const __grid_
                     tma_load_5d(st + p.planes * A_BYTES + pl * b_bytes, &tmap_dy, &bars->full[stage], w0, oh, ntile * p.n_tile,
                                 b, pl);
             }
+            if (++wa == p.AW) { wa = 0; if (++oh == p.OH) { oh = 0; ++b; } }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {

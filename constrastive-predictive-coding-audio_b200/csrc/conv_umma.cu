@@ -848,7 +848,9 @@ int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv
     k.pt = p->pad_top; k.sh = p->stride_h; k.planes = u.planes; k.stages = u.stages;
     k.dw = dw;
     const int tiles = k.n_xtiles * k.n_ntiles * p->kw;
-    int splits = (148 + tiles - 1) / tiles;
+    // one CTA per SM (shared memory): tiles * splits must not exceed the 148 SMs or a few CTAs form a second wave
+    // (ncu: 153 / 150 CTAs doubled the duration of the three large weight gradients)
+    int splits = 148 / tiles;
     const int max_splits = (k.n_chunks_total + 15) / 16;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -20,6 +20,7 @@
 // * The data gradient runs the same kernel on dy with swapped channel roles, once per output parity class
 //   (h+pt mod s_h, w+pl mod s_w): inside a class it is a stride-1 correlation with the sub-kernel
 //   w[:, :, rh + s_h*i', rw + s_w*j'], and the epilogue scatters to h = s_h*a + rh - pt.
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -43,6 +44,7 @@ struct UmmaConv {
     int nrep;                            // replicas per plane in the packed operand (>= tw)
     int srcH;                            // rows of the source tensor (taps landing outside are all-zero)
     int w_resident;                      // 1: all packed weight chunks live in shared memory for the whole kernel
+    int fuse;                            // > 0: columns are (parity class, channel) with `fuse` channels per class (32)
     int relu, stages;
     const float* bias;
     float* y;
@@ -108,7 +110,9 @@ int pack_split_launch(const float* x, __nv_bfloat16* out, long rows, int W, int 
 // weights (Cout, Cin, kh, kw) fp32 -> bf16 (planes, n_chunks, Nrows, 64), K-major rows of one K chunk.
 // GEMM tap (i', j') of a (th x tw) tap grid reads source tap (i_off + i_mul*i', j_off + j_mul*j').
 // swap = 0: rows n = co, k channel = ci (forward);  swap = 1: rows n = ci, k channel = co (data gradient).
-struct TapMap { int th, tw, i_off, i_mul, j_off, j_mul, swap; };
+// fuse = c > 0 (data gradient of a stride-2 conv, all four parity classes at once): rows n = (class, ci) with c
+// input channels per class, class = 2*rh + rw reads source tap (rh + 2*i', rw + 2*j'); taps outside the kernel are zero.
+struct TapMap { int th, tw, i_off, i_mul, j_off, j_mul, swap, fuse; };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                           int Cin, int kh, int kw, int n_rows, int k_ch, int cin_eff,
@@ -126,9 +130,15 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
         float v = 0.f;
         if (tap < ntaps && c < k_ch) {
             const int ti = tap / tm.tw, tj = tap - ti * tm.tw;
-            const int i = tm.i_off + tm.i_mul * ti, j = tm.j_off + tm.j_mul * tj;
-            const size_t co = tm.swap ? c : n, ci = tm.swap ? n : c;
-            v = __ldg(w + ((co * Cin + ci) * kh + i) * kw + j);
+            if (tm.fuse) {
+                const int cls = n / tm.fuse, ci = n - cls * tm.fuse;
+                const int i = (cls >> 1) + 2 * ti, j = (cls & 1) + 2 * tj;
+                if (i < kh && j < kw) v = __ldg(w + (((size_t)c * Cin + ci) * kh + i) * kw + j);
+            } else {
+                const int i = tm.i_off + tm.i_mul * ti, j = tm.j_off + tm.j_mul * tj;
+                const size_t co = tm.swap ? c : n, ci = tm.swap ? n : c;
+                v = __ldg(w + ((co * Cin + ci) * kh + i) * kw + j);
+            }
         }
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         out[idx] = hi;
@@ -331,8 +341,38 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_conv_kernel(const __grid_c
             mbar_wait(&bars->acc_full[buf], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 256;
-            float* ybase = p.y + ((size_t)b * p.n_rows_out * p.out_H + oh) * p.out_W + ow;
             const size_t chan_stride = (size_t)p.out_H * p.out_W;
+            if (p.fuse) {
+                // class-fused stride-2 data gradient: pixel (a, e) of the class domain owns dx[2a + rh, 2e + rw] for the
+                // four classes; the rw = 0 / 1 values of one channel are stored back to back, so a warp fills whole
+                // 32-byte sectors (the per-class kernels left half-written sectors to be merged in DRAM)
+                const int a = row - b * p.PH;
+                const bool in_dom = atom < p.n_atoms && pw < p.PW;
+                float* yb = p.y + (size_t)b * p.fuse * chan_stride;
+#pragma unroll 1
+                for (int rh = 0; rh < 2; ++rh) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr + (2 * rh) * 32, v0);
+                    tmem_ld32(taddr + (2 * rh + 1) * 32, v1);
+                    tmem_ld_wait();
+                    const int h = 2 * a + rh, w0 = 2 * pw;
+                    if (in_dom && h < p.out_H) {
+                        float* yo = yb + (size_t)h * p.out_W + w0;
+                        const bool ok0 = w0 < p.out_W, ok1 = w0 + 1 < p.out_W;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (ok0) yo[(size_t)c * chan_stride] = __uint_as_float(v0[c]);
+                            if (ok1) yo[(size_t)c * chan_stride + 1] = __uint_as_float(v1[c]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+                continue;
+            }
+            float* ybase = p.y + ((size_t)b * p.n_rows_out * p.out_H + oh) * p.out_W + ow;
             for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
@@ -371,6 +411,7 @@ struct ConvProblem {
     int out_H, out_W, oh_mul, oh_off, ow_mul, ow_off;  // destination pixel
     // operand already packed by the caller / a sibling problem: [plane][pre_nrep][rows][pre_Wp], replica r as above
     const __nv_bfloat16* pre; int pre_Wp, pre_nrep;
+    int fuse;                                          // channels per parity class of a class-fused data gradient (0: off)
 };
 
 struct UmmaPlan {
@@ -457,6 +498,7 @@ static int run_problem(const ConvProblem& c, const float* w, const float* bias, 
     k.cin_chunks = u.cin_chunks; k.n_chunks = u.n_chunks;
     k.h_mul = c.h_mul; k.tap_h_mul = c.tap_h_mul; k.h_off = c.h_off;
     k.out_H = c.out_H; k.out_W = c.out_W; k.oh_mul = c.oh_mul; k.oh_off = c.oh_off; k.ow_mul = c.ow_mul; k.ow_off = c.ow_off;
+    k.fuse = c.fuse;
     k.planes = u.planes; k.nrep = nrep; k.w_resident = u.w_resident; k.relu = relu; k.stages = u.stages; k.bias = bias; k.y = out; k.srcH = c.srcH;
     if (cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)
         return CPC_ERR_CUDA;
@@ -554,6 +596,26 @@ static DgradShare dgrad_share(const cpc_conv_params* p) {
     return d;
 }
 
+// Class-fused data gradient of a stride-2 conv (all four output parity classes in ONE launch): the GEMM pixel domain
+// is (a, e) = (h / 2, w / 2), the tap grid the 2 x 2 shifts (i', j') of dy, and the N = 4 * C_in = 128 accumulator
+// columns are (class, channel); weight rows of taps a class does not have are zero.  Every dy tile is fetched once
+// for all classes (the per-class launches fetch it 9 / 4 times) and dx is written in full sectors.
+static bool fused_dgrad_problem(const float* dy, const cpc_conv_params* p, ConvProblem& c) {
+    const char* env = getenv("CPC_NO_FUSED_DGRAD");
+    if (env && env[0] == '1') return false;
+    if (p->stride_h != 2 || p->stride_w != 2 || p->pad_top != 0 || p->pad_left != 0) return false;
+    if (p->kh < 2 || p->kh > 4 || p->kw < 2 || p->kw > 4 || p->c_in != 32) return false;
+    c = ConvProblem{};
+    c.src = dy; c.in_ch = p->c_out; c.srcH = p->h_out; c.srcW = p->w_out; c.out_ch = 4 * p->c_in;
+    c.tm = TapMap{2, 2, 0, 2, 0, 2, 1, p->c_in};
+    c.PH = (p->h_in + 1) / 2; c.PW = (p->w_in + 1) / 2;
+    c.h_mul = 1; c.tap_h_mul = -1; c.h_off = 0;
+    c.w_mul = 1; c.rep_mul = -1; c.w_off = 0;
+    c.out_H = p->h_in; c.out_W = p->w_in; c.oh_mul = 2; c.oh_off = 0; c.ow_mul = 2; c.ow_off = 0;
+    c.fuse = p->c_in;
+    return plan_problem(c, p->batch, p->precision).ok;
+}
+
 size_t umma_conv_workspace(const cpc_conv_params* p, int which) {
     if (!umma_conv_eligible(p, which)) return 0;
     size_t need = 0;
@@ -564,6 +626,11 @@ size_t umma_conv_workspace(const cpc_conv_params* p, int which) {
         const DgradShare d = dgrad_share(p);
         need = d.max_single;
         if (d.common && d.act_bytes + d.max_w_bytes > need) need = d.act_bytes + d.max_w_bytes;
+        ConvProblem f;
+        if (fused_dgrad_problem(nullptr, p, f)) {
+            UmmaPlan u = plan_problem(f, p->batch, p->precision);
+            if (u.act_bytes + u.w_bytes > need) need = u.act_bytes + u.w_bytes;
+        }
     }
     return need + 2048;
 }
@@ -580,6 +647,10 @@ int umma_conv_launch(const float* in, const float* w, const float* bias, float* 
         ConvProblem c = fwd_problem(in, p);
         if (prep) { c.pre = prep; c.pre_Wp = (p->w_out + 7) & ~7; c.pre_nrep = p->kw; }
         return run_problem(c, w, bias, out, p, p->relu, workspace, workspace_bytes, s);
+    }
+    {
+        ConvProblem f;
+        if (fused_dgrad_problem(in, p, f)) return run_problem(f, w, nullptr, out, p, 0, workspace, workspace_bytes, s);
     }
     bool need_zero = false;
     for (int rh = 0; rh < p->stride_h; ++rh)

@@ -281,6 +281,9 @@ UMMA_STRIDED_CASES = [
     (2, 64, 1, 100, 128, 1, 4, 1, 2, 0, 0, 0),      # AudioEncoder layers 2-4 shape (k 4, stride 2)
     (1, 32, 10, 20, 32, 1, 1, 2, 2, 0, 0, 0),       # stride larger than the kernel: some dgrad classes are empty
     (1, 32, 12, 30, 64, 3, 1, 2, 1, 0, 0, 2),       # vertical stride + top padding
+    (1, 32, 10, 21, 64, 2, 2, 2, 2, 0, 0, 0),       # class-fused data gradient: every class has exactly one tap
+    (2, 32, 11, 20, 64, 4, 4, 2, 2, 0, 0, 0),       # class-fused data gradient: every class has 2 x 2 taps
+    (1, 32, 14, 19, 128, 3, 2, 2, 2, 0, 0, 0),      # class-fused, odd width: the last column exists for rw = 0 only
 ]
 
 

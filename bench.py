@@ -60,14 +60,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count_since(self, t0):
+        return sum(1 for t, _ in self.rows if t >= t0)
+
+    def stop(self, t0=0.0):
+        """Summary of the samples taken at or after wall-clock time t0 (the start of the measured load)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for t, r in self.rows:
+            if t < t0:
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -210,14 +216,26 @@ def run_ours(args):
             ms = t.item()
         return ms / k
 
+    clocks = ClockSampler(local)
+    clocks.start()                                              # nvidia-smi needs a moment to deliver its first sample
     for i in range(args.warmup):
         step(dev_batches[i % 2])
-    clocks = ClockSampler(local)
-    clocks.start()
+    torch.cuda.synchronize()
     _lib.reset_launch_count()
+    t_load = time.time()
     ms_dev = timed(lambda i: step(dev_batches[i % 2]), args.steps)
     launches = launches_per_step * args.steps if graphed is not None else _lib.launch_count()
-    clk = clocks.stop()
+    # K steps of ~16 ms are shorter than a few 100 ms sampling periods: keep the identical load running (untimed) until
+    # ~0.6 s of it have been sampled.  The count derives from ms_dev (max over ranks), so every rank runs the same steps.
+    clock_window = "timed region"
+    n_extra = int(600.0 / max(ms_dev, 1e-3)) - args.steps
+    if n_extra > 0:
+        for i in range(n_extra):
+            step(dev_batches[i % 2])
+        torch.cuda.synchronize()
+        clock_window = "timed region + %d identical untimed steps right after it" % n_extra
+    clk = clocks.stop(t_load)
+    clk["window"] = clock_window
 
     # end to end through the public API: pinned host batch -> device, full step, loss + max score read back
     last = {}

@@ -382,7 +382,8 @@ def test_residual_encoder_matches_reference_golden(cpc):
 # ---------------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("shape,k,ceil", [((2, 3, 9, 11), 2, True), ((2, 3, 9, 11), 2, False), ((1, 5, 12, 12), 3, True),
-                                          ((3, 2, 7, 5), 4, True), ((2, 4, 127, 314), 2, True), ((1, 2, 6, 8), 1, False)])
+                                          ((3, 2, 7, 5), 4, True), ((2, 4, 127, 314), 2, True), ((1, 2, 6, 8), 1, False),
+                                          ((2, 3, 10, 12), 2, False), ((1, 2, 9, 12), 2, False), ((1, 2, 9, 1030), 2, True)])
 def test_max_pool_matches_torch_reference(cpc, shape, k, ceil):
     """nn.MaxPool2d(k, ceil_mode) forward / backward incl. ties (integer-valued input) -- bit exact."""
     gen = torch.Generator().manual_seed(1)

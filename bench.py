@@ -335,7 +335,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "kernel_families": [{k: f[k] for k in ("family", "share", "ms", "launches", "tflops", "gbs")} for f in fam_list],
-            "kernels": top[:24]}
+            "kernels": top[:40]}
     emit(line)
 
 

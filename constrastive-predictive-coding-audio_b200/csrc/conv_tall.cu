@@ -334,22 +334,20 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
                     const int yslot = yn % TW_YS;
                     mbar_wait(&bars->yfull[yslot], (yn / TW_YS) & 1);
                     tc_fence_after();
-                    const uint32_t y_addr = smem_u32(y_ring + yslot * TW_GROUP);
+                    const uint64_t y_d0 = make_smem_desc(smem_u32(y_ring + yslot * TW_GROUP), 16, 1024);
                     for (int k = 0; k < TW_NB; ++k) {
                         const int pg = q + d0 + k;                            // x row group index
                         if (pg < 0 || pg >= n_xgroups) continue;              // rows outside the source: zeros
-                        const uint32_t x_addr = smem_u32(x_ring + ((xn + k) % TW_XS) * TW_GROUP);
+                        const uint64_t x_d0 = make_smem_desc(smem_u32(x_ring + ((xn + k) % TW_XS) * TW_GROUP), 16, 1024);
                         const uint32_t d_tmem = tmem_base + (uint32_t)k * 128;
 #pragma unroll
                         for (int cb = 0; cb < 3; ++cb) {                       // (x hi, dy hi) (x hi, dy lo) (x lo, dy hi)
-                            const uint32_t a_addr = x_addr + (cb == 2 ? 128 * 128 : 0);
-                            const uint32_t b_addr = y_addr + (cb == 1 ? 128 * 128 : 0);
+                            const uint64_t a_d = x_d0 + (uint64_t)(cb == 2 ? (128 * 128) >> 4 : 0);
+                            const uint64_t b_d = y_d0 + (uint64_t)(cb == 1 ? (128 * 128) >> 4 : 0);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = make_smem_desc(a_addr + ks * 32, 16, 1024);
-                                const uint64_t bd = make_smem_desc(b_addr + ks * 32, 16, 1024);
-                                mma_bf16(d_tmem, ad, bd, idesc, ((started >> k) & 1u) | (uint32_t)(cb | ks));
-                            }
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_bf16(d_tmem, a_d + (uint64_t)(ks * 2), b_d + (uint64_t)(ks * 2), idesc,
+                                         ((started >> k) & 1u) | (uint32_t)(cb | ks));
                         }
                         started |= 1u << k;
                     }

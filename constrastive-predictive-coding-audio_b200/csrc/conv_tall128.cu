@@ -149,22 +149,22 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
                         mbar_wait(&bars->full[stage], (v / T8_S) & 1);
                         tc_fence_after();
                         if (j >= j_lo) {
-                            const uint32_t a_addr = smem_u32(a_ring + stage * T8_TILE);
+                            // one descriptor per operand tile; planes and K steps are constant increments of its 16-byte
+                            // address field (the issuing thread's instruction count per MMA bounds this kernel)
+                            const uint64_t a_d0 = make_smem_desc(smem_u32(a_ring + stage * T8_TILE), T8_TILE / 2, 1024);
                             for (int rho = 0; rho < T8_R; ++rho) {
                                 const int tap = j - rho;
                                 if (tap < 0 || tap >= p.kh) continue;
-                                const uint32_t b_addr = w_base + ((v - rho) % T8_T) * T8_TILE;
+                                const uint64_t b_d0 = make_smem_desc(w_base + ((v - rho) % T8_T) * T8_TILE, 16, 1024);
                                 const uint32_t d_tmem = tmem_base + (uint32_t)rho * T8_N;
 #pragma unroll
                                 for (int cb = 0; cb < 3; ++cb) {               // (hi,hi) (hi,lo) (lo,hi)
-                                    const uint32_t a_pl = a_addr + (cb == 2 ? 64 * 128 : 0);
-                                    const uint32_t b_pl = b_addr + (cb == 1 ? T8_N * 128 : 0);
+                                    const uint64_t a_d = a_d0 + (uint64_t)(cb == 2 ? (64 * 128) >> 4 : 0);
+                                    const uint64_t b_d = b_d0 + (uint64_t)(cb == 1 ? (T8_N * 128) >> 4 : 0);
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const uint64_t ad = make_smem_desc(a_pl + k * (16 * 128), T8_TILE / 2, 1024);
-                                        const uint64_t bd = make_smem_desc(b_pl + k * 32, 16, 1024);
-                                        mma_bf16(d_tmem, ad, bd, idesc, ((started >> rho) & 1u) | (uint32_t)(cb | k));
-                                    }
+                                    for (int k = 0; k < 4; ++k)
+                                        mma_bf16(d_tmem, a_d + (uint64_t)(k * ((16 * 128) >> 4)), b_d + (uint64_t)(k * 2), idesc,
+                                                 ((started >> rho) & 1u) | (uint32_t)(cb | k));
                                 }
                                 started |= 1u << rho;
                             }
@@ -313,22 +313,21 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_wgrad_kernel(const __gr
                         const int yslot = yn % T8W_YS;
                         mbar_wait(&bars->yfull[yslot], (yn / T8W_YS) & 1);
                         tc_fence_after();
-                        const uint32_t y_addr = smem_u32(y_ring + yslot * T8_TILE);
+                        const uint64_t y_d0 = make_smem_desc(smem_u32(y_ring + yslot * T8_TILE), 16, 1024);
                         for (int k = 0; k < T8W_NT; ++k) {
                             const int h = r - p.P + i0 + k;                   // x row paired with dy row r for tap i0 + k
                             if (i0 + k >= p.kh || h < 0 || h >= p.H_src) continue;
-                            const uint32_t x_addr = smem_u32(x_ring + ((xn - (T8W_NT - 1) + k) % T8W_XS) * T8_TILE);
+                            const uint64_t x_d0 =
+                                make_smem_desc(smem_u32(x_ring + ((xn - (T8W_NT - 1) + k) % T8W_XS) * T8_TILE), 16, 1024);
                             const uint32_t d_tmem = tmem_base + (uint32_t)k * T8_N;
 #pragma unroll
                             for (int cb = 0; cb < 3; ++cb) {                   // (x hi, dy hi) (x hi, dy lo) (x lo, dy hi)
-                                const uint32_t a_addr = x_addr + (cb == 2 ? 128 * 128 : 0);
-                                const uint32_t b_addr = y_addr + (cb == 1 ? 128 * 128 : 0);
+                                const uint64_t a_d = x_d0 + (uint64_t)(cb == 2 ? (128 * 128) >> 4 : 0);
+                                const uint64_t b_d = y_d0 + (uint64_t)(cb == 1 ? (128 * 128) >> 4 : 0);
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint64_t ad = make_smem_desc(a_addr + ks * 32, 16, 1024);
-                                    const uint64_t bd = make_smem_desc(b_addr + ks * 32, 16, 1024);
-                                    mma_bf16(d_tmem, ad, bd, idesc, ((started >> k) & 1u) | (uint32_t)(cb | ks));
-                                }
+                                for (int ks = 0; ks < 4; ++ks)
+                                    mma_bf16(d_tmem, a_d + (uint64_t)(ks * 2), b_d + (uint64_t)(ks * 2), idesc,
+                                             ((started >> k) & 1u) | (uint32_t)(cb | ks));
                             }
                             started |= 1u << k;
                         }

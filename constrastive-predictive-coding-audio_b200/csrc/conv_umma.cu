@@ -794,14 +794,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_wgrad_kernel(const __grid_
                 const uint32_t b0 = st + p.planes * A_BYTES;
                 const int ncombo = p.planes == 2 ? 3 : 1;
                 for (int cb = 0; cb < ncombo; ++cb) {
-                    const uint32_t a_addr = st + (cb == 2 ? A_BYTES : 0);
-                    const uint32_t b_addr = b0 + (cb == 1 ? b_bytes : 0);
+                    const uint64_t a_d = make_smem_desc(st + (cb == 2 ? A_BYTES : 0), 16, 1024);
+                    const uint64_t b_d = make_smem_desc(b0 + (cb == 1 ? b_bytes : 0), 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-                        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-                        mma_bf16(tmem_base, ad, bd, idesc, (q | cb | k) != 0);
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        mma_bf16(tmem_base, a_d + (uint64_t)(k * 2), b_d + (uint64_t)(k * 2), idesc, (q | cb | k) != 0);
                 }
                 tc_commit(&bars->empty[stage]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }

@@ -63,7 +63,10 @@ __device__ __forceinline__ void small_gather(const float* __restrict__ x, const 
     }
 }
 
-// grid (pixel chunks, B, Cout / 32); block 256 threads = 256 pixels
+// grid (pixel chunks, B, Cout / 32); block 256 threads, SF_PIX pixels per thread 256 apart (ncu: with one pixel per
+// thread the kernel was instruction-issue bound at 79 % -- 144 shared-memory weight reads and 64-bit store addressing
+// per 576 FMAs; two pixels share every weight read)
+constexpr int SF_PIX = 2;
 template <int KT>
 __global__ void __launch_bounds__(256) small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ y, SmallGeom g,
@@ -77,31 +80,60 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const float* __restrict_
     }
     if (threadIdx.x < 32) bs[threadIdx.x] = (bias && co0 + threadIdx.x < g.Cout) ? __ldg(bias + co0 + threadIdx.x) : 0.f;
     __syncthreads();
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= g.ohow) return;
+    const int pix0 = blockIdx.x * (256 * SF_PIX) + threadIdx.x;
+    if (pix0 >= g.ohow) return;
     const int b = blockIdx.y;
     int toff[KT];
     small_tap_offsets<KT>(g, toff);
-    float v[KT];
-    small_gather<KT>(x, g, toff, interior != 0, b, pix, v);
-    float acc[32];
+    float v[SF_PIX][KT];
+    bool live[SF_PIX];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = bs[c];
+    for (int u = 0; u < SF_PIX; ++u) {
+        live[u] = pix0 + u * 256 < g.ohow;
+        if (live[u]) small_gather<KT>(x, g, toff, interior != 0, b, pix0 + u * 256, v[u]);
+        else {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) v[u][k] = 0.f;
+        }
+    }
+    float acc[SF_PIX][32];
+#pragma unroll
+    for (int u = 0; u < SF_PIX; ++u)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[u][c] = bs[c];
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
             const float4 wv = *reinterpret_cast<const float4*>(&ws[k][c4 * 4]);
-            acc[c4 * 4 + 0] = fmaf(v[k], wv.x, acc[c4 * 4 + 0]);
-            acc[c4 * 4 + 1] = fmaf(v[k], wv.y, acc[c4 * 4 + 1]);
-            acc[c4 * 4 + 2] = fmaf(v[k], wv.z, acc[c4 * 4 + 2]);
-            acc[c4 * 4 + 3] = fmaf(v[k], wv.w, acc[c4 * 4 + 3]);
+#pragma unroll
+            for (int u = 0; u < SF_PIX; ++u) {
+                acc[u][c4 * 4 + 0] = fmaf(v[u][k], wv.x, acc[u][c4 * 4 + 0]);
+                acc[u][c4 * 4 + 1] = fmaf(v[u][k], wv.y, acc[u][c4 * 4 + 1]);
+                acc[u][c4 * 4 + 2] = fmaf(v[u][k], wv.z, acc[u][c4 * 4 + 2]);
+                acc[u][c4 * 4 + 3] = fmaf(v[u][k], wv.w, acc[u][c4 * 4 + 3]);
+            }
         }
     }
-    float* yo = y + ((size_t)b * g.Cout + co0) * g.ohow + pix;
+    const int n_ch = min(32, g.Cout - co0);
+    float* yo = y + ((size_t)b * g.Cout + co0) * g.ohow + pix0;
+    if (n_ch == 32) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-        if (co0 + c < g.Cout) yo[(size_t)c * g.ohow] = relu ? fmaxf(acc[c], 0.f) : acc[c];
+        for (int c = 0; c < 32; ++c, yo += g.ohow) {
+#pragma unroll
+            for (int u = 0; u < SF_PIX; ++u)
+                if (live[u]) yo[u * 256] = relu ? fmaxf(acc[u][c], 0.f) : acc[u][c];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c, yo += g.ohow) {
+            if (c < n_ch) {
+#pragma unroll
+                for (int u = 0; u < SF_PIX; ++u)
+                    if (live[u]) yo[u * 256] = relu ? fmaxf(acc[u][c], 0.f) : acc[u][c];
+            }
+        }
+    }
 }
 
 // grid (pixel chunks of SW_ITERS * 32 pixels, B, Cout / 32); block = 32 / CPW warps, warp w owns channels CPW*w .. +CPW-1
@@ -157,7 +189,7 @@ static void small_launch(int which, const float* x, const float* w, const float*
     // every window inside the input <=> no bounds checks in the gather
     const int interior = g.pt == 0 && g.pl == 0 && (g.OH - 1) * g.sh + g.kh <= g.H && (g.OW - 1) * g.sw + g.kw <= g.W;
     if (which == 0) {
-        dim3 grid(ceil_div(g.ohow, 256), g.B, ceil_div(g.Cout, 32));
+        dim3 grid(ceil_div(g.ohow, 256 * SF_PIX), g.B, ceil_div(g.Cout, 32));
         small_fwd_kernel<KT><<<grid, 256, 0, s>>>(x, w, bias, out, g, relu, interior);
     } else {
         dim3 grid(ceil_div(g.ohow, SW_ITERS * 32), g.B, ceil_div(g.Cout, 32));

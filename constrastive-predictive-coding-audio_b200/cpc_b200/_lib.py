@@ -78,6 +78,7 @@ SIGNATURES = {
     "cpc_conv_kernel_family": (ctypes.c_int, [ctypes.POINTER(ConvParams), ctypes.c_int]),
     "cpc_conv_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvParams), ctypes.c_int]),
     "cpc_conv_pack": (ctypes.c_int, [_P, _P, ctypes.POINTER(ConvParams), ctypes.c_int, _P]),
+    "cpc_conv_pack_dy": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P]),
     "cpc_conv_fwd_ex": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, _P, ctypes.c_size_t, _P]),
     "cpc_conv_dgrad_ex": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P, _P, ctypes.c_size_t, _P]),
     "cpc_conv_wgrad_ex": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, _P, _P, ctypes.c_size_t, _P]),

@@ -209,7 +209,17 @@ class _ConvFunction(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         with torch.cuda.device(dy.device):
-            packed_dy = _pack_operand(lib, dy, p, 1) if need_dw else None
+            packed_dy = None
+            if need_dw:
+                nbytes = lib.cpc_conv_packed_bytes(ctypes.byref(p), 1)
+                if nbytes and ctx.has_bias:
+                    # the packing pass over dy also reduces the bias gradient (dy is read once for both)
+                    packed_dy = torch.empty(int(nbytes), dtype=torch.uint8, device=dy.device)
+                    db = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device)
+                    _call("cpc_conv_pack dy", 0.0, lib.cpc_conv_pack_dy, _ptr(dy), _ptr(packed_dy), _ptr(db), ctypes.byref(p),
+                          _stream(), nbytes=4.0 * dy.numel() + float(nbytes))
+                else:
+                    packed_dy = _pack_operand(lib, dy, p, 1)
             if need_dx:
                 dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
                 ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
@@ -217,10 +227,12 @@ class _ConvFunction(torch.autograd.Function):
                       ctypes.byref(p), _ptr(packed_dy), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
             if need_dw:
                 dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
-                db = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+                db_here = None                                   # bias gradient still to be computed by the wgrad call
+                if ctx.has_bias and db is None:
+                    db = db_here = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device)
                 ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
                 _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad_ex, _ptr(x), _ptr(dy), _ptr(dw),
-                      _ptr(db), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws),
+                      _ptr(db_here), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws),
                       ws.numel() if ws is not None else 0, _stream())
         return dx, dw, db, None, None, None, None, None, None
 

@@ -19,6 +19,8 @@ int umma_conv_launch(const float* in, const float* w, const float* bias, float* 
                      const void* pre, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int pack_split_launch(const float* x, __nv_bfloat16* out, long rows, int W, int Wp, int planes, int nrep, int w_mul,
                       int rep_mul, int w_off, cudaStream_t s);
+int pack_split_sum_launch(const float* x, __nv_bfloat16* out, float* sums, long rows, int W, int Wp, int planes, int H, int C,
+                          cudaStream_t s);
 
 size_t umma_wgrad_workspace(const cpc_conv_params* p);
 bool umma_wgrad_eligible(const cpc_conv_params* p);
@@ -333,6 +335,22 @@ extern "C" int cpc_conv_pack(const float* src, void* packed, const cpc_conv_para
     else
         st = pack_split_launch(src, out, (long)p->batch * p->c_out * p->h_out, p->w_out, Wp, planes, 1, 1, 0, 0,
                                (cudaStream_t)stream);
+    if (st == CPC_OK) count_launch();
+    return st;
+}
+
+extern "C" int cpc_conv_pack_dy(const float* dy, void* packed, float* dbias, const cpc_conv_params* p, void* stream) {
+    if (!dbias) return cpc_conv_pack(dy, packed, p, 1, stream);
+    int st = validate(p);
+    if (st != CPC_OK) return st;
+    if (!dy || !packed) return CPC_ERR_NULL;
+    if (cpc_conv_packed_bytes(p, 1) == 0) return CPC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return CPC_ERR_ALIGNMENT;
+    if ((st = check_device()) != CPC_OK) return st;
+    const int planes = p->precision == 1 ? 1 : 2;
+    const int Wp = (p->w_out + 7) & ~7;
+    st = pack_split_sum_launch(dy, reinterpret_cast<__nv_bfloat16*>(packed), dbias, (long)p->batch * p->c_out * p->h_out,
+                               p->w_out, Wp, planes, p->h_out, p->c_out, (cudaStream_t)stream);
     if (st == CPC_OK) count_launch();
     return st;
 }

@@ -94,6 +94,92 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
     }
 }
 
+// Plain pack of dy (one replica, unit stride) that also reduces the bias gradient: rows are (item, channel, h), so
+// sums[channel] += sum of the row.  dy is read from HBM exactly once for both results (the separate bias-gradient pass
+// re-read every dy: 0.32 ms of the e24 step).  Per loop iteration a block covers 256 consecutive 8-column groups, i.e. a
+// few consecutive rows: per-row bins in shared memory, then one thread folds the bins channel by channel.
+constexpr int PACK_BINS = 264;
+__global__ void __launch_bounds__(256) pack_split_sum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                            float* __restrict__ sums, long rows, int W, int Wp, int planes,
+                                                            FastDiv d_h, FastDiv d_groups, int C, int vec_ok) {
+    // bins[parity][plane - first plane of the block]: a block's 256 consecutive groups span a few consecutive rows, i.e.
+    // one or two (item, channel) planes; lanes of one plane are a contiguous lane range, summed by a segmented warp scan
+    __shared__ float bins[2][PACK_BINS];
+    const int groups = Wp >> 3, lane = threadIdx.x & 31;
+    const long total = rows * groups;
+    const long plane_stride = rows * (long)Wp;
+    for (int t = threadIdx.x; t < 2 * PACK_BINS; t += 256) (&bins[0][0])[t] = 0.f;
+    __syncthreads();
+    const long n_iter = (total + (long)gridDim.x * 256 - 1) / ((long)gridDim.x * 256);
+    for (long it = 0; it < n_iter; ++it) {
+        float* bin = bins[it & 1];
+        const long g0 = (it * gridDim.x + blockIdx.x) * 256;          // first group of this block in this iteration
+        const long g = g0 + threadIdx.x;
+        const int plane_first = d_h.div(d_groups.div((int)min(g0, total - 1)));
+        int plane = -1;
+        float sum = 0.f;
+        if (g < total) {
+            int row, gi;
+            d_groups.divmod((int)g, row, gi);
+            const int w0 = gi << 3;
+            plane = d_h.div(row);
+            const float* src = x + (long)row * W;
+            float v[8];
+            if (vec_ok && w0 + 8 <= W) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 t = __ldg(reinterpret_cast<const float2*>(src + w0) + i);
+                    v[2 * i] = t.x; v[2 * i + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = (w0 + i < W) ? __ldg(src + w0 + i) : 0.f;
+            }
+            __align__(16) __nv_bfloat16 hi[8];
+            __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sum += v[i];
+                hi[i] = __float2bfloat16_rn(v[i]);
+                lo[i] = __float2bfloat16_rn(v[i] - __bfloat162float(hi[i]));
+            }
+            const long o = (long)row * Wp + w0;
+            *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
+            if (planes == 2) *reinterpret_cast<uint4*>(out + plane_stride + o) = *reinterpret_cast<const uint4*>(lo);
+        }
+        // segmented inclusive scan over lanes with equal plane (planes are non-decreasing across lanes)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, sum, o);
+            const int q = __shfl_up_sync(0xffffffffu, plane, o);
+            if (lane >= o && q == plane) sum += t;
+        }
+        const int next = __shfl_down_sync(0xffffffffu, plane, 1);
+        if (plane >= 0 && (lane == 31 || next != plane)) atomicAdd(&bin[plane - plane_first], sum);
+        __syncthreads();
+        if (g0 < total) {
+            const int plane_last = d_h.div(d_groups.div((int)min(g0 + 255, total - 1)));
+            for (int t = threadIdx.x; t <= plane_last - plane_first; t += 256) {
+                atomicAdd(sums + (plane_first + t) % C, bin[t]);
+                bin[t] = 0.f;                                    // ready for iteration it + 2 (a barrier lies in between)
+            }
+        }
+    }
+}
+
+int pack_split_sum_launch(const float* x, __nv_bfloat16* out, float* sums, long rows, int W, int Wp, int planes, int H, int C,
+                          cudaStream_t s) {
+    if (cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)C, s) != cudaSuccess) return CPC_ERR_CUDA;
+    const long groups = rows * (Wp / 8);
+    int blocks = (int)((groups + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    const int vec_ok = (W % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
+    if (groups >= (1l << 31)) return CPC_ERR_BAD_SHAPE;
+    pack_split_sum_kernel<<<blocks, 256, 0, s>>>(x, out, sums, rows, W, Wp, planes, FastDiv(H), FastDiv(Wp / 8), C, vec_ok);
+    return cudaGetLastError() == cudaSuccess ? CPC_OK : CPC_ERR_CUDA;
+}
+
 // host launcher shared with conv_tall.cu / conv_tall128.cu
 int pack_split_launch(const float* x, __nv_bfloat16* out, long rows, int W, int Wp, int planes, int nrep, int w_mul,
                       int rep_mul, int w_off, cudaStream_t s) {

@@ -137,6 +137,9 @@ int cpc_conv_kernel_family(const cpc_conv_params* p, int which);
  *   `packed` must be 16-byte aligned (it becomes a TMA global base address). */
 size_t cpc_conv_packed_bytes(const cpc_conv_params* p, int operand);
 int cpc_conv_pack(const float* src, void* packed, const cpc_conv_params* p, int operand, void* stream);
+/* cpc_conv_pack(dy, ..., operand = 1) that also writes the bias gradient dbias[c_out] = sum over (b, h, w) of dy when
+ * dbias is non-NULL: dy is read once for both (contrastive_estimation_training.py:161, autograd of the conv biases). */
+int cpc_conv_pack_dy(const float* dy, void* packed, float* dbias, const cpc_conv_params* p, void* stream);
 int cpc_conv_fwd_ex(const float* x, const float* w, const float* bias, float* y, const cpc_conv_params* p,
                     const void* packed_x, void* workspace, size_t workspace_bytes, void* stream);
 int cpc_conv_dgrad_ex(const float* dy, const float* w, float* dx, const cpc_conv_params* p, const void* packed_dy,

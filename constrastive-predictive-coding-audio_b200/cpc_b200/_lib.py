@@ -85,6 +85,9 @@ SIGNATURES = {
     "cpc_bn_relu_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(BnParams)]),
     "cpc_bn_relu_fwd": (ctypes.c_int, [_P] * 9 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
     "cpc_bn_relu_bwd": (ctypes.c_int, [_P] * 11 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
+    "cpc_bn_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(BnParams)]),
+    "cpc_bn_relu_fwd_packed": (ctypes.c_int, [_P] * 9 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
+    "cpc_bn_relu_bwd_packed": (ctypes.c_int, [_P] * 12 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
     "cpc_maxpool_fwd": (ctypes.c_int, [_P, _P, ctypes.POINTER(PoolParams), _P]),
     "cpc_maxpool_bwd": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(PoolParams), _P]),
     "cpc_infonce_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(InfoNceParams), ctypes.c_int]),

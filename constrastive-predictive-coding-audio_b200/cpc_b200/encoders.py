@@ -289,9 +289,16 @@ class ScalogramEncoderBlock(nn.Module):
             i += 3
         if len(stages) != 2:
             return None
+        (top_a, conv_a, bn_a), (top_b, conv_b, bn_b) = stages
+        y_a = conv_a(x, extra_top=top_a)
+        if ops.block_tail_eligible(y_a, bn_a, conv_b, top_b, bn_b):
+            # bn_a + ReLU + conv_b + bn_b (+ residual) + ReLU as one autograd node with packed intermediates
+            oh = y_a.shape[2] + top_b + 2 * conv_b.padding[0] - conv_b.weight.shape[2] + 1
+            res, off = (self._residual_branch(x, (oh, y_a.shape[3])) if self.residual else (None, (0, 0)))
+            return ops.block_tail(y_a, bn_a, conv_b, top_b, bn_b, residual=res, res_off=off, outer_relu=outer_relu)
         h = x
         for idx, (top, conv, bn) in enumerate(stages):
-            h = conv(h, extra_top=top)
+            h = y_a if idx == 0 else conv(h, extra_top=top)
             if idx == 0 or not self.residual:
                 h = ops.bn_relu(h, bn, relu=True, outer_relu=False)
                 if idx == 1 and outer_relu:

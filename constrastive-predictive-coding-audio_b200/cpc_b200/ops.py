@@ -430,6 +430,156 @@ def bn_relu(x, bn, residual=None, res_off=(0, 0), relu=True, outer_relu=False):
                                  bool(training), bn.eps, momentum)
 
 
+def _bn_state(bn):
+    """(training, momentum, running_mean, running_var) of an nn.BatchNorm2d for one forward call, advancing
+    num_batches_tracked like nn.BatchNorm2d.forward does."""
+    training = bn.training or bn.running_mean is None
+    momentum = bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    if momentum is None:
+        momentum = 0.0
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return bool(training), momentum, rm, rv
+
+
+class _BlockTailFunction(torch.autograd.Function):
+    """Everything of a ScalogramEncoderBlock behind its first conv as ONE autograd node (scalogram_model.py:399-431,
+    451-472):   out = relu_if(outer, relu(bn1(conv_b(relu(bn0(y_a))))) + crop(residual)).
+
+    Inside the node the activation between bn0 and conv_b and the gradient between bn1 and conv_b exist only as the
+    bf16 hi/lo operand planes the row-streaming conv kernels read: bn0 writes them instead of an fp32 tensor, bn1's
+    backward writes dy the same way (plus its per-channel sum = conv_b's bias gradient).  Two fp32 tensors, two packing
+    passes and the bias-gradient pass of the unfused chain disappear; every value is computed by the same kernels."""
+
+    @staticmethod
+    def forward(ctx, y_a, g0, b0, rm0, rv0, w, bias, g1, b1, rm1, rv1, residual, cfg):
+        (top, out_hw, res_off, outer_relu, tr0, eps0, mom0, tr1, eps1, mom1, precision) = cfg
+        _require_cuda(y_a, w, residual)
+        lib = _lib.load()
+        y_a = y_a.contiguous()
+        w = w.contiguous()
+        if residual is not None:
+            residual = residual.contiguous()
+        dev = y_a.device
+        B, C, H, W = y_a.shape
+        # bn0 + relu -> packed h
+        p0 = _bn_params((B, C, H, W), None, (0, 0), True, False, tr0, eps0, mom0)
+        packed_h = torch.empty(int(lib.cpc_bn_packed_bytes(ctypes.byref(p0))), dtype=torch.uint8, device=dev)
+        mean0 = torch.empty(C, dtype=torch.float32, device=dev)
+        rstd0 = torch.empty(C, dtype=torch.float32, device=dev)
+        ws = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p0)), dev)
+        pc = _conv_params((B, C, H, W), tuple(w.shape), (1, 1), top, 0, out_hw, False, precision)
+        co = w.shape[0]
+        y_b = torch.empty((B, co, out_hw[0], out_hw[1]), dtype=torch.float32, device=dev)
+        p1 = _bn_params(tuple(y_b.shape), None if residual is None else tuple(residual.shape), res_off, True, outer_relu,
+                        tr1, eps1, mom1)
+        out = torch.empty_like(y_b)
+        mean1 = torch.empty(co, dtype=torch.float32, device=dev)
+        rstd1 = torch.empty(co, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _call(_bn_key("cpc_bn_relu_fwd", p0) + " ->packed", 0.0, lib.cpc_bn_relu_fwd_packed, _ptr(y_a), _ptr(g0), _ptr(b0),
+                  _ptr(rm0), _ptr(rv0), _ptr(None), _ptr(packed_h), _ptr(mean0), _ptr(rstd0), ctypes.byref(p0), _ptr(ws),
+                  ws.numel(), _stream(), nbytes=4.0 * y_a.numel() * (2 if tr0 else 1) + float(packed_h.numel()))
+            wsc = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(pc), 0), dev)
+            _call(_conv_key("cpc_conv_fwd", pc), _conv_flops(pc), lib.cpc_conv_fwd_ex, _ptr(None), _ptr(w),
+                  _ptr(bias.contiguous() if bias is not None else None), _ptr(y_b), ctypes.byref(pc), _ptr(packed_h),
+                  _ptr(wsc), wsc.numel() if wsc is not None else 0, _stream())
+            ws1 = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p1)), dev)
+            n1 = y_b.numel()
+            _call(_bn_key("cpc_bn_relu_fwd", p1), 0.0, lib.cpc_bn_relu_fwd, _ptr(y_b), _ptr(g1), _ptr(b1), _ptr(rm1),
+                  _ptr(rv1), _ptr(residual), _ptr(out), _ptr(mean1), _ptr(rstd1), ctypes.byref(p1), _ptr(ws1), ws1.numel(),
+                  _stream(), nbytes=4.0 * n1 * ((3 if tr1 else 2) + (1 if residual is not None else 0)))
+        ctx.cfg = cfg
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(y_a, g0, b0, mean0, rstd0, packed_h, w, y_b, g1, b1, mean1, rstd1, residual)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        y_a, g0, b0, mean0, rstd0, packed_h, w, y_b, g1, b1, mean1, rstd1, residual = ctx.saved_tensors
+        (top, out_hw, res_off, outer_relu, tr0, eps0, mom0, tr1, eps1, mom1, precision) = ctx.cfg
+        lib = _lib.load()
+        dev = dout.device
+        dout = dout.contiguous()
+        B, C, H, W = y_a.shape
+        co = w.shape[0]
+        p1 = _bn_params(tuple(y_b.shape), None if residual is None else tuple(residual.shape), res_off, True, outer_relu,
+                        tr1, eps1, mom1)
+        pc = _conv_params((B, C, H, W), tuple(w.shape), (1, 1), top, 0, out_hw, False, precision)
+        p0 = _bn_params((B, C, H, W), None, (0, 0), True, False, tr0, eps0, mom0)
+        packed_dy = torch.empty(int(lib.cpc_bn_packed_bytes(ctypes.byref(p1))), dtype=torch.uint8, device=dev)
+        db = torch.empty(co, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        dg1 = torch.empty_like(g1) if g1 is not None else None
+        dbt1 = torch.empty_like(b1) if b1 is not None else None
+        d_res = torch.empty_like(residual) if (residual is not None and ctx.needs_input_grad[11]) else None
+        dh = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        dw = torch.empty_like(w)
+        dy_a = torch.empty_like(y_a)
+        dg0 = torch.empty_like(g0) if g0 is not None else None
+        dbt0 = torch.empty_like(b0) if b0 is not None else None
+        with torch.cuda.device(dev):
+            ws1 = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p1)), dev)
+            n1 = y_b.numel()
+            _call(_bn_key("cpc_bn_relu_bwd", p1) + " ->packed", 0.0, lib.cpc_bn_relu_bwd_packed, _ptr(dout), _ptr(y_b), _ptr(g1),
+                  _ptr(b1), _ptr(mean1), _ptr(rstd1), _ptr(residual), _ptr(packed_dy), _ptr(db), _ptr(dg1), _ptr(dbt1),
+                  _ptr(d_res), ctypes.byref(p1), _ptr(ws1), ws1.numel(), _stream(),
+                  nbytes=4.0 * n1 * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0)))
+            wsd = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(pc), 1), dev)
+            _call(_conv_key("cpc_conv_dgrad", pc), _conv_flops(pc), lib.cpc_conv_dgrad_ex, _ptr(None), _ptr(w), _ptr(dh),
+                  ctypes.byref(pc), _ptr(packed_dy), _ptr(wsd), wsd.numel() if wsd is not None else 0, _stream())
+            wsw = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(pc), 2), dev)
+            _call(_conv_key("cpc_conv_wgrad", pc), _conv_flops(pc), lib.cpc_conv_wgrad_ex, _ptr(None), _ptr(None), _ptr(dw),
+                  _ptr(None), ctypes.byref(pc), _ptr(packed_h), _ptr(packed_dy), _ptr(wsw),
+                  wsw.numel() if wsw is not None else 0, _stream())
+            ws0 = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p0)), dev)
+            _call(_bn_key("cpc_bn_relu_bwd", p0), 0.0, lib.cpc_bn_relu_bwd, _ptr(dh), _ptr(y_a), _ptr(g0), _ptr(b0), _ptr(mean0),
+                  _ptr(rstd0), _ptr(None), _ptr(dy_a), _ptr(dg0), _ptr(dbt0), _ptr(None), ctypes.byref(p0), _ptr(ws0),
+                  ws0.numel(), _stream(), nbytes=4.0 * y_a.numel() * 5)
+        return dy_a, dg0, dbt0, None, None, dw, db, dg1, dbt1, None, None, d_res, None
+
+
+def block_tail_eligible(y_a, bn0, conv, top, bn1):
+    """True when ``relu(bn0(y_a)) -> conv -> bn1`` can run as one node with packed intermediates: kh x 1 stride-1 conv
+    without horizontal padding on the row-streaming kernels (forward, data and weight gradient), fp32-faithful mode,
+    affine batch norms, first-order autograd."""
+    import os
+    if os.environ.get("CPC_NO_BLOCK_TAIL") == "1" or _second_order or _default_precision != "fp32":
+        return False
+    if not (y_a.is_cuda and y_a.dtype == torch.float32 and y_a.dim() == 4 and y_a.shape[3] % 2 == 0):
+        return False                                             # the packed-output kernels own pairs of columns
+    w = conv.weight
+    if (tuple(conv.stride) != (1, 1) or w.shape[3] != 1 or conv.padding[1] != 0 or conv.groups != 1
+            or tuple(conv.dilation) != (1, 1) or w.shape[1] != y_a.shape[1]):
+        return False
+    for bn in (bn0, bn1):
+        if bn.weight is None or bn.bias is None:
+            return False
+    B, C, H, W = y_a.shape
+    oh = H + top + 2 * conv.padding[0] - w.shape[2] + 1
+    if oh <= 0:
+        return False
+    p = _conv_params((B, C, H, W), tuple(w.shape), (1, 1), top + conv.padding[0], 0, (oh, W), False, "fp32")
+    lib = _lib.load()
+    return all(lib.cpc_conv_kernel_family(ctypes.byref(p), which) in (2, 3) for which in (0, 1, 2))
+
+
+def block_tail(y_a, bn0, conv, top, bn1, residual=None, res_off=(0, 0), outer_relu=False):
+    """relu_if(outer_relu, relu(bn1(conv(pad_top(relu(bn0(y_a)))))) + crop(residual)); see _BlockTailFunction."""
+    tr0, mom0, rm0, rv0 = _bn_state(bn0)
+    tr1, mom1, rm1, rv1 = _bn_state(bn1)
+    w = conv.weight
+    pad_top = top + conv.padding[0]
+    oh = y_a.shape[2] + top + 2 * conv.padding[0] - w.shape[2] + 1
+    cfg = (pad_top, (oh, y_a.shape[3]), tuple(res_off), bool(outer_relu), tr0, bn0.eps, mom0, tr1, bn1.eps, mom1, "fp32")
+    return _BlockTailFunction.apply(y_a, bn0.weight, bn0.bias, rm0, rv0, w, conv.bias, bn1.weight, bn1.bias, rm1, rv1,
+                                    residual, cfg)
+
+
 # --------------------------------------------------------------------------------------------------
 # non-overlapping max pooling
 # --------------------------------------------------------------------------------------------------

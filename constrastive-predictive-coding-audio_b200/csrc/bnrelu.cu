@@ -9,6 +9,7 @@
 // All kernels are HBM-bound streaming passes over NCHW planes: forward = statistics pass (1 read) + apply
 // pass (1-2 reads, 1 write); backward = reduction pass (2-3 reads) + gradient pass (2-3 reads, 1-2 writes).
 // Masks are recomputed from x (and the residual), so nothing but x, mean and rstd is saved for backward.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace cpc {
@@ -271,6 +272,139 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     }
 }
 
+// ---- packed-output variants ---------------------------------------------------------------------------------------
+// bf16 hi / lo planes of a conv operand ([plane][B*C*H rows][Wp], Wp = W rounded up to 8, pad columns zero).  Used when
+// the only consumer of an activation / gradient is a tensor-core conv: the producer writes the operand form directly
+// and the fp32 tensor plus its packing pass disappear.  W must be even: a thread owns PAIRS of horizontally adjacent
+// elements (8-byte loads, 4-byte bf16x2 stores; 2-byte stores ran the kernel 25 % slower than the fp32 version).
+struct PackedOut {
+    __nv_bfloat16* base;
+    long plane_stride;       // elements between the hi and the lo plane
+    int Wp;
+};
+constexpr int BN_PAIRS = BN_PER_THREAD / 2;
+constexpr int BN_PAIR_SEG = BN_THREADS * BN_PAIRS;               // pairs per block
+
+__device__ __forceinline__ void packed_store2(const PackedOut& po, const BnGeom& g, int plane, int h, int w, float a, float b) {
+    __nv_bfloat16* q = po.base + ((long)plane * g.H + h) * po.Wp + w;
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a - __low2float(hi), b - __high2float(hi));
+    *reinterpret_cast<__nv_bfloat162*>(q) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(q + po.plane_stride) = lo;
+    if (w + 2 == g.W) {                                          // last pair of the row: zero the pad columns
+        const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+        for (int k = 2; k < po.Wp - w; k += 2) {
+            *reinterpret_cast<__nv_bfloat162*>(q + k) = z;
+            *reinterpret_cast<__nv_bfloat162*>(q + po.plane_stride + k) = z;
+        }
+    }
+}
+
+// grid (B*C planes, pair segments); no residual
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_packed_kernel(const float* __restrict__ x, const float* __restrict__ affine,
+                                                                    PackedOut pk, BnGeom g, FastDiv d_w2) {
+    const int plane = blockIdx.x;
+    const int c = plane % g.C;
+    const float sc = __ldg(affine + 2 * c), sh = __ldg(affine + 2 * c + 1);
+    const float2* px = reinterpret_cast<const float2*>(x + (size_t)plane * g.HW);
+    const int n_pairs = g.HW >> 1;
+    const int j0 = blockIdx.y * BN_PAIR_SEG + threadIdx.x;
+    float2 xv[BN_PAIRS];
+#pragma unroll
+    for (int u = 0; u < BN_PAIRS; ++u) {
+        const int j = j0 + u * BN_THREADS;
+        xv[u] = j < n_pairs ? __ldg(px + j) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < BN_PAIRS; ++u) {
+        const int j = j0 + u * BN_THREADS;
+        if (j < n_pairs) {
+            float a = fmaf(xv[u].x, sc, sh), b = fmaf(xv[u].y, sc, sh);
+            if (g.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            int h, wp;
+            d_w2.divmod(j, h, wp);
+            packed_store2(pk, g, plane, h, 2 * wp, a, b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
+    const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ save_mean, const float* __restrict__ save_rstd, const float* __restrict__ res,
+    const double* __restrict__ sums2, PackedOut pk, float* __restrict__ dx_sum, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, float* __restrict__ d_res, BnGeom g, FastDiv d_w2, double count, int training) {
+    const int plane = blockIdx.x;
+    const int c = plane % g.C;
+    const float mean = __ldg(save_mean + c), rstd = __ldg(save_rstd + c);
+    const float gam = gamma ? __ldg(gamma + c) : 1.f, bet = beta ? __ldg(beta + c) : 0.f;
+    const double sg = sums2[2 * c], sgx = sums2[2 * c + 1];
+    if (plane < g.C && blockIdx.y == 0 && threadIdx.x == 0) {
+        if (dbeta) dbeta[c] = (float)sg;
+        if (dgamma) dgamma[c] = (float)sgx;
+    }
+    const float m1 = training ? (float)(sg / count) : 0.f;
+    const float m2 = training ? (float)(sgx / count) : 0.f;
+    const float k = gam * rstd;
+    const float2* px = reinterpret_cast<const float2*>(x + (size_t)plane * g.HW);
+    const float2* pd = reinterpret_cast<const float2*>(dout + (size_t)plane * g.HW);
+    const size_t roff = (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row;
+    const float* pr = res ? res + roff : nullptr;
+    float* pdr = d_res ? d_res + roff : nullptr;
+    const int n_pairs = g.HW >> 1;
+    const int j0 = blockIdx.y * BN_PAIR_SEG + threadIdx.x;
+    float2 xv[BN_PAIRS], dv[BN_PAIRS], rv[BN_PAIRS];
+    int hh[BN_PAIRS], ww[BN_PAIRS];
+    const bool need_res = pr != nullptr && g.outer_relu;
+#pragma unroll
+    for (int u = 0; u < BN_PAIRS; ++u) {
+        const int j = j0 + u * BN_THREADS;
+        const bool in = j < n_pairs;
+        xv[u] = in ? __ldg(px + j) : make_float2(0.f, 0.f);
+        dv[u] = in ? __ldg(pd + j) : make_float2(0.f, 0.f);
+        rv[u] = make_float2(0.f, 0.f);
+        hh[u] = 0; ww[u] = 0;
+        if (in) {
+            int wp;
+            d_w2.divmod(j, hh[u], wp);
+            ww[u] = 2 * wp;
+            if (need_res) {
+                const float* q = pr + (size_t)hh[u] * g.RW + ww[u];
+                rv[u] = make_float2(__ldg(q), __ldg(q + 1));
+            }
+        }
+    }
+    float total = 0.f;
+#pragma unroll
+    for (int u = 0; u < BN_PAIRS; ++u) {
+        const int j = j0 + u * BN_THREADS;
+        if (j < n_pairs) {
+            float xh0, xh1, g10, g11;
+            const float g20 = bn_grad_in(dv[u].x, xv[u].x, mean, rstd, gam, bet, pr != nullptr, rv[u].x, g, xh0, g10);
+            const float g21 = bn_grad_in(dv[u].y, xv[u].y, mean, rstd, gam, bet, pr != nullptr, rv[u].y, g, xh1, g11);
+            const float d0 = k * (g20 - m1 - xh0 * m2), d1 = k * (g21 - m1 - xh1 * m2);
+            packed_store2(pk, g, plane, hh[u], ww[u], d0, d1);
+            total += d0 + d1;
+            if (pdr) {
+                float* q = pdr + (size_t)hh[u] * g.RW + ww[u];
+                q[0] = g10; q[1] = g11;
+            }
+        }
+    }
+    if (dx_sum) {
+        // bias gradient of the conv in front of this batch norm = per-channel sum of dx (analytically zero in training
+        // mode: what the reference accumulates there is rounding noise, and so is this)
+        __shared__ float red[BN_THREADS / 32];
+        total = warp_sum(total);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = total;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = threadIdx.x < BN_THREADS / 32 ? red[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) atomicAdd(dx_sum + c, v);
+        }
+    }
+}
+
 }  // namespace cpc
 
 using namespace cpc;
@@ -281,14 +415,17 @@ extern "C" size_t cpc_bn_relu_workspace_bytes(const cpc_bn_params* p) {
     return align_up(sizeof(double) * 2 * (size_t)p->channels, 256) + align_up(sizeof(float) * 2 * (size_t)p->channels, 256);
 }
 
-extern "C" int cpc_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
-                               float* running_var, const float* residual, float* out, float* save_mean, float* save_rstd,
-                               const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       const float* residual, float* out, void* packed_out, float* save_mean, float* save_rstd,
+                       const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream) {
     int st = bn_validate(p);
     if (st != CPC_OK) return st;
-    if (!x || !out || !save_mean || !save_rstd) return CPC_ERR_NULL;
+    if (!x || (!out && !packed_out) || !save_mean || !save_rstd) return CPC_ERR_NULL;
     if (!p->training && (!running_mean || !running_var)) return CPC_ERR_NULL;
     if ((p->res_height > 0) != (residual != nullptr)) return CPC_ERR_NULL;
+    if (packed_out && (p->width % 2 != 0 || residual)) return CPC_ERR_UNSUPPORTED;
+    if (packed_out && ((reinterpret_cast<uintptr_t>(packed_out) & 15) != 0 || (reinterpret_cast<uintptr_t>(x) & 7) != 0))
+        return CPC_ERR_ALIGNMENT;
     const size_t need = cpc_bn_relu_workspace_bytes(p);
     if (!workspace || workspace_bytes < need) return CPC_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 7) != 0) return CPC_ERR_ALIGNMENT;
@@ -308,21 +445,55 @@ extern "C" int cpc_bn_relu_fwd(const float* x, const float* gamma, const float* 
     bn_finalize_kernel<<<ceil_div(g.C, 128), 128, 0, s>>>(sums, gamma, beta, running_mean, running_var, save_mean, save_rstd,
                                                          affine, g.C, (double)g.B * g.HW, p->eps, p->momentum, p->training);
     CPC_LAUNCH_CHECK();
-    bn_apply_kernel<<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, g);
+    if (packed_out) {
+        const int Wp = (g.W + 7) & ~7;
+        PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_out), (long)g.B * g.C * g.H * Wp, Wp};
+        const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, BN_PAIR_SEG));
+        bn_apply_packed_kernel<<<pgrid, BN_THREADS, 0, s>>>(x, affine, pk, g, FastDiv(g.W / 2));
+    } else {
+        bn_apply_kernel<<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, g);
+    }
     CPC_LAUNCH_CHECK();
     count_launch(launches);
     return CPC_OK;
 }
 
-extern "C" int cpc_bn_relu_bwd(const float* dout, const float* x, const float* gamma, const float* beta,
-                               const float* save_mean, const float* save_rstd, const float* residual, float* dx,
-                               float* dgamma, float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+extern "C" int cpc_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, const float* residual, float* out, float* save_mean, float* save_rstd,
+                               const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!out) return CPC_ERR_NULL;
+    return bn_fwd_impl(x, gamma, beta, running_mean, running_var, residual, out, nullptr, save_mean, save_rstd, p, workspace,
+                       workspace_bytes, stream);
+}
+
+extern "C" int cpc_bn_relu_fwd_packed(const float* x, const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, const float* residual, void* packed_out, float* save_mean,
+                                      float* save_rstd, const cpc_bn_params* p, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    if (!packed_out) return CPC_ERR_NULL;
+    return bn_fwd_impl(x, gamma, beta, running_mean, running_var, residual, nullptr, packed_out, save_mean, save_rstd, p,
+                       workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t cpc_bn_packed_bytes(const cpc_bn_params* p) {
+    if (bn_validate(p) != CPC_OK) return 0;
+    const size_t Wp = (size_t)((p->width + 7) & ~7);
+    return 2 * (size_t)p->batch * p->channels * p->height * Wp * sizeof(__nv_bfloat16);
+}
+
+static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, const float* beta, const float* save_mean,
+                       const float* save_rstd, const float* residual, float* dx, void* packed_dx, float* dx_sum,
+                       float* dgamma, float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace,
+                       size_t workspace_bytes, void* stream) {
     int st = bn_validate(p);
     if (st != CPC_OK) return st;
-    if (!dout || !x || !save_mean || !save_rstd || !dx) return CPC_ERR_NULL;
+    if (!dout || !x || !save_mean || !save_rstd || (!dx && !packed_dx)) return CPC_ERR_NULL;
     if ((p->res_height > 0) != (residual != nullptr)) return CPC_ERR_NULL;
     if (d_residual && !residual) return CPC_ERR_NULL;
+    if (packed_dx && p->width % 2 != 0) return CPC_ERR_UNSUPPORTED;
+    if (packed_dx && ((reinterpret_cast<uintptr_t>(packed_dx) & 15) != 0 ||
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dout)) & 7) != 0))
+        return CPC_ERR_ALIGNMENT;
     const size_t need = cpc_bn_relu_workspace_bytes(p);
     if (!workspace || workspace_bytes < need) return CPC_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 7) != 0) return CPC_ERR_ALIGNMENT;
@@ -331,6 +502,7 @@ extern "C" int cpc_bn_relu_bwd(const float* dout, const float* x, const float* g
     BnGeom g = bn_geom(p);
     double* sums2 = reinterpret_cast<double*>(workspace);
     if (cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * (size_t)g.C, s) != cudaSuccess) return CPC_ERR_CUDA;
+    if (packed_dx && dx_sum && cudaMemsetAsync(dx_sum, 0, sizeof(float) * (size_t)g.C, s) != cudaSuccess) return CPC_ERR_CUDA;
     const bool crop = g.RH != g.H || g.RW != g.W;
     if (d_residual && crop &&
         cudaMemsetAsync(d_residual, 0, sizeof(float) * (size_t)g.B * g.C * g.RH * g.RW, s) != cudaSuccess)
@@ -338,9 +510,36 @@ extern "C" int cpc_bn_relu_bwd(const float* dout, const float* x, const float* g
     const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
     bn_bwd_reduce_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g);
     CPC_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx, dgamma,
-                                                   dbeta, d_residual, g, (double)g.B * g.HW, p->training);
+    if (packed_dx) {
+        const int Wp = (g.W + 7) & ~7;
+        PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_dx), (long)g.B * g.C * g.H * Wp, Wp};
+        const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, BN_PAIR_SEG));
+        bn_bwd_apply_packed_kernel<<<pgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, pk,
+                                                               dx_sum, dgamma, dbeta, d_residual, g, FastDiv(g.W / 2),
+                                                               (double)g.B * g.HW, p->training);
+    } else {
+        bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx, dgamma,
+                                                       dbeta, d_residual, g, (double)g.B * g.HW, p->training);
+    }
     CPC_LAUNCH_CHECK();
     count_launch(2);
     return CPC_OK;
+}
+
+extern "C" int cpc_bn_relu_bwd(const float* dout, const float* x, const float* gamma, const float* beta,
+                               const float* save_mean, const float* save_rstd, const float* residual, float* dx,
+                               float* dgamma, float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!dx) return CPC_ERR_NULL;
+    return bn_bwd_impl(dout, x, gamma, beta, save_mean, save_rstd, residual, dx, nullptr, nullptr, dgamma, dbeta, d_residual,
+                       p, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cpc_bn_relu_bwd_packed(const float* dout, const float* x, const float* gamma, const float* beta,
+                                      const float* save_mean, const float* save_rstd, const float* residual,
+                                      void* packed_dx, float* dx_sum, float* dgamma, float* dbeta, float* d_residual,
+                                      const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!packed_dx) return CPC_ERR_NULL;
+    return bn_bwd_impl(dout, x, gamma, beta, save_mean, save_rstd, residual, nullptr, packed_dx, dx_sum, dgamma, dbeta,
+                       d_residual, p, workspace, workspace_bytes, stream);
 }

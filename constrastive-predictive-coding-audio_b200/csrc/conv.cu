@@ -372,7 +372,13 @@ extern "C" int cpc_conv_fwd_ex(const float* x, const float* w, const float* bias
                                const void* packed_x, void* workspace, size_t workspace_bytes, void* stream) {
     int st = validate(p);
     if (st != CPC_OK) return st;
-    if (!x || !w || !y) return CPC_ERR_NULL;
+    {
+        // the fp32 operand may be omitted when its packed form is given and the row-streaming kernels (which read only
+        // the packed form) serve this configuration
+        const int fam = conv_family(p, 0);
+        const bool packed_only = !x && packed_x && (fam == 2 || fam == 3);
+        if ((!x && !packed_only) || !w || !y) return CPC_ERR_NULL;
+    }
     if ((st = check_device()) != CPC_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     switch (conv_family(p, 0)) {
@@ -397,7 +403,11 @@ extern "C" int cpc_conv_dgrad_ex(const float* dy, const float* w, float* dx, con
                                  void* workspace, size_t workspace_bytes, void* stream) {
     int st = validate(p);
     if (st != CPC_OK) return st;
-    if (!dy || !w || !dx) return CPC_ERR_NULL;
+    {
+        const int fam = conv_family(p, 1);
+        const bool packed_only = !dy && packed_dy && (fam == 2 || fam == 3);
+        if ((!dy && !packed_only) || !w || !dx) return CPC_ERR_NULL;
+    }
     if ((st = check_device()) != CPC_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     switch (conv_family(p, 1)) {
@@ -431,11 +441,14 @@ extern "C" int cpc_conv_wgrad_ex(const float* x, const float* dy, float* dw, flo
                                  void* stream) {
     int st = validate(p);
     if (st != CPC_OK) return st;
-    if (!x || !dy || !dw) return CPC_ERR_NULL;
+    const int fam = conv_family(p, 2);
+    {
+        const bool tall = fam == 2 || fam == 3;
+        if ((!x && !(packed_x && tall)) || (!dy && !(packed_dy && tall && !dbias)) || !dw) return CPC_ERR_NULL;
+    }
     if ((st = check_device()) != CPC_OK) return st;
     ConvGeom g = make_geom(p);
     cudaStream_t s = (cudaStream_t)stream;
-    const int fam = conv_family(p, 2);
     if (fam != 0) {
         if (fam == 1) st = smallk_launch(2, x, nullptr, nullptr, dy, dw, p, s);
         else if (fam == 2) st = tall_wgrad_launch(x, dy, dw, p, packed_x, packed_dy, workspace, workspace_bytes, s);

@@ -179,6 +179,21 @@ int cpc_bn_relu_bwd(const float* dout, const float* x, const float* gamma, const
                     const float* save_rstd, const float* residual, float* dx, float* dgamma, float* dbeta,
                     float* d_residual, const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Packed-output variants: when the only consumer of the activation (forward) or of the gradient (backward) is a
+ * tensor-core conv that reads the bf16 hi/lo operand planes of cpc_conv_pack ([plane][B*C*H][round8(W)], fp32-faithful
+ * mode), the batch norm writes that form directly -- no fp32 tensor, no packing pass.  cpc_bn_packed_bytes gives the
+ * buffer size.  dx_sum (optional, C floats) receives the per-channel sum of dx = the bias gradient of the conv that
+ * feeds this batch norm.  The conv entry points accept a NULL fp32 operand when its packed form is supplied and
+ * cpc_conv_kernel_family is a row-streaming family (2, 3). */
+size_t cpc_bn_packed_bytes(const cpc_bn_params* p);
+int cpc_bn_relu_fwd_packed(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                           const float* residual, void* packed_out, float* save_mean, float* save_rstd,
+                           const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream);
+int cpc_bn_relu_bwd_packed(const float* dout, const float* x, const float* gamma, const float* beta, const float* save_mean,
+                           const float* save_rstd, const float* residual, void* packed_dx, float* dx_sum, float* dgamma,
+                           float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 2c. Non-overlapping max pooling (kernel = stride, no padding), forward and backward.
  *    Replaces nn.MaxPool2d on the residual branch (scalogram_model.py:434-441, ceil_mode=True) and the main-path

@@ -835,6 +835,58 @@ def test_experiment_configs_train_one_step(cpc, name):
 
 
 # ---------------------------------------------------------------------------------------------------
+# block tail: bn + relu + tall conv + bn (+ residual) + relu as one autograd node with packed intermediates
+# ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cfg", [
+    # in, hidden/out channels, conv_b kernel, top padding, residual, input (H, W), outer relu
+    dict(cin=32, cout=32, k2=(9, 1), top=8, residual=True, hw=(41, 77), outer=True),      # 32-channel row-streaming kernels
+    dict(cin=32, cout=32, k2=(16, 1), top=None, residual=False, hw=(70, 141), outer=False),
+    dict(cin=16, cout=128, k2=(6, 1), top=None, residual=True, hw=(30, 41), outer=True),  # 128-channel kernels
+    dict(cin=32, cout=128, k2=(4, 1), top=3, residual=True, hw=(21, 133), outer=False),
+    dict(cin=32, cout=32, k2=(9, 1), top=8, residual=True, hw=(41, 75), outer=True, node=False),   # odd width: unfused chain
+])
+def test_block_tail_node_matches_literal_modules(cpc, cfg):
+    """ScalogramEncoderBlock whose second conv runs on the row-streaming kernels: the single block-tail node (packed
+    activations between bn_a and conv_b, packed dy between bn_b and conv_b) against the same block evaluated module by
+    module (torch BatchNorm / ReLU, conv Functions) -- output, running statistics and every gradient."""
+    import copy
+    block_cfg = {'in_channels': cfg['cin'], 'hidden_channels': None, 'out_channels': cfg['cout'], 'kernel_size_1': (3, 3),
+                 'kernel_size_2': cfg['k2'], 'top_padding_1': None, 'top_padding_2': cfg['top'], 'padding_1': 0,
+                 'padding_2': 0, 'stride_1': 2, 'stride_2': 1, 'pooling_1': 1, 'pooling_2': 1, 'bias': True,
+                 'separable': False, 'residual': cfg['residual'], 'batch_norm': True, 'ceil_pooling': False}
+    torch.manual_seed(12)
+    block = cpc.ScalogramEncoderBlock(dict(block_cfg), name='b', activation_register=None).to(DEV).train()
+    with torch.no_grad():
+        for m in block.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.5, 0.5)
+    ref_block = copy.deepcopy(block)
+    gen = torch.Generator().manual_seed(13)
+    x = torch.randn(3, cfg['cin'], *cfg['hw'], generator=gen).to(DEV)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y = block(x1, outer_relu=cfg['outer'])
+    # the node must actually have been used (and must step aside for shapes it does not cover)
+    assert type(y.grad_fn).__name__.startswith("_BlockTailFunction") == cfg.get('node', True), type(y.grad_fn).__name__
+    with cpc.ops.second_order():                                   # literal module sequence
+        y_ref = ref_block(x2, outer_relu=cfg['outer'])
+    assert rel_err(y, y_ref) < 1e-4
+    gy = torch.randn(y.shape, generator=gen).to(DEV)
+    (y * gy).sum().backward()
+    (y_ref * gy).sum().backward()
+    assert rel_err(x1.grad, x2.grad) < TOL
+    noise_only = bn_shadowed_biases(block.state_dict().keys())
+    for (n, p), (_, q) in zip(block.named_parameters(), ref_block.named_parameters()):
+        if n in noise_only:
+            assert float((p.grad - q.grad).abs().max()) < 1e-3 * float(gy.abs().sum()) ** 0.5, n   # both are rounding noise
+        else:
+            assert grad_err(p.grad, q.grad) < TOL, n
+    for (n, b), (_, c) in zip(block.named_buffers(), ref_block.named_buffers()):
+        assert rel_err(b.float(), c.float()) < 1e-4, n
+
+
+# ---------------------------------------------------------------------------------------------------
 # gradients through the front end, InverseCQT (SURVEY 8(f) row 3)
 # ---------------------------------------------------------------------------------------------------
 

@@ -64,19 +64,30 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return r;
 }
 
-// grid (B*C planes, segments of one plane).  sums[c*2 + {0,1}] += sum x, sum x^2 (double).
+// Reduction kernels: a block walks BN_RED_SEGS consecutive segments of its plane with register accumulators and pays
+// the block reduction + 2 double atomics once (with one segment per block that tail was ~25 % of a block's life and the
+// ragged last segment of a 9828-element plane cost as much as a full one: 3.2 TB/s).
+constexpr int BN_RED_SEGS = 4;
+
+// grid (B*C planes, segment groups of one plane).  sums[c*2 + {0,1}] += sum x, sum x^2 (double).
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
                                                              int C, int HW) {
     __shared__ double red[BN_THREADS / 32];
     const int plane = blockIdx.x;
     const int c = plane % C;
     const float* px = x + (size_t)plane * HW;
-    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
     float s = 0.f, q = 0.f;
+    for (int seg = 0; seg < BN_RED_SEGS; ++seg) {
+        const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * BN_SEG + threadIdx.x;
+        if (i0 - (int)threadIdx.x >= HW) break;
+        float v[BN_PER_THREAD];
 #pragma unroll
-    for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * BN_THREADS;
-        if (i < HW) { const float v = __ldg(px + i); s += v; q = fmaf(v, v, q); }
+        for (int u = 0; u < BN_PER_THREAD; ++u) {
+            const int i = i0 + u * BN_THREADS;
+            v[u] = i < HW ? __ldg(px + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < BN_PER_THREAD; ++u) { s += v[u]; q = fmaf(v[u], v[u], q); }
     }
     const double bs = block_sum_d((double)s, red);
     const double bq = block_sum_d((double)q, red);
@@ -178,31 +189,34 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     const float* px = x + (size_t)plane * g.HW;
     const float* pd = dout + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
-    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
-    float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[BN_PER_THREAD];
     const bool need_res = pr != nullptr && g.outer_relu;
-#pragma unroll
-    for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * BN_THREADS;
-        const bool in = i < g.HW;
-        xv[u] = in ? __ldg(px + i) : 0.f;
-        dv[u] = in ? __ldg(pd + i) : 0.f;
-        rv[u] = 0.f;
-        if (need_res && in) {
-            int h, w;
-            g.d_w.divmod(i, h, w);
-            rv[u] = __ldg(pr + (size_t)h * g.RW + w);
-        }
-    }
     float s = 0.f, q = 0.f;
+    for (int seg = 0; seg < BN_RED_SEGS; ++seg) {
+        const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * BN_SEG + threadIdx.x;
+        if (i0 - (int)threadIdx.x >= g.HW) break;
+        float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[BN_PER_THREAD];
 #pragma unroll
-    for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * BN_THREADS;
-        if (i < g.HW) {
-            float xhat, g1;
-            const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, rv[u], g, xhat, g1);
-            s += g2;
-            q = fmaf(g2, xhat, q);
+        for (int u = 0; u < BN_PER_THREAD; ++u) {
+            const int i = i0 + u * BN_THREADS;
+            const bool in = i < g.HW;
+            xv[u] = in ? __ldg(px + i) : 0.f;
+            dv[u] = in ? __ldg(pd + i) : 0.f;
+            rv[u] = 0.f;
+            if (need_res && in) {
+                int h, w;
+                g.d_w.divmod(i, h, w);
+                rv[u] = __ldg(pr + (size_t)h * g.RW + w);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BN_PER_THREAD; ++u) {
+            const int i = i0 + u * BN_THREADS;
+            if (i < g.HW) {
+                float xhat, g1;
+                const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, rv[u], g, xhat, g1);
+                s += g2;
+                q = fmaf(g2, xhat, q);
+            }
         }
     }
     const double bs = block_sum_d((double)s, red);
@@ -438,7 +452,8 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
     int launches = 2;
     if (p->training) {
         if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)g.C, s) != cudaSuccess) return CPC_ERR_CUDA;
-        bn_stats_kernel<<<grid, BN_THREADS, 0, s>>>(x, sums, g.C, g.HW);
+        const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
+        bn_stats_kernel<<<rgrid, BN_THREADS, 0, s>>>(x, sums, g.C, g.HW);
         CPC_LAUNCH_CHECK();
         ++launches;
     }
@@ -508,7 +523,8 @@ static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, co
         cudaMemsetAsync(d_residual, 0, sizeof(float) * (size_t)g.B * g.C * g.RH * g.RW, s) != cudaSuccess)
         return CPC_ERR_CUDA;
     const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
-    bn_bwd_reduce_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g);
+    const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
+    bn_bwd_reduce_kernel<<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g);
     CPC_LAUNCH_CHECK();
     if (packed_dx) {
         const int Wp = (g.W + 7) & ~7;

@@ -286,6 +286,127 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     }
 }
 
+// ---- small planes -------------------------------------------------------------------------------------------------
+// With H*W well below one segment (the 2 x 77 and 16 x 77 planes of the deepest block) the plane-per-block kernels above
+// launch B*C nearly empty blocks that each pay a block reduction and two atomics: 0.2 ms for a 10 MB tensor.  Here a
+// block owns BN_SMALL_CHUNK consecutive elements of ONE CHANNEL across the batch (element e = item * HW + i).
+constexpr int BN_SMALL_CHUNK = BN_THREADS * 32;
+
+struct SmallLoc { bool in; size_t off; int i, plane; };
+__device__ __forceinline__ SmallLoc small_locate(const BnGeom& g, const FastDiv& d_hw, int c, int e, int n) {
+    SmallLoc l;
+    l.in = e < n;
+    int b = 0;
+    l.i = 0;
+    if (l.in) d_hw.divmod(e, b, l.i);
+    l.plane = b * g.C + c;
+    l.off = (size_t)l.plane * g.HW + l.i;
+    return l;
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_small_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
+                                                                   BnGeom g, FastDiv d_hw) {
+    __shared__ double red[BN_THREADS / 32];
+    const int c = blockIdx.x, n = g.B * g.HW;
+    float s = 0.f, q = 0.f;
+    const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+    for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
+        const SmallLoc l = small_locate(g, d_hw, c, e, n);
+        const float v = __ldg(x + l.off);
+        s += v; q = fmaf(v, v, q);
+    }
+    const double bs = block_sum_d((double)s, red);
+    const double bq = block_sum_d((double)q, red);
+    if (threadIdx.x == 0) { atomicAdd(sums + 2 * c, bs); atomicAdd(sums + 2 * c + 1, bq); }
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_small_apply_kernel(const float* __restrict__ x, const float* __restrict__ affine,
+                                                                   const float* __restrict__ res, float* __restrict__ out,
+                                                                   BnGeom g, FastDiv d_hw) {
+    const int c = blockIdx.x, n = g.B * g.HW;
+    const float sc = __ldg(affine + 2 * c), sh = __ldg(affine + 2 * c + 1);
+    const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+    for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
+        const SmallLoc l = small_locate(g, d_hw, c, e, n);
+        float v = fmaf(__ldg(x + l.off), sc, sh);
+        if (g.relu) v = fmaxf(v, 0.f);
+        if (res) {
+            int h, w;
+            g.d_w.divmod(l.i, h, w);
+            v += __ldg(res + (size_t)l.plane * g.RH * g.RW + (size_t)(g.roh + h) * g.RW + g.row + w);
+            if (g.outer_relu) v = fmaxf(v, 0.f);
+        }
+        out[l.off] = v;
+    }
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_small_bwd_reduce_kernel(
+    const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ save_mean, const float* __restrict__ save_rstd, const float* __restrict__ res,
+    double* __restrict__ sums2, BnGeom g, FastDiv d_hw) {
+    __shared__ double red[BN_THREADS / 32];
+    const int c = blockIdx.x, n = g.B * g.HW;
+    const float mean = __ldg(save_mean + c), rstd = __ldg(save_rstd + c);
+    const float gam = gamma ? __ldg(gamma + c) : 1.f, bet = beta ? __ldg(beta + c) : 0.f;
+    const bool need_res = res != nullptr && g.outer_relu;
+    float s = 0.f, q = 0.f;
+    const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+    for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
+        const SmallLoc l = small_locate(g, d_hw, c, e, n);
+        float rv = 0.f;
+        if (need_res) {
+            int h, w;
+            g.d_w.divmod(l.i, h, w);
+            rv = __ldg(res + (size_t)l.plane * g.RH * g.RW + (size_t)(g.roh + h) * g.RW + g.row + w);
+        }
+        float xhat, g1;
+        const float g2 = bn_grad_in(__ldg(dout + l.off), __ldg(x + l.off), mean, rstd, gam, bet, res != nullptr, rv, g, xhat, g1);
+        s += g2;
+        q = fmaf(g2, xhat, q);
+    }
+    const double bs = block_sum_d((double)s, red);
+    const double bq = block_sum_d((double)q, red);
+    if (threadIdx.x == 0) { atomicAdd(sums2 + 2 * c, bs); atomicAdd(sums2 + 2 * c + 1, bq); }
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_small_bwd_apply_kernel(
+    const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ save_mean, const float* __restrict__ save_rstd, const float* __restrict__ res,
+    const double* __restrict__ sums2, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    float* __restrict__ d_res, BnGeom g, FastDiv d_hw, double count, int training) {
+    const int c = blockIdx.x, n = g.B * g.HW;
+    const float mean = __ldg(save_mean + c), rstd = __ldg(save_rstd + c);
+    const float gam = gamma ? __ldg(gamma + c) : 1.f, bet = beta ? __ldg(beta + c) : 0.f;
+    const double sg = sums2[2 * c], sgx = sums2[2 * c + 1];
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
+        if (dbeta) dbeta[c] = (float)sg;
+        if (dgamma) dgamma[c] = (float)sgx;
+    }
+    const float m1 = training ? (float)(sg / count) : 0.f;
+    const float m2 = training ? (float)(sgx / count) : 0.f;
+    const float k = gam * rstd;
+    const bool need_res = res != nullptr && g.outer_relu;
+    const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+    for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
+        const SmallLoc l = small_locate(g, d_hw, c, e, n);
+        size_t ro = 0;
+        float rv = 0.f;
+        if (res || d_res) {
+            int h, w;
+            g.d_w.divmod(l.i, h, w);
+            ro = (size_t)l.plane * g.RH * g.RW + (size_t)(g.roh + h) * g.RW + g.row + w;
+            if (need_res) rv = __ldg(res + ro);
+        }
+        float xhat, g1;
+        const float g2 = bn_grad_in(__ldg(dout + l.off), __ldg(x + l.off), mean, rstd, gam, bet, res != nullptr, rv, g, xhat, g1);
+        dx[l.off] = k * (g2 - m1 - xhat * m2);
+        if (d_res) d_res[ro] = g1;
+    }
+}
+
+// planes below this many elements take the per-channel kernels
+constexpr int BN_SMALL_HW = 2048;
+
 // ---- packed-output variants ---------------------------------------------------------------------------------------
 // bf16 hi / lo planes of a conv operand ([plane][B*C*H rows][Wp], Wp = W rounded up to 8, pad columns zero).  Used when
 // the only consumer of an activation / gradient is a tensor-core conv: the producer writes the operand form directly
@@ -450,10 +571,16 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
     float* affine = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(sizeof(double) * 2 * (size_t)g.C, 256));
     const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
     int launches = 2;
+    const bool small = g.HW < BN_SMALL_HW && !packed_out && (int64_t)g.B * g.HW < 65535ll * BN_SMALL_CHUNK;
+    const dim3 sgrid(g.C, ceil_div(g.B * g.HW, BN_SMALL_CHUNK));
     if (p->training) {
         if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)g.C, s) != cudaSuccess) return CPC_ERR_CUDA;
-        const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
-        bn_stats_kernel<<<rgrid, BN_THREADS, 0, s>>>(x, sums, g.C, g.HW);
+        if (small) {
+            bn_small_stats_kernel<<<sgrid, BN_THREADS, 0, s>>>(x, sums, g, FastDiv(g.HW));
+        } else {
+            const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
+            bn_stats_kernel<<<rgrid, BN_THREADS, 0, s>>>(x, sums, g.C, g.HW);
+        }
         CPC_LAUNCH_CHECK();
         ++launches;
     }
@@ -465,6 +592,8 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
         PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_out), (long)g.B * g.C * g.H * Wp, Wp};
         const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, BN_PAIR_SEG));
         bn_apply_packed_kernel<<<pgrid, BN_THREADS, 0, s>>>(x, affine, pk, g, FastDiv(g.W / 2));
+    } else if (small) {
+        bn_small_apply_kernel<<<sgrid, BN_THREADS, 0, s>>>(x, affine, residual, out, g, FastDiv(g.HW));
     } else {
         bn_apply_kernel<<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, g);
     }
@@ -523,8 +652,15 @@ static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, co
         cudaMemsetAsync(d_residual, 0, sizeof(float) * (size_t)g.B * g.C * g.RH * g.RW, s) != cudaSuccess)
         return CPC_ERR_CUDA;
     const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
-    const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
-    bn_bwd_reduce_kernel<<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g);
+    const bool small = g.HW < BN_SMALL_HW && !packed_dx && (int64_t)g.B * g.HW < 65535ll * BN_SMALL_CHUNK;
+    const dim3 sgrid(g.C, ceil_div(g.B * g.HW, BN_SMALL_CHUNK));
+    if (small) {
+        bn_small_bwd_reduce_kernel<<<sgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g,
+                                                               FastDiv(g.HW));
+    } else {
+        const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
+        bn_bwd_reduce_kernel<<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g);
+    }
     CPC_LAUNCH_CHECK();
     if (packed_dx) {
         const int Wp = (g.W + 7) & ~7;
@@ -533,6 +669,10 @@ static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, co
         bn_bwd_apply_packed_kernel<<<pgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, pk,
                                                                dx_sum, dgamma, dbeta, d_residual, g, FastDiv(g.W / 2),
                                                                (double)g.B * g.HW, p->training);
+    } else if (small) {
+        bn_small_bwd_apply_kernel<<<sgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx,
+                                                              dgamma, dbeta, d_residual, g, FastDiv(g.HW), (double)g.B * g.HW,
+                                                              p->training);
     } else {
         bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx, dgamma,
                                                        dbeta, d_residual, g, (double)g.B * g.HW, p->training);

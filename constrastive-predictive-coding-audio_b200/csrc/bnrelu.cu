@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_small_stats_kernel(const float*
     const int c = blockIdx.x, n = g.B * g.HW;
     float s = 0.f, q = 0.f;
     const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+#pragma unroll 8
     for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
         const SmallLoc l = small_locate(g, d_hw, c, e, n);
         const float v = __ldg(x + l.off);
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_small_apply_kernel(const float*
     const int c = blockIdx.x, n = g.B * g.HW;
     const float sc = __ldg(affine + 2 * c), sh = __ldg(affine + 2 * c + 1);
     const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+#pragma unroll 8
     for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
         const SmallLoc l = small_locate(g, d_hw, c, e, n);
         float v = fmaf(__ldg(x + l.off), sc, sh);
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_small_bwd_reduce_kernel(
     const bool need_res = res != nullptr && g.outer_relu;
     float s = 0.f, q = 0.f;
     const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+#pragma unroll 8
     for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
         const SmallLoc l = small_locate(g, d_hw, c, e, n);
         float rv = 0.f;
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_small_bwd_apply_kernel(
     const float k = gam * rstd;
     const bool need_res = res != nullptr && g.outer_relu;
     const int e0 = blockIdx.y * BN_SMALL_CHUNK;
+#pragma unroll 8
     for (int e = e0 + threadIdx.x; e < min(n, e0 + BN_SMALL_CHUNK); e += BN_THREADS) {
         const SmallLoc l = small_locate(g, d_hw, c, e, n);
         size_t ro = 0;

@@ -1,3 +1,4 @@
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe tma_probe.cu -ldl ; run each case in its own process: ./tma_probe <case index>
 // Probe: where does TMA put a box whose inner extent is narrower than the swizzle span?
 // Tensor: bf16 [H=8][W=64], value = h*64 + w.  Box {bw, bh}; smem dumped as element indices (after un-swizzling
 // is NOT applied: raw smem order), so the placement rule can be read off directly.

@@ -20,7 +20,8 @@ int umma_conv_launch(const float* in, const float* w, const float* bias, float* 
 int pack_split_launch(const float* x, __nv_bfloat16* out, long rows, int W, int Wp, int planes, int nrep, int w_mul,
                       int rep_mul, int w_off, cudaStream_t s);
 int pack_split_sum_launch(const float* x, __nv_bfloat16* out, float* sums, long rows, int W, int Wp, int planes, int H, int C,
-                          cudaStream_t s);
+                          int nrep, cudaStream_t s);
+int umma_dy_replicas(const cpc_conv_params* p);                  // conv_umma.cu
 
 size_t umma_wgrad_workspace(const cpc_conv_params* p);
 bool umma_wgrad_eligible(const cpc_conv_params* p);
@@ -304,6 +305,9 @@ extern "C" int cpc_conv_kernel_family(const cpc_conv_params* p, int which) {
     return conv_family(p, which);
 }
 
+// replicas of the canonical caller-packed dy: 2 when the generic strided data gradient reads shifted copies
+static int dy_replicas(const cpc_conv_params* p) { return conv_family(p, 1) == 4 ? umma_dy_replicas(p) : 1; }
+
 extern "C" size_t cpc_conv_packed_bytes(const cpc_conv_params* p, int operand) {
     if (validate(p) != CPC_OK) return 0;
     const size_t planes = p->precision == 1 ? 1 : 2;
@@ -314,7 +318,9 @@ extern "C" size_t cpc_conv_packed_bytes(const cpc_conv_params* p, int operand) {
     }
     if (operand == 1) {
         if (conv_family(p, 2) < 2) return 0;
-        return align_up(planes * p->batch * p->c_out * p->h_out * Wp * 2, 1024);
+        const size_t nrep = dy_replicas(p);
+        const size_t Wd = (size_t)((p->w_out + (nrep == 2 ? 1 : 0) + 7) & ~7);
+        return align_up(planes * nrep * p->batch * p->c_out * p->h_out * Wd * 2, 1024);
     }
     return 0;
 }
@@ -332,9 +338,12 @@ extern "C" int cpc_conv_pack(const float* src, void* packed, const cpc_conv_para
     if (operand == 0)
         st = pack_split_launch(src, out, (long)p->batch * p->c_in * p->h_in, p->w_in, Wp, planes, p->kw, p->stride_w, 1,
                                -p->pad_left, (cudaStream_t)stream);
-    else
-        st = pack_split_launch(src, out, (long)p->batch * p->c_out * p->h_out, p->w_out, Wp, planes, 1, 1, 0, 0,
+    else {
+        const int nrep = dy_replicas(p);
+        const int Wd = (p->w_out + (nrep == 2 ? 1 : 0) + 7) & ~7;
+        st = pack_split_launch(src, out, (long)p->batch * p->c_out * p->h_out, p->w_out, Wd, planes, nrep, 1, -1, 0,
                                (cudaStream_t)stream);
+    }
     if (st == CPC_OK) count_launch();
     return st;
 }
@@ -348,9 +357,10 @@ extern "C" int cpc_conv_pack_dy(const float* dy, void* packed, float* dbias, con
     if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return CPC_ERR_ALIGNMENT;
     if ((st = check_device()) != CPC_OK) return st;
     const int planes = p->precision == 1 ? 1 : 2;
-    const int Wp = (p->w_out + 7) & ~7;
+    const int nrep = dy_replicas(p);
+    const int Wp = (p->w_out + (nrep == 2 ? 1 : 0) + 7) & ~7;
     st = pack_split_sum_launch(dy, reinterpret_cast<__nv_bfloat16*>(packed), dbias, (long)p->batch * p->c_out * p->h_out,
-                               p->w_out, Wp, planes, p->h_out, p->c_out, (cudaStream_t)stream);
+                               p->w_out, Wp, planes, p->h_out, p->c_out, nrep, (cudaStream_t)stream);
     if (st == CPC_OK) count_launch();
     return st;
 }

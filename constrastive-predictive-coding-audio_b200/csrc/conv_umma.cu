@@ -101,13 +101,14 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
 constexpr int PACK_BINS = 264;
 __global__ void __launch_bounds__(256) pack_split_sum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                             float* __restrict__ sums, long rows, int W, int Wp, int planes,
-                                                            FastDiv d_h, FastDiv d_groups, int C, int vec_ok) {
+                                                            FastDiv d_h, FastDiv d_groups, int C, int vec_ok, int nrep) {
     // bins[parity][plane - first plane of the block]: a block's 256 consecutive groups span a few consecutive rows, i.e.
     // one or two (item, channel) planes; lanes of one plane are a contiguous lane range, summed by a segmented warp scan
     __shared__ float bins[2][PACK_BINS];
     const int groups = Wp >> 3, lane = threadIdx.x & 31;
     const long total = rows * groups;
-    const long plane_stride = rows * (long)Wp;
+    const long rep_stride = rows * (long)Wp;                      // replica 1 (column w' = dy[w' - 1]) follows replica 0
+    const long plane_stride = nrep * rep_stride;
     for (int t = threadIdx.x; t < 2 * PACK_BINS; t += 256) (&bins[0][0])[t] = 0.f;
     __syncthreads();
     const long n_iter = (total + (long)gridDim.x * 256 - 1) / ((long)gridDim.x * 256);
@@ -146,6 +147,18 @@ __global__ void __launch_bounds__(256) pack_split_sum_kernel(const float* __rest
             const long o = (long)row * Wp + w0;
             *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
             if (planes == 2) *reinterpret_cast<uint4*>(out + plane_stride + o) = *reinterpret_cast<const uint4*>(lo);
+            if (nrep == 2) {
+                // the shifted replica of the same 8 columns: {dy[w0 - 1], v[0..6]}
+                const float vp = (w0 > 0 && w0 - 1 < W) ? __ldg(src + w0 - 1) : 0.f;
+                __align__(16) __nv_bfloat16 h1[8];
+                __align__(16) __nv_bfloat16 l1[8];
+                h1[0] = __float2bfloat16_rn(vp);
+                l1[0] = __float2bfloat16_rn(vp - __bfloat162float(h1[0]));
+#pragma unroll
+                for (int i = 1; i < 8; ++i) { h1[i] = hi[i - 1]; l1[i] = lo[i - 1]; }
+                *reinterpret_cast<uint4*>(out + rep_stride + o) = *reinterpret_cast<const uint4*>(h1);
+                if (planes == 2) *reinterpret_cast<uint4*>(out + plane_stride + rep_stride + o) = *reinterpret_cast<const uint4*>(l1);
+            }
         }
         // segmented inclusive scan over lanes with equal plane (planes are non-decreasing across lanes)
 #pragma unroll
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(256) pack_split_sum_kernel(const float* __rest
 }
 
 int pack_split_sum_launch(const float* x, __nv_bfloat16* out, float* sums, long rows, int W, int Wp, int planes, int H, int C,
-                          cudaStream_t s) {
+                          int nrep, cudaStream_t s) {
     if (cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)C, s) != cudaSuccess) return CPC_ERR_CUDA;
     const long groups = rows * (Wp / 8);
     int blocks = (int)((groups + 255) / 256);
@@ -176,7 +189,7 @@ int pack_split_sum_launch(const float* x, __nv_bfloat16* out, float* sums, long 
     if (blocks < 1) blocks = 1;
     const int vec_ok = (W % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0);
     if (groups >= (1l << 31)) return CPC_ERR_BAD_SHAPE;
-    pack_split_sum_kernel<<<blocks, 256, 0, s>>>(x, out, sums, rows, W, Wp, planes, FastDiv(H), FastDiv(Wp / 8), C, vec_ok);
+    pack_split_sum_kernel<<<blocks, 256, 0, s>>>(x, out, sums, rows, W, Wp, planes, FastDiv(H), FastDiv(Wp / 8), C, vec_ok, nrep);
     return cudaGetLastError() == cudaSuccess ? CPC_OK : CPC_ERR_CUDA;
 }
 
@@ -702,6 +715,19 @@ static bool fused_dgrad_problem(const float* dy, const cpc_conv_params* p, ConvP
     return plan_problem(c, p->batch, p->precision).ok;
 }
 
+// Canonical caller-packed dy (cpc_conv_pack operand 1): one plain replica, or -- when the data gradient of this strided
+// conv reads dy through two column-shifted replicas (w' -> dy[w' - r]) -- both of them, [plane][2][rows][round8(w_out+1)],
+// so that ONE packing pass serves the weight gradient (replica 0) and every data-gradient class.
+int umma_dy_replicas(const cpc_conv_params* p) {
+    if (p->stride_h == 1 && p->stride_w == 1) return 1;
+    if (!umma_conv_eligible(p, 1)) return 1;
+    ConvProblem f;
+    if (fused_dgrad_problem(nullptr, p, f)) return 2;
+    const DgradShare d = dgrad_share(p);
+    return (d.common && d.n_classes > 1 && d.max_tw == 2 && d.w_off == 0) ? 2 : 1;
+}
+static int dy_packed_wp(const cpc_conv_params* p, int nrep) { return (p->w_out + (nrep == 2 ? 1 : 0) + 7) & ~7; }
+
 size_t umma_conv_workspace(const cpc_conv_params* p, int which) {
     if (!umma_conv_eligible(p, which)) return 0;
     size_t need = 0;
@@ -734,9 +760,13 @@ int umma_conv_launch(const float* in, const float* w, const float* bias, float* 
         if (prep) { c.pre = prep; c.pre_Wp = (p->w_out + 7) & ~7; c.pre_nrep = p->kw; }
         return run_problem(c, w, bias, out, p, p->relu, workspace, workspace_bytes, s);
     }
+    const int pre_rep = prep ? umma_dy_replicas(p) : 1;          // layout of the caller-packed dy
     {
         ConvProblem f;
-        if (fused_dgrad_problem(in, p, f)) return run_problem(f, w, nullptr, out, p, 0, workspace, workspace_bytes, s);
+        if (fused_dgrad_problem(in, p, f)) {
+            if (prep && pre_rep == 2) { f.pre = prep; f.pre_Wp = dy_packed_wp(p, 2); f.pre_nrep = 2; }
+            return run_problem(f, w, nullptr, out, p, 0, workspace, workspace_bytes, s);
+        }
     }
     bool need_zero = false;
     for (int rh = 0; rh < p->stride_h; ++rh)
@@ -750,13 +780,16 @@ int umma_conv_launch(const float* in, const float* w, const float* bias, float* 
     const DgradShare d = dgrad_share(p);
     const int pre_Wp = (p->w_out + 7) & ~7;
     // caller-packed plain dy serves every class iff no class needs a shifted replica
-    const bool use_pre = prep && d.common && d.max_tw == 1 && d.w_off == 0 && d.max_pw <= pre_Wp;
+    const bool use_pre = prep && pre_rep == 1 && d.common && d.max_tw == 1 && d.w_off == 0 && d.max_pw <= pre_Wp;
+    const bool use_pre2 = prep && pre_rep == 2 && d.common && d.max_tw <= 2 && d.w_off == 0;
     const __nv_bfloat16* shared = nullptr;
     int shared_Wp = 0, shared_nrep = 0;
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     size_t ws_bytes = workspace_bytes;
     if (use_pre) {
         shared = prep; shared_Wp = pre_Wp; shared_nrep = 1;
+    } else if (use_pre2) {
+        shared = prep; shared_Wp = dy_packed_wp(p, 2); shared_nrep = 2;
     } else if (d.common && d.n_classes > 1) {
         if (!workspace || workspace_bytes < d.act_bytes + d.max_w_bytes + 2048) return CPC_ERR_WORKSPACE;
         uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
@@ -986,10 +1019,12 @@ int umma_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv
         const uint64_t strides[4] = {rb, rb * p->h_in, rb * p->h_in * p->c_in, rb * p->h_in * p->c_in * B};
         const uint32_t box[5] = {ATOM, (uint32_t)u.TH, (uint32_t)u.CB, 1, 1};
         if (!make_tmap_bf16(&tx, xp, 5, dims, strides, box)) return CPC_ERR_CUDA;
-        const uint64_t rd = (uint64_t)u.Wp_dy * 2;
+        // caller-packed dy may carry the data gradient's second replica: wider pitch, planes twice as far apart
+        const int dy_rep = pre_dy ? umma_dy_replicas(p) : 1;
+        const uint64_t rd = (uint64_t)(pre_dy ? dy_packed_wp(p, dy_rep) : u.Wp_dy) * 2;
         const uint64_t ddims[5] = {(uint64_t)p->w_out, (uint64_t)p->h_out, (uint64_t)p->c_out, (uint64_t)B,
                                    (uint64_t)u.planes};
-        const uint64_t dstr[4] = {rd, rd * p->h_out, rd * p->h_out * p->c_out, rd * p->h_out * p->c_out * B};
+        const uint64_t dstr[4] = {rd, rd * p->h_out, rd * p->h_out * p->c_out, rd * p->h_out * p->c_out * B * dy_rep};
         const uint32_t dbox[5] = {ATOM, 1, (uint32_t)u.n_tile, 1, 1};
         if (!make_tmap_bf16(&tdy, dyp, 5, ddims, dstr, dbox)) return CPC_ERR_CUDA;
     }

@@ -63,6 +63,43 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict
         const long row = g / groups;
         const int w0 = (int)(g - row * groups) << 3;
         const float* src = x + row * W;
+        if (w_mul == 2 && rep_mul == 1 && nrep == 3) {
+            // 3x3 / stride-2 forward operand: the three replicas of 8 output columns read ONE window of 17 consecutive
+            // source columns (replica r, column i <- window[2 i + r]): load and split it once instead of three strided
+            // gathers (the generic loop below ran at 3.5 TB/s against 5.7 for the plain pack)
+            const int wb = 2 * w0 + w_off;
+            if (wb >= 0 && wb + 17 <= W) {
+                float win[17];
+                if (vec_ok && !(wb & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 t = __ldg(reinterpret_cast<const float2*>(src + wb) + i);
+                        win[2 * i] = t.x; win[2 * i + 1] = t.y;
+                    }
+                    win[16] = __ldg(src + wb + 16);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) win[i] = __ldg(src + wb + i);
+                }
+                __nv_bfloat16 whi[17], wlo[17];
+#pragma unroll
+                for (int i = 0; i < 17; ++i) {
+                    whi[i] = __float2bfloat16_rn(win[i]);
+                    wlo[i] = __float2bfloat16_rn(win[i] - __bfloat162float(whi[i]));
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    __align__(16) __nv_bfloat16 hi[8];
+                    __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { hi[i] = whi[2 * i + r]; lo[i] = wlo[2 * i + r]; }
+                    const long o = ((long)r * rows + row) * Wp + w0;
+                    *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
+                    if (planes == 2) *reinterpret_cast<uint4*>(out + plane_stride + o) = *reinterpret_cast<const uint4*>(lo);
+                }
+                continue;
+            }
+        }
         for (int r = 0; r < nrep; ++r) {
             __align__(16) __nv_bfloat16 hi[8];
             __align__(16) __nv_bfloat16 lo[8];

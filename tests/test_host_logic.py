@@ -46,6 +46,14 @@ def test_abi_rejects_bad_arguments_before_touching_the_device(built_lib):
     c.kernel_size[0], c.bin_lo[0], c.bin_hi[0] = 128, 0, 4
     assert lib.cpc_cqt_fwd(None, None, None, None, None, ctypes.byref(c), None, 0, None) == -1  # frames overrun input
     assert lib.cpc_conv_fwd(None, None, None, None, None, None, 0, None) == -7
+    b = _lib.BnParams()
+    b.batch, b.channels, b.height, b.width, b.eps, b.training = 2, 3, 4, 6, 1e-5, 1
+    assert lib.cpc_bn_packed_bytes(ctypes.byref(b)) == 2 * 2 * 3 * 4 * 8 * 2                   # two planes, pitch 8, bf16
+    assert lib.cpc_bn_relu_fwd_packed(*([None] * 9), ctypes.byref(b), None, 0, None) == -7     # null pointers
+    assert lib.cpc_bn_relu_bwd_packed(*([None] * 12), ctypes.byref(b), None, 0, None) == -7
+    b.width = 0
+    assert lib.cpc_bn_packed_bytes(ctypes.byref(b)) == 0                                       # bad shape
+    assert lib.cpc_conv_pack_dy(None, None, None, ctypes.byref(p), None) == -1                 # stride 0 from above
     a = _lib.AdamParams(1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, 0)
     assert lib.cpc_adam_step(0, None, None, None, None, None, None, ctypes.byref(a), None) == -7  # no step counter
     a.beta2 = 1.5
@@ -63,6 +71,22 @@ def test_phase_accumulation_matches_reference_golden():
     want = torch.from_numpy(g["acc_out"])
     d = torch.remainder(out - want + np.pi, 2 * np.pi) - np.pi            # compare on the circle (mod 2 pi wrap)
     assert float(d.abs().max()) < 1e-4
+
+
+def test_second_order_switch_and_block_tail_gate():
+    """ops.second_order() is a re-entrant context flag; the block-tail node never claims CPU tensors."""
+    import cpc_b200
+    ops = cpc_b200.ops
+    assert not ops.second_order_enabled()
+    with ops.second_order():
+        assert ops.second_order_enabled()
+        with ops.second_order(False):
+            assert not ops.second_order_enabled()
+        assert ops.second_order_enabled()
+    assert not ops.second_order_enabled()
+    conv = cpc_b200.Conv2d(32, 32, (9, 1))
+    bn0, bn1 = torch.nn.BatchNorm2d(32), torch.nn.BatchNorm2d(32)
+    assert not ops.block_tail_eligible(torch.zeros(1, 32, 20, 16), bn0, conv, 8, bn1)
 
 
 def test_no_cpu_fallback(built_lib):

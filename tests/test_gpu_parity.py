@@ -884,6 +884,14 @@ def test_block_tail_node_matches_literal_modules(cpc, cfg):
             assert grad_err(p.grad, q.grad) < TOL, n
     for (n, b), (_, c) in zip(block.named_buffers(), ref_block.named_buffers()):
         assert rel_err(b.float(), c.float()) < 1e-4, n
+    # eval mode (validate()): running statistics, no autograd
+    block.eval()
+    ref_block.eval()
+    with torch.no_grad():
+        y_eval = block(x, outer_relu=cfg['outer'])
+        with cpc.ops.second_order():
+            y_eval_ref = ref_block(x, outer_relu=cfg['outer'])
+    assert rel_err(y_eval, y_eval_ref) < 1e-4
 
 
 # ---------------------------------------------------------------------------------------------------

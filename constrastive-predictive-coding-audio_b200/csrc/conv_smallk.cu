@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const float* __restrict_
 
 // grid (pixel chunks of SW_ITERS * 32 pixels, B, Cout / 32); block = 32 / CPW warps, warp w owns channels CPW*w .. +CPW-1
 // (CPW = 8 while the CPW x KT accumulators fit in registers: every x tap loaded is then reused by 8 channels)
-constexpr int SW_ITERS = 32;
+constexpr int SW_ITERS = 64;
 template <int KT, int CPW>
 __global__ void __launch_bounds__(32 * (32 / CPW)) small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                      float* __restrict__ dw, SmallGeom g, int interior) {

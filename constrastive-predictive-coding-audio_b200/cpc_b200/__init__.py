@@ -9,6 +9,7 @@ Public surface mirrors the reference's modules:
     sampler  : FileBatchSampler, SyntheticAudioDataset
     ddp      : one-process-per-GPU gradient averaging
     optim    : Adam (torch.optim.Adam semantics, one kernel per step)
+    snapshots: state_dict of the reference's whole-model snapshot pickles, without importing reference code
     ops      : conv1d / conv2d / infonce / cqt_frontend autograd functions over the C-ABI
 """
 from . import _lib, ops                                                        # noqa: F401
@@ -22,6 +23,6 @@ from .ar_models import AttentionModel, AudioGRUModel, ConvolutionalArBlock, Conv
 from .trainer import (ContrastiveEstimationTrainer, DeterministicSampler, GraphedTrainStep, difference_score_function,  # noqa: F401
                       linear_score_function, softplus_score_function)
 from .sampler import FileBatchSampler, SyntheticAudioDataset                  # noqa: F401
-from . import configs, ddp, optim                                                    # noqa: F401
+from . import configs, ddp, optim, snapshots                                                    # noqa: F401
 
 __version__ = "0.1.0"

@@ -288,6 +288,24 @@ def golden_trainer_gp(ref):
     np.savez_compressed(os.path.join(OUT, "trainer_gp.npz"), **out)
 
 
+def golden_snapshot(ref):
+    """A whole-model snapshot pickle written the way the reference writes them (torch.save(model), SnapshotManager /
+    audio_model.load_to_cpu): a small CQT + residual-encoder + conv-AR model, plus its state_dict for comparison."""
+    sm, am = ref["scalogram_model"], ref["audio_model"]
+    torch.manual_seed(6)
+    cfg = small_resnet_cfg(ref)
+    cfg['blocks'][2] = dict(cfg['blocks'][2], kernel_size_1=(30, 2), pooling_1=1, ceil_pooling=False)
+    cfg['blocks'][1] = dict(cfg['blocks'][1], kernel_size_2=(35, 1))
+    pre = sm.PreprocessingModule(dict(sm.cqt_default_dict), phase=True)
+    enc = sm.ScalogramResidualEncoder(cfg, preprocessing_module=pre)
+    ar = am.ConvolutionalArModel({'kernel_sizes': [3, 3], 'channel_count': [24, 16, 16], 'stride': [1, 1],
+                                  'pooling': [1, 2], 'bias': True, 'batch_norm': True, 'residual': False,
+                                  'activation_register': None})
+    model = am.AudioPredictiveCodingModel(enc, ar, enc_size=24, ar_size=16, visible_steps=10, prediction_steps=3)
+    torch.save(model, os.path.join(OUT, "ref_snapshot_1200"))
+    np.savez_compressed(os.path.join(OUT, "ref_snapshot_state.npz"), **sd_np(model))
+
+
 class StoredPairModel(torch.nn.Module):
     """A 'model' whose parameters ARE (pred, targets): lets the reference trainer's own loss code and
     autograd produce loss / gradients for arbitrary (pred, targets)."""
@@ -418,6 +436,7 @@ def main():
     golden_validate(ref)
     golden_trainer_gp(ref)
     golden_cqt_grad(ref)
+    golden_snapshot(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -89,6 +89,45 @@ def test_second_order_switch_and_block_tail_gate():
     assert not ops.block_tail_eligible(torch.zeros(1, 32, 20, 16), bn0, conv, 8, bn1)
 
 
+def test_reference_snapshot_loads_without_reference_code(tmp_path):
+    """A whole-model pickle written by the unmodified reference (tests/golden/ref_snapshot_1200, produced by
+    oracle/make_golden.py golden_snapshot) is read without any reference module importable, and its state_dict loads
+    strictly into the model this package builds from the same config dicts (setup_functions.py:134-164)."""
+    import cpc_b200
+    from conftest import GOLDEN
+    from test_oracle_golden import small_resnet_blocks
+    assert "audio_model" not in sys.modules and "scalogram_model" not in sys.modules
+    path = os.path.join(GOLDEN, "ref_snapshot_1200")
+    want = load_golden("ref_snapshot_state.npz")
+    state = cpc_b200.snapshots.extract_state_dict(path)
+    assert list(state) == list(want) or set(state) == set(want)
+    for k, v in state.items():
+        assert np.array_equal(v.numpy(), want[k]), k
+    blocks = small_resnet_blocks()
+    blocks[0]['in_channels'] = 1
+    blocks[2] = dict(blocks[2], kernel_size_1=(30, 2), pooling_1=1, ceil_pooling=False)
+    blocks[1] = dict(blocks[1], kernel_size_2=(35, 1))
+    pre = cpc_b200.PreprocessingModule(dict(cpc_b200.cqt_default_dict), phase=True)
+    enc = cpc_b200.ScalogramResidualEncoder({'phase': True, 'blocks': blocks, 'activation_register': None},
+                                            preprocessing_module=pre)
+    ar = cpc_b200.ConvolutionalArModel({'kernel_sizes': [3, 3], 'channel_count': [24, 16, 16], 'stride': [1, 1],
+                                        'pooling': [1, 2], 'bias': True, 'batch_norm': True, 'residual': False,
+                                        'activation_register': None})
+    model = cpc_b200.AudioPredictiveCodingModel(enc, ar, enc_size=24, ar_size=16, visible_steps=10, prediction_steps=3)
+    assert cpc_b200.snapshots.load_reference_snapshot(model, path, strict=True) == 1200
+    for k, v in model.state_dict().items():
+        assert np.array_equal(v.numpy(), want[k]), k
+    # round trip through the portable form
+    out = tmp_path / "mine_7"
+    cpc_b200.snapshots.save_snapshot(model, str(out))
+    again = cpc_b200.snapshots.extract_state_dict(str(out))
+    assert set(again) == set(want) and cpc_b200.snapshots.snapshot_step(str(out)) == 7
+    # the stand-ins are inert: calling one explains what to do instead of computing anything
+    graph = cpc_b200.snapshots.read_reference_snapshot(path)
+    with pytest.raises(RuntimeError):
+        graph(torch.zeros(1, 1, 8))
+
+
 def test_no_cpu_fallback(built_lib):
     import cpc_b200
     enc = cpc_b200.AudioEncoder()

@@ -50,12 +50,21 @@ def _stub_class(module, name, is_module=True):
 _NON_MODULES = {"ActivationRegister"}
 
 
+# everything else a model pickle legitimately needs; any other global is refused (a pickle can name arbitrary callables)
+_ALLOWED_ROOTS = ("torch", "collections", "numpy", "_codecs", "copyreg")
+_ALLOWED_BUILTINS = {"set", "frozenset", "dict", "list", "tuple", "slice", "range", "complex", "bytearray", "getattr",
+                     "object", "int", "float", "bool", "str", "bytes"}
+
+
 class _SnapshotUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         root = module.split(".")[0]
         if root in REFERENCE_MODULES or root == "__main__":
             return _stub_class(module, name, is_module=name not in _NON_MODULES)
-        return super().find_class(module, name)
+        if root in _ALLOWED_ROOTS or (root in ("builtins", "__builtin__") and name in _ALLOWED_BUILTINS):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError("snapshot names %s.%s, which is neither a reference class nor a torch / numpy / "
+                                     "container type" % (module, name))
 
 
 class _PickleModule:

@@ -126,6 +126,16 @@ def test_reference_snapshot_loads_without_reference_code(tmp_path):
     graph = cpc_b200.snapshots.read_reference_snapshot(path)
     with pytest.raises(RuntimeError):
         graph(torch.zeros(1, 1, 8))
+    # a pickle may name any callable: globals outside the reference / torch / container set are refused
+    import pickle
+
+    class Hostile:
+        def __reduce__(self):
+            return (os.getcwd, ())
+    bad = tmp_path / "bad_1"
+    bad.write_bytes(pickle.dumps(Hostile()))
+    with pytest.raises(pickle.UnpicklingError):
+        cpc_b200.snapshots.read_reference_snapshot(str(bad))
 
 
 def test_no_cpu_fallback(built_lib):

@@ -73,6 +73,54 @@ def test_phase_accumulation_matches_reference_golden():
     assert float(d.abs().max()) < 1e-4
 
 
+def test_conv_dispatch_table_for_the_baseline_layers(built_lib):
+    """Host-side dispatch (no device needed): which kernel family serves forward / dgrad / wgrad of every arch-7 conv at
+    the BASELINE sizes, and the size of the canonical packed operands -- two dy replicas exactly for the strided convs
+    whose data gradient reads column-shifted copies."""
+    from cpc_b200 import _lib
+    lib = _lib.load()
+
+    def params(ci, h, w, co, kh, kw, s, pt=0):
+        p = _lib.ConvParams()
+        p.batch, p.c_in, p.h_in, p.w_in, p.c_out, p.kh, p.kw = 64, ci, h, w, co, kh, kw
+        p.stride_h = p.stride_w = s
+        p.pad_top, p.pad_left, p.precision = pt, 0, 0
+        p.h_out, p.w_out = (h + pt - kh) // s + 1, (w - kw) // s + 1
+        return p
+
+    def round8(v):
+        return (v + 7) // 8 * 8
+
+    table = {  # name: (params, families (fwd, dgrad, wgrad), dy replicas)
+        "block0 conv_a": (params(2, 256, 629, 32, 3, 3, 2), (1, 0, 1), 0),
+        "block0 conv_b": (params(32, 127, 314, 32, 64, 1, 1, pt=63), (2, 2, 2), 1),
+        "block1 conv_a": (params(32, 127, 314, 128, 3, 3, 2), (4, 4, 4), 2),
+        "block1 conv_b": (params(128, 63, 156, 128, 30, 1, 1), (3, 3, 3), 1),
+        "block1 residual": (params(32, 64, 157, 128, 1, 1, 1), (4, 4, 4), 1),
+        "block2 conv_a": (params(128, 34, 156, 256, 3, 3, 2), (4, 4, 4), 2),
+        "block2 conv_b": (params(256, 16, 77, 256, 15, 1, 1), (4, 4, 4), 1),
+        "block3 conv_a": (params(256, 2, 77, 512, 2, 2, 1), (4, 4, 4), 1),
+    }
+    for name, (p, families, dy_rep) in table.items():
+        got = tuple(lib.cpc_conv_kernel_family(ctypes.byref(p), which) for which in (0, 1, 2))
+        assert got == families, (name, got)
+        rows = 64 * p.c_out * p.h_out
+        want = 0 if dy_rep == 0 else 2 * dy_rep * rows * round8(p.w_out + (1 if dy_rep == 2 else 0)) * 2
+        assert lib.cpc_conv_packed_bytes(ctypes.byref(p), 1) == (want + 1023) // 1024 * 1024, name
+        assert lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1) >= 0
+    # bf16 mode and the CUDA-core override change the answer
+    p = table["block0 conv_b"][0]
+    p.precision = 1
+    assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 4                   # row-streaming kernels are fp32-faithful only
+    p.precision = 0
+    os.environ["CPC_FORCE_CUDA_CORE_CONV"] = "1"
+    try:
+        assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 0
+        assert lib.cpc_conv_packed_bytes(ctypes.byref(p), 1) == 0
+    finally:
+        del os.environ["CPC_FORCE_CUDA_CORE_CONV"]
+
+
 def test_second_order_switch_and_block_tail_gate():
     """ops.second_order() is a re-entrant context flag; the block-tail node never claims CPU tensors."""
     import cpc_b200

@@ -43,6 +43,30 @@ def test_cqt_matches_reference(plan):
     assert rel_err(O.cqt_forward(torch.from_numpy(g["x2"]), plan2), g["complex2"]) < 1e-6
 
 
+def test_cqt_input_gradients_match_reference():
+    """d/d(audio) through the oracle's CQT and phase scalogram against the reference's autograd (cqt_grad.npz); also the
+    PhaseAccumulation formula (constant_q_transform.py:306-313) restated inline."""
+    g = load_golden("cqt_grad.npz")
+    plan = O.CqtPlan(8000, 55, 96, 24, 0.5, 64)
+    assert plan.kernel_sizes == list(g["kernel_sizes"])
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    z = O.cqt_forward(x, plan)
+    assert rel_err(z, g["z"]) < 1e-6
+    (z * torch.from_numpy(g["gz"])).sum().backward()
+    assert rel_err(x.grad, g["gx"]) < 1e-5
+    x2 = torch.from_numpy(g["x2"]).requires_grad_(True)
+    y = O.preprocess(x2, plan, phase=True, offset_zero=True, output_power=1., pooling=[1, 2], scaling=3.)
+    assert rel_err(y[:, 0], g["y2"][:, 0]) < 1e-6
+    (y * torch.from_numpy(g["gy2"])).sum().backward()
+    assert rel_err(x2.grad, g["gx2"]) < 1e-3                      # 1/|z| factors: fp32 summation order matters
+    fixed, scaling = O.phase_constants(plan)
+    ph = torch.from_numpy(g["acc_in"])
+    acc = torch.cumsum(torch.cat([torch.zeros(1, 96, 1), ph / torch.from_numpy(scaling).view(1, -1, 1)
+                                  - torch.from_numpy(fixed).view(1, -1, 1)], dim=2), dim=2) % (2 * np.pi) - np.pi
+    d = torch.remainder(acc - torch.from_numpy(g["acc_out"]) + np.pi, 2 * np.pi) - np.pi
+    assert float(d.abs().max()) < 1e-4
+
+
 def test_audio_encoder_matches_reference():
     g = load_golden("audio_encoder.npz")
     assert list(g["kat_shape"]) == [7, 32, 28]                 # tests/test_audioEncoder.py:19-25

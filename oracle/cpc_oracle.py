@@ -286,6 +286,19 @@ def infonce_loss(pred, targets, all_steps, kind='linear', regularization=0.0):
     return loss, scores.max()
 
 
+def gradient_penalty(pred, targets, scalogram, all_steps, kind='linear', factor=10.0):
+    """Wasserstein gradient penalty, contrastive_estimation_training.py:144-155: sum of the (in per-step mode already
+    diagonal-reduced, :116) scores differentiated w.r.t. the scalogram with create_graph, then
+    factor * mean((||grad||_2 over the channel axis - 1)^2).  ``scalogram`` must require grad and be the tensor the
+    encoder consumed."""
+    scores = scores_full(pred, targets, kind)
+    if not all_steps:
+        scores = torch.diagonal(scores, dim1=1, dim2=3).permute(0, 2, 1).contiguous()
+    grad, = torch.autograd.grad(outputs=scores.sum(), inputs=scalogram, create_graph=True, retain_graph=True,
+                                only_inputs=True)
+    return ((grad.norm(2, dim=1) - 1) ** 2).mean() * factor
+
+
 def infonce_loss_clean(pred, targets, all_steps, kind='linear', regularization=0.0):
     """The same loss written as the cross-entropy it is: softmax over the
     predictions (d[,k]) for each target (t,k').  Equal to ``infonce_loss`` because the

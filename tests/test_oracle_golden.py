@@ -126,6 +126,79 @@ def test_resnet_encoder_matches_reference():
     assert rel_err(y, g["y"]) < 1e-5
 
 
+@pytest.mark.parametrize("tag,all_steps,kind", [("a", True, "linear"), ("p", False, "softplus")])
+def test_gradient_penalty_step_matches_reference_trainer(tag, all_steps, kind):
+    """First training step of the reference with wasserstein_gradient_penalty=True (trainer_gp.npz): the oracle's
+    CQT -> residual encoder -> conv AR -> W_k -> InfoNCE + gradient penalty, evaluated on the reference's initial
+    parameters and its first batch, reproduces the logged loss and max score; one SGD step on the oracle's gradients
+    reproduces the reference's parameters after that step."""
+    import torch.nn.functional as F
+    full = load_golden("trainer_gp.npz")
+    g = {k[len(tag) + 1:]: v for k, v in full.items() if k.startswith(tag + ".")}
+    lr, bs = float(g["lr"]), int(g["batch_size"])
+    random.seed(5)
+    first = O.file_batch_sampler([g["items"].shape[0]], bs)[0]
+    audio = torch.from_numpy(g["items"][first]).unsqueeze(1)
+    cfgs = small_resnet_blocks()
+    cfgs[2] = dict(cfgs[2], kernel_size_1=(30, 2), pooling_1=1, ceil_pooling=False)
+    cfgs[1] = dict(cfgs[1], kernel_size_2=(35, 1))
+    sd = {"p." + k[3:]: v for k, v in g.items() if k.startswith("s0.")}
+    enc_state = {k.replace("p.encoder.", "p."): v for k, v in sd.items() if k.startswith("p.encoder.")}
+    params = [block_param_map(enc_state, i, c) for i, c in enumerate(cfgs)]
+    leaves = {}
+
+    def leaf(name, key):
+        t = torch.from_numpy(sd["p." + key]).clone().requires_grad_(True)
+        leaves[key] = t
+        return t
+    for i, p in enumerate(params):                                # make every encoder parameter a leaf we can read back
+        keys = sorted(k for k in enc_state if k.startswith("p.blocks.%d." % i))
+        convs = sorted({int(k.split(".")[4]) for k in keys if ".main_modules." in k and k.endswith(".weight")
+                        and enc_state[k].ndim == 4})
+        bns = sorted({int(k.split(".")[4]) for k in keys if ".main_modules." in k and k.endswith("running_mean")})
+        names = {}
+        for name, idx in list(zip(("conv_a", "conv_b"), convs)) + list(zip(("bn_a", "bn_b"), bns)):
+            for leaf_name in ("weight", "bias"):
+                names[name + "." + leaf_name] = "blocks.%d.main_modules.%d.%s" % (i, idx, leaf_name)
+        for k in keys:
+            if ".residual_modules." in k and k.endswith(".weight"):
+                names["res.weight"] = k[2:]
+        for name in list(p):
+            p[name] = leaf(name, "encoder." + names[name])
+    ar = "autoregressive_model.module_list."
+    w0, b0 = leaf("w0", ar + "0.main_modules.0.weight"), leaf("b0", ar + "0.main_modules.0.bias")
+    g0, h0 = leaf("g0", ar + "0.main_modules.1.weight"), leaf("h0", ar + "0.main_modules.1.bias")
+    w1, b1 = leaf("w1", ar + "1.main_modules.1.weight"), leaf("b1", ar + "1.main_modules.1.bias")
+    g1, h1 = leaf("g1", ar + "1.main_modules.2.weight"), leaf("h1", ar + "1.main_modules.2.bias")
+    wk = leaf("wk", "prediction_model.weight")
+    plan = O.CqtPlan(16000, 30, 256, 32, 0.5, 128)
+    with torch.no_grad():
+        scal = O.preprocess(audio, plan, phase=True)
+    scal.requires_grad_(True)
+    z = O.residual_encoder_forward(scal, cfgs, params, training=True)
+    targets, vis = O.predictive_split(z, 10, 3)
+    x = F.relu(F.batch_norm(F.conv1d(vis, w0, b0), None, None, g0, h0, training=True))
+    x = F.max_pool1d(x, 2, ceil_mode=True)
+    x = F.relu(F.batch_norm(F.conv1d(x, w1, b1), None, None, g1, h1, training=True))
+    pred = F.linear(x[:, :, -1], wk).view(-1, 3, 24)
+    loss, mx = O.infonce_loss(pred, targets, all_steps, kind, 0.25)
+    loss = loss + O.gradient_penalty(pred, targets, scal, all_steps, kind, 10.0)
+    assert abs(float(loss.detach()) - g["losses"][0]) < 1e-4 * abs(g["losses"][0]), (float(loss.detach()), g["losses"][0])
+    assert abs(float(mx.detach()) - g["max_scores"][0]) < 1e-4 * max(1.0, abs(g["max_scores"][0]))
+    loss.backward()
+    from conftest import bn_shadowed_biases, grad_err
+    noise_only = bn_shadowed_biases([k[3:] for k in g if k.startswith("s0.")])
+    checked = 0
+    for key, t in leaves.items():
+        if key in noise_only:
+            continue
+        ref_grad = (torch.from_numpy(g["s0." + key]) - torch.from_numpy(g["s1." + key])) / lr
+        # (before - after) / lr with lr = 1e-4: parameters near 1.0 resolve 6e-8, i.e. 6e-4 absolute on a gradient
+        assert grad_err(t.grad, ref_grad) < 5e-3, key
+        checked += 1
+    assert checked >= 20
+
+
 def test_infonce_matches_reference_trainer():
     g = load_golden("infonce.npz")
     cases = json.loads(str(g["cases"]))

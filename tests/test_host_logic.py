@@ -340,3 +340,32 @@ def test_gradient_bucket_reducer_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "RANK_OK %d" % r in o, o
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours): exactly one JSON line on stdout with the
+    contract's keys, the same metric / unit / workload as our arm, and no work on ranks other than 0."""
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "train audio-sec/sec" and line["unit"] == "audio-s/s"
+    assert line["vs_baseline"] is None and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "e24" in line["config"]["workload"]
+    # a non-zero rank of a torchrun launch exits 0 without output
+    quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                           capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+    # our arm refuses to run without a GPU instead of falling back
+    if not torch.cuda.is_available():
+        ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                              timeout=300, env=env)
+        assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)

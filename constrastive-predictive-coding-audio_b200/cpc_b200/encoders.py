@@ -10,6 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, ops
+from . import frontend
 from .frontend import CQT, PhaseDifference
 from .model import ActivationWriter
 
@@ -188,8 +189,15 @@ class ScalogramEncoder(nn.Module):
         self.downsampling_factor = args_dict['hop_length'] * np.prod(args_dict['pooling']) * np.prod(args_dict['stride'])
 
     def forward(self, x):
-        self.cqt._check_frozen()
-        if self.phase:
+        if self.cqt.needs_autograd(x):
+            # trainable filterbank / differentiable audio: scalogram_model.py:212-222 term by term on the conv kernels
+            z = self.cqt.forward_differentiable(x)
+            if self.phase:
+                amp = torch.log(torch.pow(frontend.abs(z[:, :, 1:]), 2) + 1e-9)
+                x = torch.stack([amp, self.phase_diff(frontend.angle(z))], dim=1)
+            else:
+                x = torch.log(torch.pow(frontend.abs(z), 2) + 1e-9).unsqueeze(1)
+        elif self.phase:
             x = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW_PHASE,
                                  phase_fixed=self.phase_diff.fixed_phase_diff.reshape(-1),
                                  phase_scale=self.phase_diff.scaling.reshape(-1), eps=1e-9)

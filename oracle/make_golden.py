@@ -288,6 +288,32 @@ def golden_trainer_gp(ref):
     np.savez_compressed(os.path.join(OUT, "trainer_gp.npz"), **out)
 
 
+def golden_scalogram_encoder(ref):
+    """ScalogramEncoder (scalogram_model.py:129-227): own CQT -> log power (+ phase difference) ->
+    pad / conv / pool / ReLU / BatchNorm stack.  Small stacks, both input variants; forward, parameter gradients."""
+    sm = ref["scalogram_model"]
+    out = {}
+    for tag, phase in (("m", False), ("p", True)):
+        torch.manual_seed(8)
+        cfg = dict(sm.cqt_default_dict)
+        cfg.update({'kernel_sizes': [(9, 1), (5, 5), (5, 1), (3, 3)], 'top_padding': [8, 0, 0, 0],
+                    'channel_count': [1, 8, 8, 16, 24], 'pooling': [1, 2, 1, 2], 'stride': [1, 1, 1, 1], 'bias': True,
+                    'batch_norm': True, 'phase': phase, 'separable': False, 'lowpass_init': 0., 'instance_norm': False,
+                    'dropout': 0.})
+        enc = sm.ScalogramEncoder(cfg)
+        enc.train()
+        g = torch.Generator().manual_seed(31)
+        x = 0.1 * torch.randn(2, 1, 16384 + 1 + 128 * 40, generator=g)
+        y = enc(x)
+        gy = torch.randn(y.shape, generator=g)
+        (y * gy).sum().backward()
+        out.update({tag + ".x": x.numpy(), tag + ".y": y.detach().numpy(), tag + ".gy": gy.numpy(),
+                    tag + ".rf": np.array(enc.receptive_field), tag + ".ds": np.array(enc.downsampling_factor)})
+        out.update({tag + ".p." + k: v for k, v in sd_np(enc).items() if not k.startswith("cqt.")})
+        out.update({tag + ".g." + n: p.grad.numpy() for n, p in enc.named_parameters() if p.grad is not None})
+    np.savez_compressed(os.path.join(OUT, "scalogram_encoder.npz"), **out)
+
+
 def golden_snapshot(ref):
     """A whole-model snapshot pickle written the way the reference writes them (torch.save(model), SnapshotManager /
     audio_model.load_to_cpu): a small CQT + residual-encoder + conv-AR model, plus its state_dict for comparison."""
@@ -437,6 +463,7 @@ def main():
     golden_trainer_gp(ref)
     golden_cqt_grad(ref)
     golden_snapshot(ref)
+    golden_scalogram_encoder(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

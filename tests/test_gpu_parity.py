@@ -377,6 +377,59 @@ def test_residual_encoder_matches_reference_golden(cpc):
             assert rel_err(v, g["p." + k]) < TOL, k
 
 
+@pytest.mark.parametrize("tensor_cqt", [False, True])
+@pytest.mark.parametrize("tag,phase", [("m", False), ("p", True)])
+def test_scalogram_encoder_matches_reference_golden(cpc, monkeypatch, tag, phase, tensor_cqt):
+    """ScalogramEncoder (scalogram_model.py:129-227): own CQT -> log power (+ phase difference) ->
+    ZeroPad / conv / pool / ReLU / BatchNorm stack, forward and parameter gradients against the reference.  Held to 1e-3
+    with the fp32 filterbank; with the tensor-core filterbank the log / atan2 of near-silent cells widens the bound
+    (same effect as in the training replays)."""
+    monkeypatch.setenv("CPC_NO_TENSOR_CQT", "0" if tensor_cqt else "1")
+    full = load_golden("scalogram_encoder.npz")
+    g = {k[len(tag) + 1:]: v for k, v in full.items() if k.startswith(tag + ".")}
+    cfg = dict(cpc.cqt_default_dict)
+    cfg.update({'kernel_sizes': [(9, 1), (5, 5), (5, 1), (3, 3)], 'top_padding': [8, 0, 0, 0],
+                'channel_count': [1, 8, 8, 16, 24], 'pooling': [1, 2, 1, 2], 'stride': [1, 1, 1, 1], 'bias': True,
+                'batch_norm': True, 'phase': phase, 'separable': False, 'lowpass_init': 0., 'instance_norm': False,
+                'dropout': 0.})
+    enc = cpc.ScalogramEncoder(dict(cfg, channel_count=list(cfg['channel_count'])))
+    assert enc.receptive_field == int(g["rf"]) and int(enc.downsampling_factor) == int(g["ds"])
+    sd = {k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("p.")}
+    own = enc.state_dict()
+    assert set(sd) == {k for k in own if not k.startswith("cqt.")}, set(sd) ^ {k for k in own if not k.startswith("cqt.")}
+    for k in sd:                                                # the golden holds BN statistics AFTER its forward pass
+        if k.endswith("running_mean"):
+            sd[k] = torch.zeros_like(sd[k])
+        if k.endswith("running_var"):
+            sd[k] = torch.ones_like(sd[k])
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros_like(sd[k])
+    enc.load_state_dict(sd, strict=False)
+    enc.to(DEV).train()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    y = enc(x)
+    assert tuple(y.shape) == g["y"].shape
+    tol = 5e-2 if tensor_cqt else TOL
+    assert rel_err(y, g["y"]) < tol
+    (y * torch.from_numpy(g["gy"]).to(DEV)).sum().backward()
+    for n, p in enc.named_parameters():
+        if n.startswith("cqt.") or n.startswith("phase_diff."):
+            continue
+        assert grad_err(p.grad, g["g." + n]) < tol, n
+    for k in own:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel_err(enc.state_dict()[k], g["p." + k]) < tol, k
+    # a trainable filterbank takes the differentiable front end: same values
+    if not tensor_cqt:
+        enc_t = cpc.ScalogramEncoder(dict(cfg, channel_count=list(cfg['channel_count']), trainable_cqt=True))
+        enc_t.load_state_dict(sd, strict=False)
+        enc_t.to(DEV).train()
+        y_t = enc_t(x)
+        assert rel_err(y_t, g["y"]) < tol
+        (y_t * torch.from_numpy(g["gy"]).to(DEV)).sum().backward()
+        assert all(c.weight.grad is not None and bool(torch.isfinite(c.weight.grad).all()) for c in enc_t.cqt.conv_modules)
+
+
 # ---------------------------------------------------------------------------------------------------
 # max pooling
 # ---------------------------------------------------------------------------------------------------

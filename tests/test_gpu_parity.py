@@ -947,6 +947,36 @@ def test_block_tail_node_matches_literal_modules(cpc, cfg):
     assert rel_err(y_eval, y_eval_ref) < 1e-4
 
 
+def test_activation_taps_receive_intermediates_and_match_the_fused_path(cpc):
+    """With an ActivationRegister attached (audio_model.py:222-284) a block runs module by module so that the taps see
+    the intermediate activations; the result equals the block-tail node of the same block without taps."""
+    import copy
+    block_cfg = {'in_channels': 32, 'hidden_channels': None, 'out_channels': 32, 'kernel_size_1': (3, 3),
+                 'kernel_size_2': (9, 1), 'top_padding_1': None, 'top_padding_2': 8, 'padding_1': 0, 'padding_2': 0,
+                 'stride_1': 2, 'stride_2': 1, 'pooling_1': 1, 'pooling_2': 1, 'bias': True, 'separable': False,
+                 'residual': True, 'batch_norm': True, 'ceil_pooling': False}
+    torch.manual_seed(14)
+    plain = cpc.ScalogramEncoderBlock(dict(block_cfg), name='blk', activation_register=None).to(DEV).train()
+    register = cpc.ActivationRegister()
+    tapped = cpc.ScalogramEncoderBlock(dict(block_cfg), name='blk', activation_register=register).to(DEV).train()
+    tapped.load_state_dict(copy.deepcopy(plain.state_dict()))
+    x = torch.randn(2, 32, 41, 77, generator=torch.Generator().manual_seed(15)).to(DEV)
+    y_plain = plain(x.clone().requires_grad_(True), outer_relu=True)
+    y_tapped = tapped(x.clone().requires_grad_(True), outer_relu=True)
+    assert type(y_plain.grad_fn).__name__.startswith("_BlockTailFunction")
+    assert not type(y_tapped.grad_fn).__name__.startswith("_BlockTailFunction")
+    assert rel_err(y_tapped, y_plain) < 1e-4
+    acts = register.get_activations()
+    assert set(acts) == {'blk_main_conv_1', 'blk_main_conv_2'}
+    assert tuple(acts['blk_main_conv_1'].shape) == (2, 32, 20, 38)          # after conv_a + bn + relu
+    assert tuple(acts['blk_main_conv_2'].shape) == tuple(y_plain.shape)      # block output before the outer ReLU
+    assert rel_err(torch.relu(acts['blk_main_conv_2']), y_plain) < 1e-4
+    register.active = False
+    register.activations.clear()
+    tapped(x, outer_relu=True)
+    assert len(register.get_activations()) == 0
+
+
 # ---------------------------------------------------------------------------------------------------
 # gradients through the front end, InverseCQT (SURVEY 8(f) row 3)
 # ---------------------------------------------------------------------------------------------------

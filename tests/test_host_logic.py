@@ -369,3 +369,30 @@ def test_bench_reference_arm_prints_one_contract_line():
         ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                               timeout=300, env=env)
         assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
+
+
+def test_literal_loss_block_and_small_helpers():
+    """Host-side pieces that never touch a kernel: the literal loss block used for score functions the fused kernel
+    does not know (contrastive_estimation_training.py:108-122,141) against the oracle, DeterministicSampler (:363-382),
+    num_parameters (audio_model.py:293-297)."""
+    import cpc_b200
+    import cpc_oracle as O
+    from cpc_b200.trainer import reference_loss_from_scores
+    gen = torch.Generator().manual_seed(3)
+    pred = torch.randn(5, 4, 16, generator=gen) * 0.3
+    tgt = torch.randn(5, 16, 4, generator=gen)
+    for fn, kind in ((cpc_b200.linear_score_function, "linear"), (cpc_b200.softplus_score_function, "softplus")):
+        for all_steps in (True, False):
+            loss, mx = reference_loss_from_scores(fn(pred, tgt), 5, 4, all_steps, 0.3)
+            want, want_mx = O.infonce_loss(pred, tgt, all_steps, kind, 0.3)
+            assert abs(float(loss) - float(want)) < 1e-6 * max(1.0, abs(float(want))), (kind, all_steps)
+            assert abs(float(mx) - float(want_mx)) < 1e-6
+    # the inverse-square-distance score (:25-33) keeps its (B, K, B, K) contract
+    assert tuple(cpc_b200.difference_score_function(pred, tgt).shape) == (5, 4, 5, 4)
+    sampler = cpc_b200.DeterministicSampler(list(range(10)), batch_size=4, drop_last=True)
+    assert list(sampler) == [[0, 1, 2, 3], [4, 5, 6, 7]] and len(sampler) == 2
+    sampler = cpc_b200.DeterministicSampler(list(range(10)), batch_size=4, drop_last=False)
+    assert list(sampler)[-1] == [8, 9] and len(sampler) == 3
+    enc = cpc_b200.AudioEncoder()
+    assert cpc_b200.num_parameters(enc) == sum(p.numel() for p in enc.parameters())
+    assert enc.receptive_field == 465 and enc.downsampling_factor == 160

@@ -396,3 +396,24 @@ def test_literal_loss_block_and_small_helpers():
     enc = cpc_b200.AudioEncoder()
     assert cpc_b200.num_parameters(enc) == sum(p.numel() for p in enc.parameters())
     assert enc.receptive_field == 465 and enc.downsampling_factor == 160
+
+
+def test_preprocessing_identity_and_geometry_without_kernels():
+    """PreprocessingModule(cqt_dict=None) is the identity (scalogram_model.py:77-78); with a CQT its geometry attributes
+    follow the filterbank (:48-51, :70-72); unsupported scalogram pooling is refused at construction time."""
+    import cpc_b200
+    pre = cpc_b200.PreprocessingModule(None)
+    x = torch.randn(2, 1, 50)
+    assert pre(x) is x and pre.downsampling_factor == 1 and pre.receptive_field == 1
+    d = dict(cpc_b200.cqt_default_dict)
+    pre = cpc_b200.PreprocessingModule(d, phase=True, pooling=[1, 2])
+    assert pre.receptive_field == 16384 and pre.downsampling_factor == 256
+    assert sorted(k for k in pre.state_dict() if not k.startswith("cqt.")) == ["phase_diff.fixed_phase_diff", "phase_diff.scaling"]
+    assert len(pre.cqt.conv_modules) == 9 and pre.cqt.conv_modules[0].weight.shape == (38, 1, 16384)
+    assert not any(p.requires_grad for p in pre.parameters())
+    pre.cqt.trainable = True
+    assert all(p.requires_grad for p in pre.cqt.parameters()) and pre.cqt.needs_autograd(x)
+    with torch.no_grad():
+        assert not pre.cqt.needs_autograd(x)
+    with pytest.raises(NotImplementedError):
+        cpc_b200.PreprocessingModule(d, pooling=[2, 2])

@@ -3,8 +3,10 @@ keys (configs/cqt_configs.py, scalogram_resnet_configs.py, autoregressive_model_
 contrastive_estimation_configs.py), plus ``setup_model`` (setup_functions.py:68-117).
 
 Values are the ones the reference ends up with *as imported* (its configs alias and mutate shared dicts;
-oracle/make_golden.py dumps them from the reference and tests/test_configs.py compares).  The reference's
-own ``configs/`` package also loads unchanged against this package through ``compat/``.
+oracle/make_golden.py dumps them from the reference into tests/golden/configs.json and
+tests/test_host_logic.py compares).  The reference's own ``configs/`` package loads unchanged against this
+package through the module shims in ``compat/``: tests/test_compat_configs.py builds every experiment
+(e0 ... e32) that way and compares item lengths and state_dict keys with the reference's own setup_model.
 """
 import copy
 

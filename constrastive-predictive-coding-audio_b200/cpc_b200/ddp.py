@@ -42,6 +42,29 @@ def shard_batch(batch, rank, world):
     return batch[rank * per:(rank + 1) * per]
 
 
+class ShardedBatchSampler(torch.utils.data.Sampler):
+    """Wraps a batch sampler for one-process-per-GPU training: rank 0 iterates the wrapped sampler (so its use of
+    Python's ``random`` is exactly the single-process one), the epoch's index lists are broadcast, and every rank
+    yields only its contiguous shard ``batch[r*B/W:(r+1)*B/W]`` of each batch -- ranks agree on the global batch and
+    load 1/W of it."""
+
+    def __init__(self, batch_sampler, rank, world, group=None):
+        self.batch_sampler, self.rank, self.world, self.group = batch_sampler, rank, world, group
+
+    def __iter__(self):
+        payload = [list(map(list, iter(self.batch_sampler)))] if self.rank == 0 else [None]
+        if self.world > 1:
+            dist.broadcast_object_list(payload, src=0, group=self.group)
+        for batch in payload[0]:
+            if len(batch) % self.world:
+                raise ValueError("global batch %d is not divisible by world size %d" % (len(batch), self.world))
+            per = len(batch) // self.world
+            yield batch[self.rank * per:(self.rank + 1) * per]
+
+    def __len__(self):
+        return len(self.batch_sampler)
+
+
 def broadcast_parameters(module, src=0):
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return

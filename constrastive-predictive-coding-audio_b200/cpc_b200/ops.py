@@ -178,7 +178,7 @@ class _ConvFunction(torch.autograd.Function):
         ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 0), x.device)
         with torch.cuda.device(x.device):
             # the packed copy of x serves the forward pass now and the weight gradient later
-            keep = weight.requires_grad and torch.is_grad_enabled()
+            keep = ctx.needs_input_grad[1]                      # (torch.is_grad_enabled() is always False in here)
             packed_x = _pack_operand(lib, x, p, 0) if keep else None
             _call(_conv_key("cpc_conv_fwd", p), _conv_flops(p), lib.cpc_conv_fwd_ex, _ptr(x), _ptr(w),
                   _ptr(bias.contiguous() if bias is not None else None), _ptr(y), ctypes.byref(p), _ptr(packed_x),

@@ -94,8 +94,11 @@ class ContrastiveEstimationTrainer:
             batch = self.preprocessing(batch)
             # The reference marks the scalogram as requiring grad (:102) but only the gradient penalty ever
             # reads that gradient; without the penalty the first layer's data gradient is dead work, so it is
-            # not requested here (identical losses and parameter gradients).
-            batch.requires_grad = bool(self.wasserstein_gradient_penalty)
+            # not requested here (identical losses and parameter gradients).  The flag is only ever raised: with a
+            # trainable filterbank the scalogram is a non-leaf that already requires grad, and assigning False to
+            # it would raise.
+            if self.wasserstein_gradient_penalty and not batch.requires_grad:
+                batch.requires_grad_(True)
         kind = _FUSED_KINDS.get(self.score_function)
         if self.wasserstein_gradient_penalty:
             return self._loss_with_gradient_penalty(batch, kind)
@@ -139,48 +142,66 @@ class ContrastiveEstimationTrainer:
             cls = optim.Adam
         return cls(self.model.parameters(), lr=lr, **kwargs)
 
+    def _any_rank_nan(self, loss):
+        """True when the loss is NaN on ANY rank (one host sync; one tiny all-reduce when world > 1), so that all
+        ranks leave train() together instead of one returning and the others blocking in the next all-reduce."""
+        flag = torch.isnan(loss.detach()).to(torch.float32).reshape(1)
+        if self.world > 1:
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+        return bool(flag.item())
+
     def train(self, batch_size=32, epochs=10, lr=0.0001, continue_training_at_step=0, num_workers=1, max_steps=None,
               profile=False):
         self.model.train()
         optimizer = self.make_optimizer(lr)
         sampler = FileBatchSampler(index_count_per_file=self.dataset.get_example_count_per_file(),
                                    batch_size=batch_size, file_batch_size=self.file_batch_size, drop_last=True)
+        reducer = None
+        if self.world > 1:
+            # every rank starts from rank 0's weights and sees rank 0's batches: the sampler draws from rank 0's
+            # (unseeded, global) `random` state exactly as the single-process reference does, the index lists are
+            # broadcast, and each rank loads only its contiguous shard of every batch (DataParallel.scatter chunking)
+            ddp.broadcast_parameters(self.model)
+            sampler = ddp.ShardedBatchSampler(sampler, self.rank, self.world)
+            reducer = ddp.GradientBucketReducer(self.model)
         dataloader = torch.utils.data.DataLoader(self.dataset, batch_sampler=sampler, num_workers=num_workers,
                                                  pin_memory=True)
-        reducer = ddp.GradientBucketReducer(self.model) if self.world > 1 else None
         self.training_step = continue_training_at_step
-        for current_epoch in range(epochs):
-            if self.verbose:
-                print("epoch", current_epoch)
-            with torch.autograd.profiler.profile(use_device='cuda', enabled=profile) as prof:
-                for batch in iter(dataloader):
-                    batch = ddp.shard_batch(batch, self.rank, self.world).to(device=self.device, non_blocking=True)
-                    loss, max_score = self.loss_on_batch(batch)
-                    self.model.zero_grad()
-                    loss.backward()
-                    if reducer is not None:
-                        reducer.finish()
-                    optimizer.step()
-                    # one host sync per step for (loss, max score) instead of the reference's three
-                    loss_value, max_value = torch.stack([loss.detach(), max_score.detach()]).tolist()
-                    self.last_loss, self.last_max_score = loss_value, max_value
-                    if math.isnan(loss_value):
-                        print("nan loss")
-                        print("returned with nan loss at step", self.training_step)
-                        return
-                    if self.logger is not None:
-                        self.logger.loss_meter.update(loss_value)
-                        self.logger.score_meter.update(max_value)
-                        self.logger.log(self.training_step)
-                    elif self.verbose:
-                        print("loss at step step " + str(self.training_step) + ":", loss_value)
-                    self.training_step += 1
-                    if max_steps is not None and self.training_step >= max_steps:
+        try:
+            for current_epoch in range(epochs):
+                if self.verbose:
+                    print("epoch", current_epoch)
+                with torch.autograd.profiler.profile(use_device='cuda', enabled=profile) as prof:
+                    for batch in iter(dataloader):
+                        batch = batch.to(device=self.device, non_blocking=True)
+                        loss, max_score = self.loss_on_batch(batch)
+                        # :124-133 -- the reference leaves BEFORE backward / optimizer.step, so weights and optimizer
+                        # state stay finite
+                        if self._any_rank_nan(loss):
+                            print("nan loss")
+                            print("returned with nan loss at step", self.training_step)
+                            self.last_loss = float("nan")
+                            return
+                        self.model.zero_grad()
+                        loss.backward()
                         if reducer is not None:
-                            reducer.remove()
-                        return prof
-        if reducer is not None:
-            reducer.remove()
+                            reducer.finish()
+                        optimizer.step()
+                        # one host read per step for (loss, max score)
+                        loss_value, max_value = torch.stack([loss.detach(), max_score.detach()]).tolist()
+                        self.last_loss, self.last_max_score = loss_value, max_value
+                        if self.logger is not None:
+                            self.logger.loss_meter.update(loss_value)
+                            self.logger.score_meter.update(max_value)
+                            self.logger.log(self.training_step)
+                        elif self.verbose:
+                            print("loss at step step " + str(self.training_step) + ":", loss_value)
+                        self.training_step += 1
+                        if max_steps is not None and self.training_step >= max_steps:
+                            return prof
+        finally:
+            if reducer is not None:
+                reducer.remove()
 
     # -- validation: fused metrics kernel for the known score functions, literal block otherwise --------
     def validate(self, batch_size=64, num_workers=1, max_steps=None):
@@ -336,23 +357,19 @@ class GraphedTrainStep:
 
 
 class DeterministicSampler(torch.utils.data.Sampler):
-    """contrastive_estimation_training.py:363-382."""
+    """contrastive_estimation_training.py:363-382: single indices of ``data_source`` in a pseudo-random order that is
+    the same on every iteration (Python's ``random`` re-seeded with ``seed`` each time)."""
 
-    def __init__(self, data_source, batch_size, drop_last=True):
+    def __init__(self, data_source, seed=0):
         self.data_source = data_source
-        self.batch_size = batch_size
-        self.drop_last = drop_last
+        self.seed = seed
 
     def __iter__(self):
-        batch = []
-        for idx in range(len(self.data_source)):
-            batch.append(idx)
-            if len(batch) == self.batch_size:
-                yield batch
-                batch = []
-        if batch and not self.drop_last:
-            yield batch
+        import random
+        order = list(range(len(self.data_source)))
+        random.seed(self.seed)
+        random.shuffle(order)
+        return iter(order)
 
     def __len__(self):
-        full, rest = divmod(len(self.data_source), self.batch_size)
-        return full if self.drop_last or rest == 0 else full + 1
+        return len(self.data_source)

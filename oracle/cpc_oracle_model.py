@@ -102,6 +102,7 @@ class OracleE24(nn.Module):
             if i < len(self.blocks) - 1:
                 x = F.relu(x)
         z = x[:, :, 0, :]
+        self.last_z = z.detach()
         targets, vis = O.predictive_split(z, self.v, self.k)
         pred = self.predict(self.ar(vis)).view(-1, self.k, self.e)
         return pred, targets
@@ -120,3 +121,95 @@ def train_steps(model, audio_batches, lr=1e-4, all_steps=True, kind='linear', re
         opt.step()
         losses.append(float(loss.detach()))
     return losses
+
+
+# ---------------------------------------------------------------------------------------------------
+# Shared fixtures for the full-size e24 golden (tests/golden/e24_step.npz, oracle/make_golden.py::golden_e24)
+# ---------------------------------------------------------------------------------------------------
+
+def _name_seed(name, salt=0):
+    import zlib
+    return (zlib.crc32(name.encode()) + salt) % (2 ** 31)
+
+
+def seeded_values(shapes):
+    """{name: shape} -> {name: tensor}: deterministic parameter values keyed by the parameter NAME, so that the
+    reference (make_golden.py), this oracle and the CUDA product can be given identical weights without a 37 MB
+    fixture.  Conv / linear weights and their biases ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (torch's default
+    bound); batch-norm scales ~ U(0.8, 1.2), shifts ~ U(-0.1, 0.1) (non-trivial on purpose)."""
+    out = {}
+    for name, shape in shapes.items():
+        shape = tuple(shape)
+        g = torch.Generator().manual_seed(_name_seed(name))
+        u = torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1
+        numel = 1
+        for d in shape:
+            numel *= d
+        if len(shape) >= 2:
+            val = u * (1.0 / (numel / shape[0]) ** 0.5)
+            if name.startswith("prediction_model."):
+                val = val * 0.05                                         # keeps the initial scores O(1): softmax not saturated
+        else:
+            w = shapes.get(name[:-len("bias")] + "weight") if name.endswith("bias") else None
+            if w is not None and len(w) >= 2:                            # conv / linear bias
+                wn = 1
+                for d in w:
+                    wn *= d
+                val = u * (1.0 / (wn / w[0]) ** 0.5)
+            elif name.endswith("weight"):                                # batch-norm scale
+                val = 1.0 + 0.2 * u
+            else:                                                        # batch-norm shift
+                val = 0.1 * u
+        out[name] = val
+    return out
+
+
+def reseed_parameters(named_parameters, name_map=None):
+    """Overwrite parameters in place with ``seeded_values``.  ``name_map`` (reference key -> own key) lets a model
+    with different parameter names (OracleE24) take the values of the reference's keys."""
+    named = dict(named_parameters)
+    if name_map is None:
+        name_map = {n: n for n in named}
+    assert set(name_map.values()) == set(named), set(name_map.values()) ^ set(named)
+    values = seeded_values({ref: tuple(named[own].shape) for ref, own in name_map.items()})
+    with torch.no_grad():
+        for ref, own in name_map.items():
+            named[own].copy_(values[ref].to(named[own].device))
+
+
+def subsample_index(name, numel, count=8192):
+    """Sorted, seeded subset of flat indices (all of them when the tensor is small) used to store gradients /
+    parameters of the full-size model compactly."""
+    if numel <= count:
+        return torch.arange(numel)
+    g = torch.Generator().manual_seed(_name_seed(name, 1))
+    return torch.sort(torch.randperm(numel, generator=g)[:count]).values
+
+
+def e24_audio(batch, length=97024, seed=1234):
+    """The BASELINE synthetic input: 0.1 * randn, seeded."""
+    return 0.1 * torch.randn(batch, length, generator=torch.Generator().manual_seed(seed))
+
+
+def oracle_e24_name_map():
+    """reference state_dict key -> OracleE24 parameter name (e24: arch 7 as imported + ar_conv_architecture_3)."""
+    m = {}
+    main = {0: {0: 'conv_a', 1: 'bn_a', 5: 'conv_b', 6: 'bn_b'}, 1: {0: 'conv_a', 1: 'bn_a', 4: 'conv_b', 5: 'bn_b'},
+            2: {0: 'conv_a', 1: 'bn_a', 4: 'conv_b', 5: 'bn_b'}, 3: {0: 'conv_a', 3: 'conv_b'}}
+    res_idx = {0: 1, 1: 1, 2: 1, 3: 0}
+    for b, mods in main.items():
+        for idx, ours in mods.items():
+            for leaf in ('weight', 'bias'):
+                m['encoder.blocks.%d.main_modules.%d.%s' % (b, idx, leaf)] = 'blocks.%d.%s.%s' % (b, ours, leaf)
+        m['encoder.blocks.%d.residual_modules.%d.weight' % (b, res_idx[b])] = 'blocks.%d.res.weight' % b
+    pooling = [1, 1, 2, 1, 2, 1]
+    chans = [512, 512, 512, 256, 256, 256, 256]
+    for l, pool in enumerate(pooling):
+        c = 1 if pool > 1 else 0
+        for leaf in ('weight', 'bias'):
+            m['autoregressive_model.module_list.%d.main_modules.%d.%s' % (l, c, leaf)] = 'ar.convs.%d.%s' % (l, leaf)
+            m['autoregressive_model.module_list.%d.main_modules.%d.%s' % (l, c + 1, leaf)] = 'ar.bns.%d.%s' % (l, leaf)
+            if chans[l] != chans[l + 1]:
+                m['autoregressive_model.module_list.%d.residual_modules.%d.%s' % (l, c, leaf)] = 'ar.skips.%d.%s' % (l, leaf)
+    m['prediction_model.weight'] = 'predict.weight'
+    return m

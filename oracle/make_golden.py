@@ -17,6 +17,8 @@ ml_utilities / matplotlib).  Everything saved here is an output of the reference
                    reference's code computing loss and gradients)
   sampler.npz      FileBatchSampler index streams for several (counts, batch, file_batch, seed) settings
   configs.json     as-imported experiment dicts e24 / e25 / e20 (classes replaced by their names)
+  e24_step.npz     BASELINE configs[1] at full item length: setup_model(experiments['e24']) trained for two Adam steps by
+                   the reference's train() (losses, encoder output, gradient / parameter subsamples)
 """
 import json
 import os
@@ -410,6 +412,164 @@ def golden_validate(ref):
     np.savez_compressed(os.path.join(OUT, "validate.npz"), **out)
 
 
+def _run_e24(ref, audio_seed, perturb=0.0, batch=4):
+    """One run of the reference on experiments['e24']: setup_model, seeded weights, train() for two Adam steps.
+    ``perturb`` > 0 multiplies the scalogram by (1 + perturb * randn): the conditioning probe (see golden_e24)."""
+    import importlib
+    import cpc_oracle_model as OM
+    cfg = ref_shim.load_reference_configs()
+    sf = importlib.import_module("setup_functions")
+    am, cet = ref["audio_model"], ref["contrastive_estimation_training"]
+
+    def ar_block_forward(self, x):                       # audio_model.py:124-136 with `main_x = main_x + ...`
+        original_x = x
+        for m in self.main_modules:
+            x = m(x)
+        main_x = x
+        if self.residual:
+            x = original_x
+            for m in self.residual_modules:
+                x = m(x)
+            main_x = main_x + x[:, :, -main_x.shape[2]:]
+        self.output_activation_writer(main_x)
+        return main_x
+
+    saved_forward = am.ConvolutionalArBlock.forward
+    am.ConvolutionalArBlock.forward = ar_block_forward
+    try:
+        e = cfg.experiments['e24']
+        tc = e['training_config']
+        torch.manual_seed(0)
+        model, pre, _ = sf.setup_model(cqt_params=e['cqt_config'], encoder_params=e['encoder_config'],
+                                       ar_params=e['ar_model_config'], trainer_args=tc, device=None)
+        OM.reseed_parameters(model.named_parameters())
+        run = {"model": model, "tc": tc, "names": [n for n, _ in model.named_parameters()],
+               "before": {n: p.detach().clone() for n, p in model.named_parameters()}}
+        items = OM.e24_audio(2 * batch, model.item_length, seed=audio_seed)
+        captured = run["captured"] = {}
+
+        class RecordingAdam(torch.optim.Adam):
+            def step(self, closure=None):
+                if "grads" not in captured:
+                    captured["grads"] = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+                return super().step(closure)
+
+        order = run["order"] = []
+
+        class LoggingDataset(ListDataset):
+            def __getitem__(self, i):
+                order.append(int(i))
+                return self.items[i]
+
+        def keep(key):
+            def hook(module, inputs, output):                    # must return None: a returned value replaces the output
+                if key not in captured:
+                    captured[key] = output.detach().clone()
+            return hook
+
+        hooks = [model.encoder.register_forward_hook(keep("z")), pre.register_forward_hook(keep("scal"))]
+        preprocessing = pre
+        if perturb > 0:
+            noise_gen = torch.Generator().manual_seed(99)
+
+            class Perturbed(torch.nn.Module):
+                def forward(self, x):
+                    y = pre(x)
+                    return y * (1 + perturb * torch.randn(y.shape, generator=noise_gen))
+
+            preprocessing = Perturbed()
+        logger = run["logger"] = CaptureLogger()
+        trainer = cet.ContrastiveEstimationTrainer(model=model, dataset=LoggingDataset(items), logger=logger, device=None,
+                                                   optimizer=RecordingAdam, regularization=tc['regularization'],
+                                                   prediction_noise=tc['prediction_noise'], file_batch_size=1,
+                                                   score_over_all_timesteps=tc['score_over_all_timesteps'],
+                                                   score_function=tc['score_function'],
+                                                   wasserstein_gradient_penalty=tc['wasserstein_gradient_penalty'],
+                                                   gradient_penalty_factor=tc['gradient_penalty_factor'],
+                                                   preprocessing=preprocessing, prediction_steps=tc['prediction_steps'],
+                                                   ar_size=model.ar_size)
+        random.seed(0)
+        trainer.train(batch_size=batch, epochs=1, lr=tc['learning_rate'], num_workers=0, max_steps=1 if perturb > 0 else 2)
+        for h in hooks:
+            h.remove()
+        run["items"] = items
+    finally:
+        am.ConvolutionalArBlock.forward = saved_forward
+    return run
+
+
+def golden_e24(ref):
+    """BASELINE configs[1] itself: the reference's setup_model(experiments['e24']) (CQT+phase -> resnet arch 7 ->
+    ConvolutionalArModel arch 3 -> Linear 256 -> 16*512) at the full item length L = 97 024, batch 4, trained by the
+    reference's own ContrastiveEstimationTrainer.train() for two Adam steps (lr 1e-4, the experiment's settings:
+    linear score, all-steps softmax, regularization 0).  Stored: both logged losses / max scores, the encoder output
+    and scalogram statistics of step 1, every parameter gradient of step 1 (seeded 8192-entry subsamples + full norms)
+    and every parameter after step 2 (same subsamples).  Weights and audio are NOT stored: they are regenerated from
+    seeds by oracle/cpc_oracle_model.py (reseed_parameters / e24_audio), which this script uses too.
+
+    One line of the reference cannot run on torch >= 1.5: audio_model.py:133 adds the residual IN PLACE onto a ReLU
+    output (autograd error in backward).  The forward of that block is replaced here by the same statements with the
+    add written out of place -- numerically identical.
+
+    Conditioning (measured here, stored as ``sn6.<name>`` / ``sn7.<name>``).  The gradients of a ReLU / max-pool network
+    are discontinuous in the activations: a pre-activation within rounding distance of zero gates its whole downstream
+    gradient on or off.  The log-power scalogram sits around -14 with ulp 9.5e-7 while its informative spread is ~1.3, so
+    ANY independent evaluation of CQT + log (other summation order, other log) differs from the reference by ~1 ulp on
+    many entries -- and the reference's OWN gradients move by 2e-3 ... 1e-2 (encoder, first AR layers) when its scalogram is
+    multiplied by (1 + 1e-7 * randn) resp. (1 + 1e-6 * randn), or when only its CPU thread count changes (a gate at
+    3.8e-7 in AR layer 1 flips between 1 and 8 threads: 8e-3 on every encoder gradient).  Sixteen audio seeds all behave
+    the same.  A 1e-3 bound on these gradients is therefore not a property any implementation can have; the tests hold
+    forward quantities (scalogram, encoder output, loss, max score) to 1e-3 and each gradient to
+    max(1e-3, 3 x the reference's self-noise at 1e-6)."""
+    import cpc_oracle_model as OM
+    audio_seed = 1234
+    run = _run_e24(ref, audio_seed)
+    keys = set(run["model"].state_dict().keys())
+    shadowed = set()
+    for k in keys:                                                # conv bias directly in front of a batch norm: true gradient 0
+        if k.endswith(".bias"):
+            head, idx = k[:-len(".bias")].rsplit(".", 1)
+            if idx.isdigit() and ("%s.%d.running_mean" % (head, int(idx) + 1)) in keys:
+                shadowed.add(k)
+    noises = {}
+    for tag, eps in (("sn6", 1e-6), ("sn7", 1e-7)):
+        probe = _run_e24(ref, audio_seed, perturb=eps)
+        noises[tag] = {}
+        for n in run["names"]:
+            a, b = run["captured"]["grads"][n].double(), probe["captured"]["grads"][n].double()
+            noises[tag][n] = float((a - b).norm() / a.norm().clamp_min(1e-30))
+        print(tag, "worst self-noise %.2e" % max(v for n, v in noises[tag].items() if n not in shadowed))
+    model, tc, names, captured, logger = run["model"], run["tc"], run["names"], run["captured"], run["logger"]
+    items, order, before = run["items"], run["order"], run["before"]
+    batch = 4
+    scal = captured["scal"].detach()
+    out = {"item_length": np.array(model.item_length), "batch": np.array(batch), "lr": np.array(tc['learning_rate']),
+           "audio_seed": np.array(audio_seed),
+           "order": np.array(order), "losses": np.array(logger.losses), "max_scores": np.array(logger.scores),
+           "audio_check": items[:, ::4099].numpy().copy(),
+           "z": captured["z"].numpy(), "scal_shape": np.array(scal.shape),
+           "scal_power_sub": scal[:, 0, ::7, ::11].numpy().copy(), "scal_phase_sub": scal[:, 1, ::7, ::11].numpy().copy(),
+           "scal_power_norm": np.array(float(scal[:, 0].double().norm())),
+           "names": np.array(json.dumps(names)), "bn_shadowed": np.array(json.dumps(sorted(shadowed))),
+           "score_kind": np.array(tc['score_function'].__name__), "all_steps": np.array(bool(tc['score_over_all_timesteps'])),
+           "regularization": np.array(float(tc['regularization'])),
+           "prediction_steps": np.array(int(tc['prediction_steps'])), "visible_steps": np.array(int(tc['visible_steps']))}
+    after = dict(model.named_parameters())
+    for n in names:
+        idx = OM.subsample_index(n, before[n].numel())
+        g = captured["grads"][n]
+        out["g." + n] = g.reshape(-1)[idx].numpy().copy()
+        out["gn." + n] = np.array(float(g.double().norm()))
+        out["sn6." + n] = np.array(noises["sn6"][n])
+        out["sn7." + n] = np.array(noises["sn7"][n])
+        out["p2." + n] = after[n].detach().reshape(-1)[idx].numpy().copy()
+    for k, v in model.state_dict().items():                       # batch-norm running statistics after two steps
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            out["bn." + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "e24_step.npz"), **out)
+    print("e24 golden: audio seed", audio_seed, "losses", logger.losses, "max scores", logger.scores, "order", order)
+
+
 def golden_sampler(ref):
     ad = ref["audio_dataset"]
     out, cases = {}, []
@@ -447,6 +607,44 @@ def golden_configs():
         json.dump(dump, fh, indent=1, sort_keys=True)
 
 
+def build_all_experiments(experiments, setup_model):
+    """Build every experiment of configs/experiment_configs.py in dict order through ``setup_model`` (the configs alias
+    and mutate shared dicts, so order matters) -> {name: {'item_length', 'params': {key: shape}, 'buffers': [...]} |
+    {'error': exception type}}.  Used for the reference here and for the compat/ shims in tests/test_compat_configs.py."""
+    out = {}
+    for name, e in experiments.items():
+        if not isinstance(e, dict) or 'encoder_config' not in e:
+            continue                                              # classification experiments (c1, c2): other workload
+        try:
+            tc = e['training_config']
+            model, pre, _ = setup_model(cqt_params=e['cqt_config'], encoder_params=e['encoder_config'],
+                                        ar_params=e['ar_model_config'], trainer_args=tc, device=None)
+            sd = model.state_dict()
+            params = {n for n, _ in model.named_parameters()}
+            out[name] = {"item_length": int(model.item_length),
+                         "params": {k: list(v.shape) for k, v in sd.items() if k in params},
+                         "buffers": sorted(k for k in sd if k not in params),
+                         "preprocessing": {k: list(v.shape) for k, v in pre.state_dict().items()},
+                         "score_function": tc['score_function'].__name__,
+                         "encoder": type(model.encoder).__name__, "ar": type(model.autoregressive_model).__name__}
+        except Exception as exc:                                   # noqa: BLE001 -- the reference's own failures are data here
+            out[name] = {"error": type(exc).__name__}
+    return out
+
+
+def golden_configs_all(ref=None):
+    """Every experiment the reference's configs define (e0 ... e32, default, *_local), built by the reference's own
+    setup_model: item length, parameter names / shapes, buffer names.  tests/test_compat_configs.py builds the same
+    experiments from the UNCHANGED reference configs against the product through compat/ and compares."""
+    import importlib
+    cfg = ref_shim.load_reference_configs()
+    sf = importlib.import_module("setup_functions")
+    out = build_all_experiments(cfg.experiments, sf.setup_model)
+    with open(os.path.join(OUT, "configs_all.json"), "w") as fh:
+        json.dump(out, fh, indent=0, sort_keys=True)
+    print({k: (v.get("item_length") or v.get("error")) for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -464,6 +662,8 @@ def main():
     golden_cqt_grad(ref)
     golden_snapshot(ref)
     golden_scalogram_encoder(ref)
+    golden_e24(ref)
+    golden_configs_all(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -887,6 +887,77 @@ def test_experiment_configs_train_one_step(cpc, name):
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
 
 
+@pytest.mark.parametrize("graphed", [False, True])
+def test_e24_full_size_training_steps_match_reference_golden(cpc, graphed):
+    """BASELINE configs[1] itself, at the full item length, on the path bench.py measures (tensor-core CQT, block-tail
+    nodes, single-kernel Adam, optionally the whole step as one CUDA graph): two training steps of
+    setup_model(experiments['e24']) against the reference's own setup_model + train() (tests/golden/e24_step.npz,
+    oracle/make_golden.py::golden_e24).  Scalogram, encoder output, loss and max score are held to 1e-3; gradients to
+    max(1e-3, 3 x the self-noise the reference shows under a 1-ulp-sized change of its scalogram) -- see
+    tests/test_oracle_golden.py::check_e24_against_golden."""
+    import cpc_oracle_model as OM
+    from test_oracle_golden import check_e24_against_golden
+    g = load_golden("e24_step.npz")
+    names = json.loads(str(g["names"]))
+    exp = cpc.configs.experiment("e24")
+    tc = exp["training_config"]
+    torch.manual_seed(0)
+    dev = torch.device(DEV)
+    model, pre, _ = cpc.configs.setup_model(exp["cqt_config"], exp["encoder_config"], exp["ar_model_config"], tc, device=dev)
+    assert model.item_length == int(g["item_length"])
+    assert [n for n, _ in model.named_parameters()] == names         # same state_dict keys, same order as the reference
+    OM.reseed_parameters(model.named_parameters())
+    assert tc["score_function"] is cpc.linear_score_function and str(g["score_kind"]) == "linear_score_function"
+    assert bool(tc["score_over_all_timesteps"]) == bool(g["all_steps"]) and tc["regularization"] == float(g["regularization"])
+    trainer = cpc.ContrastiveEstimationTrainer(model=model, dataset=None, device=dev, regularization=tc["regularization"],
+                                               score_over_all_timesteps=tc["score_over_all_timesteps"],
+                                               score_function=tc["score_function"], preprocessing=pre,
+                                               prediction_steps=tc["prediction_steps"], verbose=False)
+    batch, order = int(g["batch"]), [int(i) for i in g["order"]]
+    audio = OM.e24_audio(2 * batch, model.item_length, seed=int(g["audio_seed"]))
+    assert np.array_equal(audio[:, ::4099].numpy(), g["audio_check"])
+    batches = [audio[order[i * batch:(i + 1) * batch]] for i in range(2)]
+    # the scalogram the encoder sees
+    scal = pre(batches[0].to(dev).unsqueeze(1))
+    assert tuple(scal.shape) == tuple(int(v) for v in g["scal_shape"])
+    assert rel_err(scal[:, 0, ::7, ::11], g["scal_power_sub"]) < TOL
+    scale = pre.phase_diff.scaling.reshape(-1).cpu()[::7]
+    assert phase_err_fraction(scal[:, 1, ::7, ::11], g["scal_phase_sub"], scale) < 2e-3
+    model.train()
+    opt = trainer.make_optimizer(float(g["lr"]))
+    assert isinstance(opt, cpc.optim.Adam)
+    seen = {}
+    hook = model.encoder.register_forward_hook(lambda m, i, o: seen.__setitem__("z", o.detach()))
+    losses, maxes = [], []
+    if graphed:
+        step = cpc.GraphedTrainStep(trainer, opt, (batch, model.item_length), warmup=2)
+        for i, x in enumerate(batches):
+            loss, mx = step(x.pin_memory())
+            torch.cuda.synchronize()
+            losses.append(loss.item())
+            maxes.append(mx.item())
+            if i == 0:
+                grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+                z1 = seen["z"].clone()                          # the graph's static encoder output, rewritten every replay
+    else:
+        for i, x in enumerate(batches):
+            loss, mx = trainer.loss_on_batch(x.to(dev))
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if i == 0:
+                grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+                z1 = seen["z"].clone()
+            opt.step()
+            losses.append(loss.item())
+            maxes.append(mx.item())
+    hook.remove()
+    report = check_e24_against_golden(g, names, losses, maxes, z1, grads, dict(model.named_parameters()), tol=TOL,
+                                      update_tol=2e-2)
+    worst = sorted(((v[0], v[1], k) for k, v in report.items() if not k.startswith("__")), reverse=True)[:3]
+    print("e24 golden (graphed=%s): losses %s vs %s; worst gradient errors %s; update mismatch %.4f"
+          % (graphed, losses, g["losses"].tolist(), worst, report["__update_mismatch_fraction"][0]))
+
+
 # ---------------------------------------------------------------------------------------------------
 # block tail: bn + relu + tall conv + bn (+ residual) + relu as one autograd node with packed intermediates
 # ---------------------------------------------------------------------------------------------------

@@ -326,6 +326,42 @@ loss.backward()
 ddp.allreduce_gradients([p for p in model.parameters()], world, bucket_mb=0.0005)
 for p, q in zip(model.parameters(), ref.parameters()):
     assert torch.allclose(p.grad, q.grad, atol=1e-6), (p.grad - q.grad).abs().max()
+# ShardedBatchSampler: every rank sees rank 0's batches (drawn from rank 0's unseeded global `random`), takes its slice
+import random
+from cpc_b200.sampler import FileBatchSampler
+random.seed(100 + rank)                                      # ranks deliberately start from different random states
+base = FileBatchSampler([24], batch_size=8, file_batch_size=1, drop_last=True)
+if rank == 0:
+    random.seed(100)
+    expect = [list(b) for b in FileBatchSampler([24], batch_size=8, file_batch_size=1, drop_last=True)]
+    random.seed(100)
+else:
+    expect = None
+box = [expect]
+dist.broadcast_object_list(box, src=0)
+expect = box[0]
+mine = list(ddp.ShardedBatchSampler(base, rank, world))
+assert mine == [b[rank * 4:(rank + 1) * 4] for b in expect], (mine, expect)
+# a NaN on one rank makes every rank leave train() before the optimizer touches the weights
+import cpc_b200
+class Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.ones(3))
+    def forward(self, batch):
+        return self.w, batch
+class ToyTrainer(cpc_b200.ContrastiveEstimationTrainer):
+    def loss_on_batch(self, batch):
+        loss = (self.model.w ** 2).sum() * (float("nan") if self.rank == 1 else 1.0)
+        return loss, loss.detach()
+class Items(torch.utils.data.Dataset):
+    def __len__(self): return 16
+    def __getitem__(self, i): return torch.zeros(4)
+    def get_example_count_per_file(self): return [16]
+toy = Toy()
+trainer = ToyTrainer(model=toy, dataset=Items(), device=torch.device("cpu"), optimizer=torch.optim.SGD, verbose=False)
+out = trainer.train(batch_size=8, epochs=1, lr=0.1, num_workers=0, max_steps=3)
+assert out is None and trainer.training_step == 0 and bool((toy.w == 1).all()), (trainer.training_step, toy.w)
 dist.barrier()
 print("RANK_OK", rank)
 '''
@@ -389,10 +425,14 @@ def test_literal_loss_block_and_small_helpers():
             assert abs(float(mx) - float(want_mx)) < 1e-6
     # the inverse-square-distance score (:25-33) keeps its (B, K, B, K) contract
     assert tuple(cpc_b200.difference_score_function(pred, tgt).shape) == (5, 4, 5, 4)
-    sampler = cpc_b200.DeterministicSampler(list(range(10)), batch_size=4, drop_last=True)
-    assert list(sampler) == [[0, 1, 2, 3], [4, 5, 6, 7]] and len(sampler) == 2
-    sampler = cpc_b200.DeterministicSampler(list(range(10)), batch_size=4, drop_last=False)
-    assert list(sampler)[-1] == [8, 9] and len(sampler) == 3
+    # DeterministicSampler (:363-382): single indices, shuffled by random.seed(seed), the same order on every pass
+    import random
+    sampler = cpc_b200.DeterministicSampler(list(range(10)), seed=3)
+    want = list(range(10))
+    random.seed(3)
+    random.shuffle(want)
+    assert list(sampler) == want and list(sampler) == want and len(sampler) == 10 and want != list(range(10))
+    assert list(cpc_b200.DeterministicSampler(list(range(10)))) == list(cpc_b200.DeterministicSampler(list(range(10)), seed=0))
     enc = cpc_b200.AudioEncoder()
     assert cpc_b200.num_parameters(enc) == sum(p.numel() for p in enc.parameters())
     assert enc.receptive_field == 465 and enc.downsampling_factor == 160

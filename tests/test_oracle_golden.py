@@ -242,3 +242,87 @@ def test_validation_metrics_match_reference_validate():
         assert abs(float(score) - float(g[t + ".score"])) < 1e-5 * max(1.0, abs(float(g[t + ".score"]))), c
         n = c["b"] * c["k"] if c["all_steps"] else c["b"]
         assert torch.allclose(math.log(n) - losses, torch.from_numpy(g[t + ".mi"]), rtol=1e-5, atol=1e-5), c
+
+
+def check_e24_against_golden(g, names, losses, max_scores, z, grads, params_after, tol, update_tol):
+    """Shared by the CPU oracle pin below and the GPU parity test: ``names`` are the reference's state_dict keys,
+    ``grads`` / ``params_after`` map them to full tensors (step-1 gradients, parameters after the second Adam step).
+
+    Forward quantities are held to ``tol``.  Each gradient is held to max(tol, 3 x the reference's own self-noise):
+    make_golden.py measured how far the reference's gradients move when its scalogram changes by 1e-7 / 1e-6 relative
+    (about one fp32 ulp of the log-power values) -- ReLU gates near zero make them move by up to 1e-2 (``sn6.*``,
+    ``sn7.*`` in the fixture), so no independent implementation can be closer than that to one particular run."""
+    import cpc_oracle_model as OM
+    assert abs(losses[0] - float(g["losses"][0])) < tol * abs(float(g["losses"][0])), (losses, g["losses"])
+    assert abs(max_scores[0] - float(g["max_scores"][0])) < tol * abs(float(g["max_scores"][0])), (max_scores, g["max_scores"])
+    assert rel_err(z, g["z"]) < tol
+    shadowed = set(json.loads(str(g["bn_shadowed"])))
+    report = {}
+    for n in names:
+        idx = OM.subsample_index(n, grads[n].numel())
+        ref = torch.from_numpy(g["g." + n]).double()
+        mine = grads[n].detach().reshape(-1).cpu()[idx].double()
+        if n in shadowed:
+            # conv bias in front of a train-mode batch norm: the true gradient is exactly zero, both sides hold rounding noise
+            assert float(mine.abs().max()) < 1e-3 * max(1.0, float(ref.abs().max()) * 1e3), n
+            continue
+        err = float((mine - ref).norm() / ref.norm().clamp_min(1e-30))
+        bound = max(tol, 3.0 * max(float(g["sn6." + n]), float(g["sn7." + n])))
+        report[n] = (err, bound)
+        assert err < bound, (n, err, bound)
+        full = float(grads[n].detach().double().norm())
+        assert abs(full - float(g["gn." + n])) < bound * float(g["gn." + n]), (n, full, float(g["gn." + n]))
+    # second step: Adam has moved every weight by ~lr * sign(gradient); the second loss and the parameters see it
+    assert abs(losses[1] - float(g["losses"][1])) < update_tol * abs(float(g["losses"][1])), (losses, g["losses"])
+    lr = float(g["lr"])
+    moved_wrong = 0.0
+    total = 0
+    for n in names:
+        idx = OM.subsample_index(n, params_after[n].numel())
+        ref = torch.from_numpy(g["p2." + n]).double()
+        mine = params_after[n].detach().reshape(-1).cpu()[idx].double()
+        assert float((mine - ref).abs().max()) < 4.5 * lr, n           # two Adam steps move an entry by at most ~2 lr each side
+        if n not in shadowed:
+            moved_wrong += float(((mine - ref).abs() > 0.25 * lr).double().sum())
+            total += len(idx)
+    report["__update_mismatch_fraction"] = (moved_wrong / total, 0.02)
+    assert moved_wrong / total < 0.02                                  # entries whose two-step Adam update disagrees by > lr/4
+    return report
+
+
+def test_oracle_e24_full_size_step_matches_reference():
+    """BASELINE configs[1] at full item length (L = 97 024, batch 4): OracleE24 -- the CPU arm bench.py times --
+    against two training steps of the reference's setup_model(experiments['e24']) + train() (e24_step.npz)."""
+    import cpc_oracle_model as OM
+    g = load_golden("e24_step.npz")
+    names = json.loads(str(g["names"]))
+    torch.manual_seed(0)
+    model = OM.OracleE24(int(g["visible_steps"]), int(g["prediction_steps"]))
+    assert model.item_length == int(g["item_length"])
+    name_map = OM.oracle_e24_name_map()
+    assert sorted(name_map) == sorted(names)
+    OM.reseed_parameters(model.named_parameters(), name_map)
+    own = dict(model.named_parameters())
+    batch, order = int(g["batch"]), [int(i) for i in g["order"]]
+    audio = OM.e24_audio(2 * batch, model.item_length)
+    assert np.array_equal(audio[:, ::4099].numpy(), g["audio_check"])
+    assert str(g["score_kind"]) == "linear_score_function" and bool(g["all_steps"]) and float(g["regularization"]) == 0.0
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]))
+    model.train()
+    losses, maxes, grads, z1 = [], [], None, None
+    for step in range(2):
+        pred, targets = model(audio[order[step * batch:(step + 1) * batch]])
+        loss, mx = O.infonce_loss(pred, targets, True, "linear", 0.0)
+        model.zero_grad()
+        loss.backward()
+        if step == 0:
+            grads = {ref: own[o].grad.detach().clone() for ref, o in name_map.items()}
+            z1 = model.last_z.clone()
+        opt.step()
+        losses.append(float(loss.detach()))
+        maxes.append(float(mx))
+    report = check_e24_against_golden(g, names, losses, maxes, z1, grads, {ref: own[o] for ref, o in name_map.items()},
+                                      tol=1e-4, update_tol=2e-2)
+    print("oracle e24: losses", losses, "worst gradient error",
+          max(((k, v) for k, v in report.items() if not k.startswith("__")), key=lambda kv: kv[1][0]),
+          "update mismatch fraction", report["__update_mismatch_fraction"][0])

@@ -21,7 +21,7 @@ def sources():
 def _digest():
     h = hashlib.sha256()
     inc = os.path.join(HERE, "..", "include", "cpc_b200.h")
-    for f in sorted(os.listdir(CSRC)):
+    for f in sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))):
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode()); h.update(fh.read())
     with open(inc, "rb") as fh:

@@ -13,8 +13,11 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcpc_b200.so")
 CQT_MAX_GROUPS = 16
 CQT_COMPLEX, CQT_LOGPOW, CQT_LOGPOW_PHASE = 0, 1, 2
 SCORE_LINEAR, SCORE_SOFTPLUS = 0, 1
+CQT_FLAG_NO_TENSOR = 1
+CONV_FLAG_CUDA_CORE, CONV_FLAG_NO_TALL, CONV_FLAG_NO_SMALLK, CONV_FLAG_NO_FUSED_DGRAD = 1, 2, 4, 8
+INFONCE_FLAG_NO_TENSOR = 1
 INFONCE_OUT_FLOATS = 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class CqtParams(ctypes.Structure):
@@ -25,7 +28,7 @@ class CqtParams(ctypes.Structure):
                 ("bin_hi", ctypes.c_int32 * CQT_MAX_GROUPS), ("weight_offset", ctypes.c_int64 * CQT_MAX_GROUPS),
                 ("mode", ctypes.c_int32), ("pool_t", ctypes.c_int32),
                 ("eps", ctypes.c_float), ("log_offset", ctypes.c_float), ("norm", ctypes.c_float),
-                ("power", ctypes.c_float)]
+                ("power", ctypes.c_float), ("flags", ctypes.c_int32)]
 
 
 class ConvParams(ctypes.Structure):
@@ -33,7 +36,8 @@ class ConvParams(ctypes.Structure):
                 ("w_in", ctypes.c_int32), ("c_out", ctypes.c_int32), ("h_out", ctypes.c_int32),
                 ("w_out", ctypes.c_int32), ("kh", ctypes.c_int32), ("kw", ctypes.c_int32),
                 ("stride_h", ctypes.c_int32), ("stride_w", ctypes.c_int32), ("pad_top", ctypes.c_int32),
-                ("pad_left", ctypes.c_int32), ("relu", ctypes.c_int32), ("precision", ctypes.c_int32)]
+                ("pad_left", ctypes.c_int32), ("relu", ctypes.c_int32), ("precision", ctypes.c_int32),
+                ("flags", ctypes.c_int32)]
 
 
 class BnParams(ctypes.Structure):
@@ -53,7 +57,7 @@ class InfoNceParams(ctypes.Structure):
     _fields_ = [("batch", ctypes.c_int32), ("steps", ctypes.c_int32), ("enc", ctypes.c_int32),
                 ("all_steps", ctypes.c_int32), ("score_kind", ctypes.c_int32), ("regularization", ctypes.c_float),
                 ("tgt_stride_b", ctypes.c_int64), ("tgt_stride_e", ctypes.c_int64), ("tgt_stride_k", ctypes.c_int64),
-                ("precision", ctypes.c_int32)]
+                ("precision", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 class AdamParams(ctypes.Structure):
@@ -71,6 +75,9 @@ SIGNATURES = {
     "cpc_launch_count_reset": (None, []),
     "cpc_cqt_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(CqtParams)]),
     "cpc_cqt_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.POINTER(CqtParams), _P, ctypes.c_size_t, _P]),
+    "cpc_cqt_packed_filter_bytes": (ctypes.c_size_t, [ctypes.POINTER(CqtParams)]),
+    "cpc_cqt_pack_filters": (ctypes.c_int, [_P, _P, ctypes.POINTER(CqtParams), _P]),
+    "cpc_cqt_fwd_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(CqtParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvParams), ctypes.c_int]),
     "cpc_conv_fwd": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_dgrad": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),

@@ -12,7 +12,23 @@ import math
 import torch
 import torch.nn as nn
 
+from . import ops
 from .model import ActivationWriter
+
+
+class ArConv1d(nn.Conv1d):
+    """``nn.Conv1d`` of the AR models (same parameters / state_dict keys).  On a B200 in the fp32 parity mode its
+    forward / backward run on the same fp32-faithful tcgen05 implicit-GEMM kernels as the encoder instead of cuDNN --
+    cuDNN's fp32 path is either TF32 (not fp32: 10-bit mantissa) or CUDA-core FMA (2.8 ms of a 14 ms e24 step).  Any
+    other input (CPU tensors, other dtypes, dilation / groups) takes the stock torch path: the AR model is caller-side
+    code and stays usable everywhere."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and self.groups == 1 and self.dilation == (1,)
+                and self.padding_mode == 'zeros' and not isinstance(self.padding, str) and self.in_channels >= 16
+                and not ops.second_order_enabled()):
+            return ops.conv1d(x, self.weight, self.bias, self.stride[0], self.padding[0])
+        return super().forward(x)
 
 
 class AudioGRUModel(nn.Module):
@@ -40,7 +56,7 @@ class ConvolutionalArBlock(nn.Module):
         self.main_modules = nn.ModuleList()
         if pooling > 1:
             self.main_modules.append(nn.MaxPool1d(pooling, ceil_mode=True))
-        self.main_modules.append(nn.Conv1d(in_channels, out_channels, kernel_size, stride=stride, bias=bias))
+        self.main_modules.append(ArConv1d(in_channels, out_channels, kernel_size, stride=stride, bias=bias))
         if batch_norm:
             self.main_modules.append(nn.BatchNorm1d(out_channels))
         self.main_modules.append(nn.ReLU())
@@ -51,7 +67,7 @@ class ConvolutionalArBlock(nn.Module):
             if pooling * stride > 1:
                 self.residual_modules.append(nn.MaxPool1d(pooling * stride, ceil_mode=True))
             if in_channels != out_channels:
-                self.residual_modules.append(nn.Conv1d(in_channels, out_channels, kernel_size=1))
+                self.residual_modules.append(ArConv1d(in_channels, out_channels, kernel_size=1))
         self.output_activation_writer = ActivationWriter(register=activation_register, name=self.name)
 
     def forward(self, x):

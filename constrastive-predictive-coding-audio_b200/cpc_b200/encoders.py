@@ -200,9 +200,11 @@ class ScalogramEncoder(nn.Module):
         elif self.phase:
             x = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW_PHASE,
                                  phase_fixed=self.phase_diff.fixed_phase_diff.reshape(-1),
-                                 phase_scale=self.phase_diff.scaling.reshape(-1), eps=1e-9)
+                                 phase_scale=self.phase_diff.scaling.reshape(-1), eps=1e-9,
+                                 packed_filters=self.cqt.tensor_core_filters())
         else:
-            x = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW, eps=1e-9)
+            x = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW, eps=1e-9,
+                                 packed_filters=self.cqt.tensor_core_filters())
         x = _run_modules(self.module_list, x)
         return x.squeeze(2)
 

@@ -137,7 +137,15 @@ class CQT(nn.Module):
             with torch.no_grad():
                 self._packed = torch.cat([c.weight.detach().reshape(-1) for c in self.conv_modules]).contiguous()
             self._packed_key = key
+            self._tensor_filters = None
         return self._packed
+
+    def tensor_core_filters(self):
+        """The filterbank as the tensor-core kernel reads it (``ops.cqt_pack_filters``), cached with the weights."""
+        weights = self.packed_weights()
+        if getattr(self, "_tensor_filters", None) is None:
+            self._tensor_filters = (ops.cqt_pack_filters(weights, self.kernel_plan()),)
+        return self._tensor_filters[0]
 
     def needs_autograd(self, x):
         """True when a gradient must flow through the transform: a trainable filterbank (``trainable_cqt``) or an
@@ -160,7 +168,8 @@ class CQT(nn.Module):
     def forward(self, x):
         if self.needs_autograd(x):
             return self.forward_differentiable(x)
-        return ops.cqt_frontend(x, self.packed_weights(), self.kernel_plan(), _lib.CQT_COMPLEX)
+        return ops.cqt_frontend(x, self.packed_weights(), self.kernel_plan(), _lib.CQT_COMPLEX,
+                                packed_filters=self.tensor_core_filters())
 
 
 class InverseCQT(nn.Module):
@@ -294,11 +303,12 @@ class PreprocessingModule(nn.Module):
             y = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW_PHASE,
                                  phase_fixed=self.phase_diff.fixed_phase_diff.reshape(-1),
                                  phase_scale=self.phase_diff.scaling.reshape(-1), pool_t=pool_t, eps=self.offset,
-                                 log_offset=self.log_offset, norm=self.normalization_factor, power=self.output_power)
+                                 log_offset=self.log_offset, norm=self.normalization_factor, power=self.output_power,
+                                 packed_filters=self.cqt.tensor_core_filters())
         else:
             y = ops.cqt_frontend(x, self.cqt.packed_weights(), self.cqt.kernel_plan(), _lib.CQT_LOGPOW, pool_t=pool_t,
                                  eps=self.offset, log_offset=self.log_offset, norm=self.normalization_factor,
-                                 power=self.output_power)
+                                 power=self.output_power, packed_filters=self.cqt.tensor_core_filters())
         self.output = y
         return y
 

@@ -27,6 +27,14 @@ def get_default_precision():
     return _default_precision
 
 
+def strict_fp32_libraries():
+    """The stock-PyTorch parts of the step (AR model convs / attention, the W_k Linear) run on cuDNN / cuBLAS; both
+    would otherwise be free to use TF32 (10-bit mantissa) while the result is reported as fp32 and compared with the
+    reference's CPU fp32.  Called by the trainer and setup_model in the fp32 parity mode."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
 # Second-order mode (the Wasserstein gradient penalty, contrastive_estimation_training.py:144-155, differentiates
 # d(sum scores)/d(scalogram) once more): convolutions stay on the B200 kernels -- their backward is then recorded
 # as differentiable dgrad / wgrad Functions -- while the fused BN+ReLU and max-pool Functions, whose backward
@@ -46,6 +54,30 @@ def second_order(enabled=True):
 
 def second_order_enabled():
     return _second_order
+
+
+# Kernel-selection switches (A/B tests, diagnostics).  The C-ABI library itself holds no state and reads no
+# environment: each call receives the switches in its parameter struct's ``flags`` field.  On the host side they
+# can be set programmatically (``ops.kernel_switches["CPC_NO_TENSOR_CQT"] = True``) or through environment
+# variables of the same names, read at call time.
+kernel_switches = {}
+_CONV_SWITCHES = (("CPC_FORCE_CUDA_CORE_CONV", _lib.CONV_FLAG_CUDA_CORE), ("CPC_NO_TALL_CONV", _lib.CONV_FLAG_NO_TALL),
+                  ("CPC_NO_SMALLK_CONV", _lib.CONV_FLAG_NO_SMALLK), ("CPC_NO_FUSED_DGRAD", _lib.CONV_FLAG_NO_FUSED_DGRAD))
+
+
+def _switch(name):
+    import os
+    if name in kernel_switches:
+        return bool(kernel_switches[name])
+    return os.environ.get(name) == "1"
+
+
+def _conv_flags():
+    flags = 0
+    for name, bit in _CONV_SWITCHES:
+        if _switch(name):
+            flags |= bit
+    return flags
 
 
 def _require_cuda(*tensors):
@@ -149,6 +181,7 @@ def _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, relu, prec
     p.pad_top, p.pad_left = pad_top, pad_left
     p.relu = int(relu)
     p.precision = _PRECISION[precision]
+    p.flags = _conv_flags()
     return p
 
 
@@ -547,8 +580,7 @@ def block_tail_eligible(y_a, bn0, conv, top, bn1):
     """True when ``relu(bn0(y_a)) -> conv -> bn1`` can run as one node with packed intermediates: kh x 1 stride-1 conv
     without horizontal padding on the row-streaming kernels (forward, data and weight gradient), fp32-faithful mode,
     affine batch norms, first-order autograd."""
-    import os
-    if os.environ.get("CPC_NO_BLOCK_TAIL") == "1" or _second_order or _default_precision != "fp32":
+    if _switch("CPC_NO_BLOCK_TAIL") or _second_order or _default_precision != "fp32":
         return False
     if not (y_a.is_cuda and y_a.dtype == torch.float32 and y_a.dim() == 4 and y_a.shape[3] % 2 == 0):
         return False                                             # the packed-output kernels own pairs of columns
@@ -654,6 +686,7 @@ def _nce_params(pred, targets, all_steps, kind, reg, precision):
     p.regularization = float(reg)
     p.tgt_stride_b, p.tgt_stride_e, p.tgt_stride_k = targets.stride()
     p.precision = _PRECISION[precision]
+    p.flags = _lib.INFONCE_FLAG_NO_TENSOR if _switch("CPC_NO_TENSOR_INFONCE") else 0
     return p
 
 
@@ -733,8 +766,38 @@ def infonce_validate(pred, targets, all_steps, kind="linear", precision=None):
 # CQT front end (no autograd: the filterbank is frozen in training, constant_q_transform.py:145)
 # --------------------------------------------------------------------------------------------------
 
+def _cqt_params(plan, batch, n_samples, x_pitch, n_frames, mode, pool_t, eps, log_offset, norm, power):
+    p = _lib.CqtParams()
+    p.batch, p.n_samples, p.x_pitch = batch, n_samples, x_pitch
+    p.n_bins, p.hop, p.n_frames = plan["n_bins"], plan["hop"], n_frames
+    p.n_groups = len(plan["kernel_sizes"])
+    for g, (ks, (lo, hi), wo) in enumerate(zip(plan["kernel_sizes"], plan["ranges"], plan["weight_offsets"])):
+        p.kernel_size[g], p.bin_lo[g], p.bin_hi[g], p.weight_offset[g] = ks, lo, hi, wo
+    p.mode, p.pool_t = mode, pool_t
+    p.eps, p.log_offset, p.norm, p.power = eps, log_offset, norm, power
+    p.flags = _lib.CQT_FLAG_NO_TENSOR if _switch("CPC_NO_TENSOR_CQT") else 0
+    return p
+
+
+def cqt_pack_filters(weights, plan):
+    """The filterbank in the form the tensor-core kernel reads (scaled fp16 hi / lo planes, per-bin scales, live tap
+    ranges), or None when the configuration has no tensor-core path.  Depends on the weights only: ``CQT`` caches it."""
+    _require_cuda(weights)
+    lib = _lib.load()
+    k0 = plan["kernel_sizes"][0]
+    p = _cqt_params(plan, 1, k0 + 1, k0 + 1, 1, _lib.CQT_COMPLEX, 1, 0.0, 0.0, 1.0, 1.0)
+    p.flags = 0
+    nbytes = lib.cpc_cqt_packed_filter_bytes(ctypes.byref(p))
+    if nbytes == 0:
+        return None
+    packed = torch.empty(int(nbytes), dtype=torch.uint8, device=weights.device)
+    with torch.cuda.device(weights.device):
+        _call("cpc_cqt_pack_filters", 0.0, lib.cpc_cqt_pack_filters, _ptr(weights), _ptr(packed), ctypes.byref(p), _stream())
+    return packed
+
+
 def cqt_frontend(x, weights, plan, mode, phase_fixed=None, phase_scale=None, pool_t=1, eps=0.0, log_offset=0.0,
-                 norm=1.0, power=1.0):
+                 norm=1.0, power=1.0, packed_filters=None):
     """x (B, L) or (B,1,L) fp32 on CUDA; ``weights`` the packed filterbank; ``plan`` a dict with
     kernel_sizes / ranges / weight_offsets / hop / n_bins.  Output layout per ``mode`` (see cpc_b200.h)."""
     _require_cuda(x, weights)
@@ -751,14 +814,7 @@ def cqt_frontend(x, weights, plan, mode, phase_fixed=None, phase_scale=None, poo
     t = (l - 1 - k0) // plan["hop"] + 1
     if t <= 0:
         raise ValueError("input of %d samples is shorter than the CQT receptive field %d (+1)" % (l, k0))
-    p = _lib.CqtParams()
-    p.batch, p.n_samples, p.x_pitch = b, l, x.stride(0)
-    p.n_bins, p.hop, p.n_frames = plan["n_bins"], plan["hop"], t
-    p.n_groups = len(plan["kernel_sizes"])
-    for g, (ks, (lo, hi), wo) in enumerate(zip(plan["kernel_sizes"], plan["ranges"], plan["weight_offsets"])):
-        p.kernel_size[g], p.bin_lo[g], p.bin_hi[g], p.weight_offset[g] = ks, lo, hi, wo
-    p.mode, p.pool_t = mode, pool_t
-    p.eps, p.log_offset, p.norm, p.power = eps, log_offset, norm, power
+    p = _cqt_params(plan, b, l, x.stride(0), t, mode, pool_t, eps, log_offset, norm, power)
     f = plan["n_bins"]
     if mode == _lib.CQT_COMPLEX:
         out = torch.empty((b, f, t, 2), dtype=torch.float32, device=x.device)
@@ -771,7 +827,8 @@ def cqt_frontend(x, weights, plan, mode, phase_fixed=None, phase_scale=None, poo
     ws = _workspace(lib.cpc_cqt_workspace_bytes(ctypes.byref(p)), x.device)
     with torch.cuda.device(x.device):
         taps = sum(2 * (hi - lo) * ks for ks, (lo, hi) in zip(plan["kernel_sizes"], plan["ranges"]))
-        _call("cpc_cqt_fwd b%d L%d T%d mode%d" % (b, l, t, mode), 2.0 * taps * b * t, lib.cpc_cqt_fwd, _ptr(x),
-              _ptr(weights), _ptr(phase_fixed), _ptr(phase_scale), _ptr(out), ctypes.byref(p), _ptr(ws),
-              ws.numel() if ws is not None else 0, _stream())
+        c_out = 2 if mode == _lib.CQT_LOGPOW_PHASE else (2 if mode == _lib.CQT_COMPLEX else 1)
+        _call("cpc_cqt_fwd b%d L%d T%d mode%d" % (b, l, t, mode), 2.0 * taps * b * t, lib.cpc_cqt_fwd_ex, _ptr(x),
+              _ptr(weights), _ptr(packed_filters), _ptr(phase_fixed), _ptr(phase_scale), _ptr(out), ctypes.byref(p), _ptr(ws),
+              ws.numel() if ws is not None else 0, _stream(), nbytes=4.0 * b * l + 4.0 * out.numel())
     return out

@@ -83,6 +83,8 @@ class ContrastiveEstimationTrainer:
             self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         self.last_loss = None
         self.last_max_score = None
+        if ops.get_default_precision() == "fp32":
+            ops.strict_fp32_libraries()                         # no TF32 in the cuDNN / cuBLAS parts (AR model, W_k)
         if verbose:
             print("use score function", self.score_function)
 

@@ -41,8 +41,7 @@ bool smallk_eligible(const cpc_conv_params* p, int which);
 int smallk_launch(int which, const float* x, const float* w, const float* bias, const float* dy, float* out,
                   const cpc_conv_params* p, cudaStream_t s);
 static bool smallk_path(const cpc_conv_params* p, int which) {
-    const char* e = std::getenv("CPC_NO_SMALLK_CONV");          // A/B switch: keep tiny-K convs on the tiled kernels
-    if (e && e[0] == '1') return false;
+    if (p->flags & CPC_CONV_FLAG_NO_SMALLK) return false;       // A/B switch: keep tiny-K convs on the tiled kernels
     return smallk_eligible(p, which);
 }
 
@@ -55,21 +54,17 @@ int tall128_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_c
                          const void* pre_dy, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 // Debug switches (tests use them to A/B kernel families on one shape): CPC_FORCE_CUDA_CORE_CONV=1 selects the
-// fp32 CUDA-core kernels, CPC_NO_TALL_CONV=1 keeps tall convolutions on the generic tcgen05 kernel.
+// fp32 CUDA-core kernels, flags & CPC_CONV_FLAG_NO_TALL keeps tall convolutions on the generic tcgen05 kernel.
 // Returns 0 (not a tall conv), 1 (conv_tall.cu, 32 -> 32 channels) or 2 (conv_tall128.cu).
 static int tall_path(const cpc_conv_params* p, int which) {
-    const char* e = std::getenv("CPC_FORCE_CUDA_CORE_CONV");
-    if (e && e[0] == '1') return 0;
-    e = std::getenv("CPC_NO_TALL_CONV");
-    if (e && e[0] == '1') return 0;
+    if (p->flags & (CPC_CONV_FLAG_CUDA_CORE | CPC_CONV_FLAG_NO_TALL)) return 0;
     if (tall_conv_eligible(p, which)) return 1;
     if (tall128_eligible(p, which)) return 2;
     return 0;
 }
 
 static bool tensor_core_path(const cpc_conv_params* p, int which) {
-    const char* e = std::getenv("CPC_FORCE_CUDA_CORE_CONV");
-    if (e && e[0] == '1') return false;
+    if (p->flags & CPC_CONV_FLAG_CUDA_CORE) return false;
     return which == 2 ? umma_wgrad_eligible(p) : umma_conv_eligible(p, which);
 }
 

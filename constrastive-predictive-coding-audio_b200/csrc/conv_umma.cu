@@ -737,8 +737,7 @@ static DgradShare dgrad_share(const cpc_conv_params* p) {
 // columns are (class, channel); weight rows of taps a class does not have are zero.  Every dy tile is fetched once
 // for all classes (the per-class launches fetch it 9 / 4 times) and dx is written in full sectors.
 static bool fused_dgrad_problem(const float* dy, const cpc_conv_params* p, ConvProblem& c) {
-    const char* env = getenv("CPC_NO_FUSED_DGRAD");
-    if (env && env[0] == '1') return false;
+    if (p->flags & CPC_CONV_FLAG_NO_FUSED_DGRAD) return false;
     if (p->stride_h != 2 || p->stride_w != 2 || p->pad_top != 0 || p->pad_left != 0) return false;
     if (p->kh < 2 || p->kh > 4 || p->kw < 2 || p->kw > 4 || p->c_in != 32) return false;
     c = ConvProblem{};

@@ -8,8 +8,6 @@
 // Stage 2: one elementwise pass turning (re, im) into the scalogram the trainer consumes.
 #include "common.cuh"
 
-#include <cstdlib>
-
 namespace cpc {
 
 struct CqtGroups {
@@ -149,14 +147,16 @@ namespace cpc {
 bool cqt_umma_eligible(const cpc_cqt_params* p);
 int cqt_umma_tensor_groups(const cpc_cqt_params* p);
 size_t cqt_umma_workspace(const cpc_cqt_params* p);
-int cqt_umma_launch(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale, float* out,
-                    const cpc_cqt_params* p, void* workspace, size_t workspace_bytes, cudaStream_t s);
+size_t cqt_umma_packed_filter_bytes(const cpc_cqt_params* p);
+int cqt_umma_pack_filters(const float* weights, void* packed, const cpc_cqt_params* p, cudaStream_t s);
+int cqt_umma_launch(const float* x, const float* weights, const void* packed_filters, const float* phase_fixed,
+                    const float* phase_scale, float* out, const cpc_cqt_params* p, void* workspace, size_t workspace_bytes,
+                    cudaStream_t s);
 }
 
-// CPC_NO_TENSOR_CQT=1 keeps every group on the CUDA-core kernels (A/B switch for tests)
+// flags & CPC_CQT_FLAG_NO_TENSOR keeps every group on the CUDA-core kernels (A/B switch for tests)
 static bool tensor_cqt(const cpc_cqt_params* p) {
-    const char* e = std::getenv("CPC_NO_TENSOR_CQT");
-    if (e && e[0] == '1') return false;
+    if (p->flags & CPC_CQT_FLAG_NO_TENSOR) return false;
     return cqt_umma_eligible(p);
 }
 
@@ -173,8 +173,23 @@ extern "C" size_t cpc_cqt_workspace_bytes(const cpc_cqt_params* p) {
     return simt_cplx_bytes(p, 0);
 }
 
-extern "C" int cpc_cqt_fwd(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale,
-                           float* out, const cpc_cqt_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" size_t cpc_cqt_packed_filter_bytes(const cpc_cqt_params* p) {
+    if (!p || cqt_validate(p) != CPC_OK || !tensor_cqt(p)) return 0;
+    return cqt_umma_packed_filter_bytes(p);
+}
+
+extern "C" int cpc_cqt_pack_filters(const float* weights, void* packed, const cpc_cqt_params* p, void* stream) {
+    int st = cqt_validate(p);
+    if (st != CPC_OK) return st;
+    if (!weights || !packed) return CPC_ERR_NULL;
+    if (!tensor_cqt(p)) return CPC_ERR_UNSUPPORTED;
+    if ((st = check_device()) != CPC_OK) return st;
+    return cqt_umma_pack_filters(weights, packed, p, (cudaStream_t)stream);
+}
+
+extern "C" int cpc_cqt_fwd_ex(const float* x, const float* weights, const void* packed_filters, const float* phase_fixed,
+                              const float* phase_scale, float* out, const cpc_cqt_params* p, void* workspace,
+                              size_t workspace_bytes, void* stream) {
     int st = cqt_validate(p);
     if (st != CPC_OK) return st;
     if (!x || !weights || !out) return CPC_ERR_NULL;
@@ -195,15 +210,15 @@ extern "C" int cpc_cqt_fwd(const float* x, const float* weights, const float* ph
     int g_first = 0;
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     if (tensor_cqt(p)) {
-        // groups with >= 128 taps: tensor cores, written in the final format
+        // tensor cores, written in the final format
         const size_t uw = cqt_umma_workspace(p);
-        st = cqt_umma_launch(x, weights, phase_fixed, phase_scale, out, p, ws, uw, s);
+        st = cqt_umma_launch(x, weights, packed_filters, phase_fixed, phase_scale, out, p, ws, uw, s);
         if (st != CPC_OK) return st;
         g_first = cqt_umma_tensor_groups(p);
         ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws) + uw, 1024));
         if (g_first >= p->n_groups) return CPC_OK;
     }
-    // remaining (short) groups: CUDA-core filterbank + elementwise pass over their bins
+    // remaining groups: CUDA-core filterbank + elementwise pass over their bins
     const int f0 = p->bin_lo[g_first], fs = p->n_bins - f0;
     const bool direct = p->mode == CPC_CQT_COMPLEX;
     float* cplx = direct ? out : reinterpret_cast<float*>(ws);
@@ -224,4 +239,9 @@ extern "C" int cpc_cqt_fwd(const float* x, const float* weights, const float* ph
         count_launch();
     }
     return CPC_OK;
+}
+
+extern "C" int cpc_cqt_fwd(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale,
+                           float* out, const cpc_cqt_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+    return cpc_cqt_fwd_ex(x, weights, nullptr, phase_fixed, phase_scale, out, p, workspace, workspace_bytes, stream);
 }

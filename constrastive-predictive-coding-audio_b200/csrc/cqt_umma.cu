@@ -7,30 +7,63 @@
 // GEMM view per group: M = 128 frames of one item, N = 2*n_g channels (padded to NP), K = K_g taps.
 // The audio is viewed as a matrix X2[s][r] = x[hop*s + r]; frame t, taps [hop*m + 64*h, +64) is row t + m of
 // X2, column half h.  So ALL the A operands of a 128-frame tile are row-shifted windows of one shared-memory
-// slab of 256 X2 rows, which is loaded ONCE per tile (128 KB with both bf16 planes): the K loop only moves the
-// descriptor start address by m rows (SWIZZLE_128B K-major with the descriptor's base-offset field), while
-// the filter chunks (B operand) stream through a 4-stage TMA ring.  One tile accumulates every group of its
-// "set" into separate TMEM columns, then the epilogue turns (re, im) into the scalogram in registers:
+// slab of 256 X2 rows, which is loaded ONCE per tile (128 KB with both planes): the K loop only moves the
+// descriptor start address by m rows (SWIZZLE_128B K-major), while the filter chunks (B operand) stream through
+// a TMA ring.  One tile accumulates every group of its "set" into separate TMEM columns, then the epilogue turns
+// (re, im) into the scalogram in registers:
 //   complex (B,F,T,2) | log-power (B,1,F,T) | log-power + unwrapped phase difference (B,2,F,T-1),
-// with coalesced stores along t.  fp32-faithful arithmetic = bf16 hi/lo split, 3 MMA groups.
-// Tiles (set, item, frame block) are handed out through an atomic counter in descending cost order.
+// with coalesced stores along t.  Tiles (set, item, frame block) are handed out through an atomic counter in
+// descending cost order.
+//
+// fp32-exact arithmetic on 16-bit tensor-core operands.  Both operands are split into TWO fp16 planes after an exact
+// power-of-two scaling that puts the largest magnitude of the item (audio) / of the bin (filter) at 2^14:
+//     v * 2^s = hi + lo + r,   hi = fp16(v * 2^s),  lo = fp16(v * 2^s - hi),   |r| <= max(2^-23 |v * 2^s|, 2^-25)
+// i.e. 22 mantissa bits wherever |v| >= 2^-17 of the item's / bin's peak and an absolute error of 2^-39 of the peak
+// below that (bf16 hi/lo planes only carry 16 bits: the 1e-5 relative error of that scheme is what log / atan2 of
+// near-silent cells amplified beyond the 1e-3 parity bound).  Products hi*hi, hi*lo, lo*hi are exact in the fp32
+// accumulator; lo*lo (2^-22) is dropped; the epilogue multiplies by 2^-(s_item + s_bin).
+// The three products of a K step are TWO MMAs: the filter planes are stacked along N, [W_hi | W_lo], so that
+// X_hi * [W_hi | W_lo] fetches the audio window once for both (these MMAs are bound by the shared-memory operand
+// fetch, not by the tensor pipe), then X_lo * W_hi accumulates onto the W_lo columns; the epilogue adds the two column
+// blocks.  Short groups (K < 1024, 4 % of the work) use three N = NP MMAs into one column block instead, which lets
+// several of them share a tile.  Long groups split their tap range over up to four accumulator segments (see CQ_SEG4_MIN_K:
+// the tensor core's accumulator truncates), so a tile owns all 512 TMEM columns and tiles are not double-buffered.  64-tap chunks in which every filter of the group is zero (the centre-padding of
+// constant_q_transform.py:132-140: 25 % of the longest group) are found while packing the filters and skipped.
 #include "common.cuh"
 #include "umma.cuh"
 
-#include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace cpc {
 using namespace umma;
 
 constexpr int CQ_THREADS = 384;                        // 4 control warps + 2 x 4 epilogue warps
-constexpr int CQ_ACC_COLS = 256;                       // TMEM columns per accumulator buffer (two buffers)
+constexpr int CQ_ACC_COLS = 512;                       // TMEM columns of a tile's accumulators (all of TMEM, one buffer)
 constexpr int CQ_SLAB_ROWS = 256;
 constexpr int CQ_SLAB_PLANE = CQ_SLAB_ROWS * 128;        // 32 KB: one column half, one plane
 constexpr int CQ_BSTAGES = 5;
 constexpr int CQ_MAX_SETS = 8;
+constexpr int CQ_WIDE_MIN_K = 1024;                    // groups at least this long stack [W_hi | W_lo] along N
+// The tensor core adds into its fp32 accumulator with truncation (measured: every accumulating MMA shrinks the running sum
+// by ~2^-26 of its magnitude, coherently, so the relative error of a group grows linearly with its number of K steps:
+// 1.05e-5 after the 768 steps of the 16384-tap group against 1.8e-6 for an fp32 FMA chain).  Long groups therefore
+// accumulate their tap range in CQ_SEG* separate column blocks ("segments") which the epilogue adds in registers.
+constexpr int CQ_SEG4_MIN_K = 8192, CQ_SEG2_MIN_K = 2048;
 
 struct CqGroup {
     int K, off, n_g, bin_lo, n_chunks, w_row0;           // w_row0: first row of the group in the packed filters
+    int wide, col, n_seg;                                // wide: [main | correction] column blocks; col: first TMEM column;
+                                                         // n_seg: accumulator segments along the tap axis
+};
+
+// Per-call device bookkeeping (workspace): the tile scheduler's counter.
+struct CqMeta {
+    int counter;
+};
+// Lives at the end of the packed filter blob: written once by the filter packing kernels, read by every forward call.
+struct CqFilterMeta {
+    int live_lo[CPC_CQT_MAX_GROUPS];                     // first / one-past-last tap (in the group's padded tap axis) at
+    int live_hi[CPC_CQT_MAX_GROUPS];                     //   which any filter of the group is non-zero
 };
 
 struct CqtUmma {
@@ -39,37 +72,89 @@ struct CqtUmma {
     int n_sets, set_first[CQ_MAX_SETS], set_count[CQ_MAX_SETS];
     int n_tiles;
     CqGroup g[CPC_CQT_MAX_GROUPS];
+    int n_groups;
     int mode, To;
     float eps, log_offset, norm, power;
     const float* phase_fixed;
     const float* phase_scale;
+    const float* inv_item;                               // (B)  2^-s of the item's audio scaling
+    const float* inv_bin;                                // (F)  2^-s of the bin's filter scaling
     float* out;
-    int* counter;
-    int base_offset;
+    CqMeta* meta;
+    const CqFilterMeta* fmeta;
 };
 
 struct __align__(8) CqBarriers {
-    uint64_t bfull[CQ_BSTAGES], bempty[CQ_BSTAGES], slab_full, slab_empty, acc_full[2], acc_empty[2], sfull[2], sempty[2];
+    uint64_t bfull[CQ_BSTAGES], bempty[CQ_BSTAGES], slab_full, slab_empty, acc_full, acc_empty, sfull[2], sempty[2];
     uint32_t tmem_base;
     int tile_id[2];
+    int c_lo[CPC_CQT_MAX_GROUPS], c_hi[CPC_CQT_MAX_GROUPS];   // live 64-tap chunk range of every group
     float exch[2][2][4][32];                         // [epilogue warp set][parity][warp][bin]
 };
 
-// x (B, pitch) fp32 -> bf16 [plane][b][S*hop] (zeros past the item)
-__global__ void __launch_bounds__(256) cqt_pack_audio_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+// 2^s with s clamped so that the result and its reciprocal are normal floats
+__device__ __forceinline__ float pow2i(int s) {
+    s = s < -100 ? -100 : (s > 100 ? 100 : s);
+    return __int_as_float((s + 127) << 23);
+}
+// power-of-two scale that puts a magnitude with float bits `bits` into [2^14, 2^15)
+__device__ __forceinline__ int scale_exponent(uint32_t bits) { return 14 - ((int)((bits >> 23) & 0xff) - 127); }
+
+__global__ void cqt_init_meta_kernel(CqMeta* meta, uint32_t* item_max, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) meta->counter = 0;
+    if (i < B) item_max[i] = 0u;
+}
+__global__ void cqt_init_filter_meta_kernel(CqFilterMeta* fm) {
+    const int i = threadIdx.x;
+    if (i < CPC_CQT_MAX_GROUPS) { fm->live_lo[i] = 0x7fffffff; fm->live_hi[i] = 0; }
+}
+
+// largest |x| of every item (float bits of non-negative values order like unsigned integers)
+__global__ void __launch_bounds__(256) cqt_item_max_kernel(const float* __restrict__ x, uint32_t* __restrict__ item_max, int L,
+                                                          int pitch) {
+    const int b = blockIdx.y;
+    const float* row = x + (size_t)b * pitch;
+    uint32_t m = 0;
+    const int stride = gridDim.x * blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        const int n4 = L >> 2;
+        for (int q = tid; q < n4; q += stride) {
+            const float4 v = __ldg(row4 + q);
+            m = max(max(m, __float_as_uint(fabsf(v.x))), __float_as_uint(fabsf(v.y)));
+            m = max(max(m, __float_as_uint(fabsf(v.z))), __float_as_uint(fabsf(v.w)));
+        }
+        const int tail = (n4 << 2) + tid;                  // the (< 4) trailing samples, by the first threads
+        if (tail < L) m = max(m, __float_as_uint(fabsf(__ldg(row + tail))));
+    } else {
+        for (int i = tid; i < L; i += stride) m = max(m, __float_as_uint(fabsf(__ldg(row + i))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(item_max + b, m);
+}
+
+// x (B, pitch) fp32 -> fp16 [plane][b][S*hop] of x * 2^s_b (zeros past the item)
+__global__ void __launch_bounds__(256) cqt_pack_audio_kernel(const float* __restrict__ x, __half* __restrict__ out,
+                                                            const uint32_t* __restrict__ item_max, float* __restrict__ inv_item,
                                                             int B, int L, int pitch, int Lp) {
     const long groups = (long)B * (Lp >> 3);
     const long plane = (long)B * Lp;
     for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long)gridDim.x * blockDim.x) {
         const int b = (int)(gi / (Lp >> 3));
         const int i0 = (int)(gi - (long)b * (Lp >> 3)) << 3;
-        __align__(16) __nv_bfloat16 hi[8];
-        __align__(16) __nv_bfloat16 lo[8];
+        const int se = scale_exponent(__ldg(item_max + b));
+        const float scale = pow2i(se);
+        if (i0 == 0) inv_item[b] = pow2i(-se);
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float v = (i0 + i < L) ? __ldg(x + (size_t)b * pitch + i0 + i) : 0.f;
-            hi[i] = __float2bfloat16_rn(v);
-            lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi[i]));
+            const float v = (i0 + i < L) ? __ldg(x + (size_t)b * pitch + i0 + i) * scale : 0.f;
+            hi[i] = __float2half_rn(v);
+            lo[i] = __float2half_rn(v - __half2float(hi[i]));
         }
         const long o = (long)b * Lp + i0;
         *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(hi);
@@ -77,31 +162,66 @@ __global__ void __launch_bounds__(256) cqt_pack_audio_kernel(const float* __rest
     }
 }
 
-// filters: group block (2*n_g, K_g) fp32 row-major [real bins; imag bins] -> bf16 rows of 64 taps:
-//   row = w_row0 + chunk * 2*NP + plane * NP + n
-__global__ void __launch_bounds__(256) cqt_pack_filters_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                              int K, int n2, int NP, int w_row0) {
-    const int n_chunks = K >> 6;
-    const long total = (long)n_chunks * NP * 64;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int kk = (int)(idx & 63);
-        const int n = (int)((idx >> 6) % NP);
-        const int c = (int)((idx >> 6) / NP);
-        // rows [0, n_g) real bins, rows [NP/2, NP/2 + n_g) imaginary bins, everything else zero
-        const int ng = n2 >> 1, hp = NP >> 1;
-        const int src = n < hp ? (n < ng ? n : -1) : (n - hp < ng ? ng + n - hp : -1);
-        const float v = src >= 0 ? __ldg(w + (size_t)src * K + c * 64 + kk) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const size_t row = (size_t)w_row0 + (size_t)c * 2 * NP + n;
-        out[row * 64 + kk] = hi;
-        out[(row + NP) * 64 + kk] = __float2bfloat16_rn(v - __bfloat162float(hi));
+// filters: group block (2*n_g, K_src) fp32 row-major [real bins; imag bins] -> fp16 rows of 64 taps:
+//   row = w_row0 + chunk * 2*NP + plane * NP + n,   n < NP/2: real part of bin n, n >= NP/2: imaginary part of bin n - NP/2
+// The group's tap axis is K >= K_src taps long with the source filters centred in it (`pad` zero taps on either side: a
+// 64-tap group becomes a 128-tap group so that its window starts on a 64-sample boundary of the slab).
+// One block per bin slot: pass 1 finds the bin's peak magnitude (-> its power-of-two scale) and its non-zero tap range,
+// pass 2 writes the two planes of both rows.  Slots beyond the group's bins write zero rows.
+__global__ void __launch_bounds__(256) cqt_pack_filters_kernel(const float* __restrict__ w, __half* __restrict__ out,
+                                                              float* __restrict__ inv_bin, CqFilterMeta* fm, int g, int K,
+                                                              int K_src, int pad, int ng, int NP, int w_row0, int bin_lo) {
+    __shared__ uint32_t s_max;
+    __shared__ int s_lo, s_hi;
+    const int j = blockIdx.x;                              // bin slot, < NP / 2
+    const bool real_bin = j < ng;
+    if (threadIdx.x == 0) { s_max = 0u; s_lo = 0x7fffffff; s_hi = 0; }
+    __syncthreads();
+    if (real_bin) {
+        uint32_t m = 0;
+        int lo = 0x7fffffff, hi = 0;
+        for (int k = threadIdx.x; k < K_src; k += blockDim.x) {
+            const float re = __ldg(w + (size_t)j * K_src + k), im = __ldg(w + (size_t)(ng + j) * K_src + k);
+            const uint32_t a = max(__float_as_uint(fabsf(re)), __float_as_uint(fabsf(im)));
+            if (a) { m = max(m, a); lo = min(lo, k + pad); hi = max(hi, k + pad + 1); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMax(&s_max, m); atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    }
+    __syncthreads();
+    const int se = scale_exponent(s_max);
+    const float scale = pow2i(se);
+    if (real_bin && threadIdx.x == 0) {
+        inv_bin[bin_lo + j] = pow2i(-se);
+        if (s_hi > s_lo) { atomicMin(&fm->live_lo[g], s_lo); atomicMax(&fm->live_hi[g], s_hi); }
+    }
+    const int hp = NP >> 1;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int c = k >> 6, kk = k & 63;
+        const int ks = k - pad;
+        const bool live = real_bin && ks >= 0 && ks < K_src;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const float v = live ? __ldg(w + (size_t)(part * ng + j) * K_src + ks) * scale : 0.f;
+            const __half hi = __float2half_rn(v);
+            const size_t row = (size_t)w_row0 + (size_t)c * 2 * NP + part * hp + j;
+            out[row * 64 + kk] = hi;
+            out[(row + NP) * 64 + kk] = __float2half_rn(v - __half2float(hi));
+        }
     }
 }
 
-__device__ __forceinline__ uint64_t cq_desc(uint32_t addr, int use_base_offset) {
-    // K-major SWIZZLE_128B; the window may start on any 128-byte row of the slab
-    uint64_t d = make_smem_desc(addr, 16, 1024);
-    if (use_base_offset) d |= (uint64_t)((addr >> 7) & 7) << 49;
+// Instruction descriptor for kind::f16 with FP16 A/B (format code 0) and F32 accumulate, both operands K-major.
+__host__ __device__ inline uint32_t make_idesc_f16(int m, int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                                // D format F32
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(m >> 4) << 24;
     return d;
 }
 
@@ -148,13 +268,23 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
         for (int s = 0; s < CQ_BSTAGES; ++s) { mbar_init(&bars->bfull[s], 1); mbar_init(&bars->bempty[s], 1); }
         mbar_init(&bars->slab_full, 1);
         mbar_init(&bars->slab_empty, 1);
+        mbar_init(&bars->acc_full, 1);
+        mbar_init(&bars->acc_empty, 8);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->acc_full[s], 1);
-            mbar_init(&bars->acc_empty[s], 8);
             mbar_init(&bars->sfull[s], 1);
             mbar_init(&bars->sempty[s], 9);
         }
         fence_barrier_init();
+    }
+    if (warp == 3 && lane < p.n_groups) {
+        // live chunk range of the group (at least one chunk, so that every accumulator column is written)
+        const int n_chunks = p.g[lane].n_chunks;
+        int lo = p.fmeta->live_lo[lane] >> 6, hi = (p.fmeta->live_hi[lane] + 63) >> 6;
+        if (hi <= lo) { lo = 0; hi = 1; }
+        lo = lo < 0 ? 0 : (lo > n_chunks - 1 ? n_chunks - 1 : lo);
+        hi = hi > n_chunks ? n_chunks : (hi < lo + 1 ? lo + 1 : hi);
+        bars->c_lo[lane] = lo;
+        bars->c_hi[lane] = hi;
     }
     if (warp == 2) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
     tc_fence_before();
@@ -169,7 +299,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             for (uint32_t i = 0;; ++i) {
                 const int slot = i & 1;
                 mbar_wait(&bars->sempty[slot], ((i >> 1) & 1) ^ 1);
-                int tile = atomicAdd(p.counter, 1);
+                int tile = atomicAdd(&p.meta->counter, 1);
                 if (tile >= p.n_tiles) tile = -1;
                 bars->tile_id[slot] = tile;
                 mbar_arrive(&bars->sfull[slot]);
@@ -182,8 +312,10 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                     tma_load_4d(slab + h * 2 * CQ_SLAB_PLANE, &tmap_x, &bars->slab_full, h * 64, blk * p.fpb, b, 0);
                 ++tn;
                 for (int gi = 0; gi < p.set_count[set]; ++gi) {
-                    const CqGroup& g = p.g[p.set_first[set] + gi];
-                    for (int c = 0; c < g.n_chunks; ++c, ++bn) {
+                    const int gidx = p.set_first[set] + gi;
+                    const CqGroup& g = p.g[gidx];
+                    const int c_hi = bars->c_hi[gidx];
+                    for (int c = bars->c_lo[gidx]; c < c_hi; ++c, ++bn) {
                         const int stage = bn % CQ_BSTAGES;
                         mbar_wait(&bars->bempty[stage], ((bn / CQ_BSTAGES) & 1) ^ 1);
                         mbar_expect_tx(&bars->bfull[stage], (uint32_t)b_stage);
@@ -193,10 +325,9 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform loop, one elected lane issues.  An N = 64 MMA occupies the tensor pipe for
-        // only 32 cycles, so the issue path is kept to one 64-bit add per descriptor =====
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
         {
-            const uint32_t idesc = make_idesc_bf16(128, p.NP, 0, 0);
+            const uint32_t idesc_np = make_idesc_f16(128, p.NP), idesc_2np = make_idesc_f16(128, 2 * p.NP);
             const uint32_t slab_addr = smem_u32(slab);
             const uint32_t hop_shift = p.hop == 64 ? 6 : 7;                  // hop is 64 or 128
             uint32_t bn = 0, tn = 0;
@@ -209,39 +340,56 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                 if (tile < 0) break;
                 int set, b, blk;
                 cq_tile(p, tile, set, b, blk);
-                const uint32_t buf = tn & 1;
-                mbar_wait(&bars->acc_empty[buf], ((tn >> 1) & 1) ^ 1);
+                mbar_wait(&bars->acc_empty, (tn & 1) ^ 1);
                 mbar_wait(&bars->slab_full, tn & 1);
                 tc_fence_after();
                 for (int gi = 0; gi < p.set_count[set]; ++gi) {
-                    const CqGroup& g = p.g[p.set_first[set] + gi];
-                    const uint32_t d_tmem = tmem_base + buf * CQ_ACC_COLS + (uint32_t)(gi * p.NP);
-                    for (int c = 0; c < g.n_chunks; ++c, ++bn) {
+                    const int gidx = p.set_first[set] + gi;
+                    const CqGroup& g = p.g[gidx];
+                    const int c_lo = bars->c_lo[gidx], c_hi = bars->c_hi[gidx];
+                    const int seg_len = (c_hi - c_lo + g.n_seg - 1) / g.n_seg;
+                    const uint32_t seg_cols = (uint32_t)(g.wide ? 2 * p.NP : p.NP);
+                    int seg = 0, in_seg = 0;
+                    for (int c = c_lo; c < c_hi; ++c, ++bn) {
                         const int stage = bn % CQ_BSTAGES;
                         mbar_wait(&bars->bfull[stage], (bn / CQ_BSTAGES) & 1);
                         tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)g.col + (uint32_t)seg * seg_cols;
                         const uint32_t so = (uint32_t)(g.off + c * 64);        // sample offset of this tap chunk
                         const uint32_t m = so >> hop_shift, half = (so & (p.hop - 1)) >> 6;
                         const uint32_t a_hi = slab_addr + half * 2 * CQ_SLAB_PLANE + m * 128;
                         const uint32_t b_hi = smem_u32(b_ring + stage * b_stage);
                         if (elect_one()) {
-                            const uint64_t a_d_hi = cq_desc(a_hi, p.base_offset), a_d_lo = cq_desc(a_hi + CQ_SLAB_PLANE, p.base_offset);
+                            // K-major SWIZZLE_128B; the audio window may start on any 128-byte row of the slab (the
+                            // swizzle follows absolute address bits, so no descriptor base offset is needed)
+                            const uint64_t a_d_hi = make_smem_desc(a_hi, 16, 1024), a_d_lo = make_smem_desc(a_hi + CQ_SLAB_PLANE, 16, 1024);
                             const uint64_t b_d_hi = make_smem_desc(b_hi, 16, 1024), b_d_lo = make_smem_desc(b_hi + p.NP * 128, 16, 1024);
+                            const uint32_t first = (uint32_t)in_seg;           // 0 on the first chunk of a segment: overwrite
+                            if (g.wide) {
 #pragma unroll
-                            for (int cb = 0; cb < 3; ++cb) {                   // (hi,hi) (hi,lo) (lo,hi)
-                                const uint64_t ad = cb == 2 ? a_d_lo : a_d_hi, bd = cb == 1 ? b_d_lo : b_d_hi;
+                                for (int k = 0; k < 4; ++k) {                  // +32 B per K step = +2 in the address field
+                                    // X_hi * [W_hi | W_lo] -> both column blocks; X_lo * W_hi -> onto the second block
+                                    mma_bf16(d_tmem, a_d_hi + (uint64_t)(2 * k), b_d_hi + (uint64_t)(2 * k), idesc_2np, first | (uint32_t)k);
+                                    mma_bf16(d_tmem + (uint32_t)p.NP, a_d_lo + (uint64_t)(2 * k), b_d_hi + (uint64_t)(2 * k), idesc_np, 1u);
+                                }
+                            } else {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)                    // +32 B per K step = +2 in the address field
-                                    mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (uint32_t)(c | cb | k));
+                                for (int cb = 0; cb < 3; ++cb) {               // (hi,hi) (hi,lo) (lo,hi) into one column block
+                                    const uint64_t ad = cb == 2 ? a_d_lo : a_d_hi, bd = cb == 1 ? b_d_lo : b_d_hi;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_np, first | (uint32_t)(cb | k));
+                                }
                             }
                             tc_commit(&bars->bempty[stage]);
                         }
                         __syncwarp();
+                        if (++in_seg == seg_len) { in_seg = 0; ++seg; }
                     }
                 }
                 if (elect_one()) {
                     tc_commit(&bars->slab_empty);
-                    tc_commit(&bars->acc_full[buf]);
+                    tc_commit(&bars->acc_full);
                 }
                 __syncwarp();
                 ++tn;
@@ -264,18 +412,47 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             int set, b, blk;
             cq_tile(p, tile, set, b, blk);
             const int t = blk * p.fpb + r;                                     // frame of this thread
-            const uint32_t buf = tn & 1;
-            mbar_wait(&bars->acc_full[buf], (tn >> 1) & 1);
+            mbar_wait(&bars->acc_full, tn & 1);
             tc_fence_after();
-            const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * CQ_ACC_COLS;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+            const float inv_item = __ldg(p.inv_item + b);
             for (int gi = eset; gi < p.set_count[set]; gi += 2) {
-                const CqGroup& g = p.g[p.set_first[set] + gi];
+                const int gidx = p.set_first[set] + gi;
+                const CqGroup& g = p.g[gidx];
+                // segments that received taps (the MMA warp's split of the live chunk range)
+                const int n_live = bars->c_hi[gidx] - bars->c_lo[gidx];
+                const int seg_len = (n_live + g.n_seg - 1) / g.n_seg;
+                const int used = (n_live + seg_len - 1) / seg_len;
+                const int seg_cols = g.wide ? 2 * p.NP : p.NP;
                 for (int j0 = 0; j0 < g.n_g; j0 += 32) {
                     uint32_t re[32], im[32];
-                    tmem_ld32(lane_base + (uint32_t)(gi * p.NP + j0), re);
-                    tmem_ld32(lane_base + (uint32_t)(gi * p.NP + (p.NP >> 1) + j0), im);
+                    tmem_ld32(lane_base + (uint32_t)(g.col + j0), re);
+                    tmem_ld32(lane_base + (uint32_t)(g.col + (p.NP >> 1) + j0), im);
                     tmem_ld_wait();
+                    // further accumulator blocks of the group: the segments' main blocks, and (wide groups) every segment's
+                    // correction block (hi*lo + lo*hi); added here in fp32 with round-to-nearest
+                    const int blocks = used * (g.wide ? 2 : 1);
+                    for (int q = 1; q < blocks; ++q) {
+                        const int seg = g.wide ? (q >> 1) : q;
+                        const int cbase = g.col + seg * seg_cols + ((g.wide && (q & 1)) ? p.NP : 0);
+                        uint32_t cr[32];
+                        tmem_ld32(lane_base + (uint32_t)(cbase + j0), cr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) re[j] = __float_as_uint(__uint_as_float(re[j]) + __uint_as_float(cr[j]));
+                        tmem_ld32(lane_base + (uint32_t)(cbase + (p.NP >> 1) + j0), cr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) im[j] = __float_as_uint(__uint_as_float(im[j]) + __uint_as_float(cr[j]));
+                    }
                     const int nb = min(32, g.n_g - j0);
+                    // undo the two power-of-two scalings (exact)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __ldg(p.inv_bin + g.bin_lo + j0 + (j < nb ? j : 0));
+                        re[j] = __float_as_uint(__uint_as_float(re[j]) * inv_item * sc);
+                        im[j] = __float_as_uint(__uint_as_float(im[j]) * inv_item * sc);
+                    }
                     if (p.mode == CPC_CQT_COMPLEX) {
                         if (t < p.T) {
 #pragma unroll
@@ -291,7 +468,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                             for (int j = 0; j < 32; ++j)
                                 if (j < nb) {
                                     const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
-                                    float amp = (__logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
+                                    float amp = (logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
                                     if (p.power != 1.f) amp = powf(amp, p.power);
                                     p.out[((size_t)b * p.F + g.bin_lo + j0 + j) * p.To + t] = amp;
                                 }
@@ -317,7 +494,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                             if (emit && j < nb) {
                                 const int f = g.bin_lo + j0 + j;
                                 const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
-                                float amp = (__logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
+                                float amp = (logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
                                 float pd = ph[j] - prev + __ldg(p.phase_fixed + f);
                                 if (pd > kPi) pd -= 2.f * kPi;
                                 if (pd < -kPi) pd += 2.f * kPi;
@@ -332,7 +509,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+            if (lane == 0) mbar_arrive(&bars->acc_empty);
             ++tn;
         }
     }
@@ -344,10 +521,13 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
 // ---- host side --------------------------------------------------------------------------------------
 struct CqtUmmaPlan {
     bool ok;
-    int n_tensor_groups;          // groups [0, n) run here, the rest (K < 128) on the CUDA-core kernel
+    int n_tensor_groups;          // groups [0, n) run here, the rest on the CUDA-core kernel
     int NP, halves, S, Lp;
-    size_t audio_bytes, filter_bytes, total_rows;
+    size_t audio_bytes, filter_bytes, fmeta_bytes, meta_bytes, total_rows;
 };
+
+// tap count of group g on the tensor path: groups shorter than 128 taps are zero-padded (centred) to 128
+static inline int cq_eff_k(int k) { return k < 128 ? 128 : k; }
 
 static CqtUmmaPlan cqt_umma_plan(const cpc_cqt_params* p) {
     CqtUmmaPlan u{};
@@ -357,9 +537,12 @@ static CqtUmmaPlan cqt_umma_plan(const cpc_cqt_params* p) {
     const int k0 = p->kernel_size[0];
     if (k0 < 128 || k0 / p->hop > 128) return u;                      // slab holds 128 frames + 127 row shifts
     int n = 0, np = 16;
-    while (n < p->n_groups && p->kernel_size[n] >= 128) {
+    while (n < p->n_groups) {
+        const int ke = cq_eff_k(p->kernel_size[n]);
+        // the group's window must start on a 64-sample boundary of the slab and consist of whole 64-tap chunks
+        if (ke > k0 || (ke & 63) || (((k0 - ke) / 2) & 63) || ((ke - p->kernel_size[n]) & 1)) break;
         const int n2 = 2 * (p->bin_hi[n] - p->bin_lo[n]);
-        if (n2 > 64) return u;
+        if (n2 > 64) break;
         const int need = 2 * (((n2 >> 1) + 7) & ~7);                 // real | imag halves, each a multiple of 8 columns
         np = need > np ? need : np;
         ++n;
@@ -372,72 +555,128 @@ static CqtUmmaPlan cqt_umma_plan(const cpc_cqt_params* p) {
     u.Lp = u.S * p->hop;
     u.audio_bytes = align_up((size_t)2 * p->batch * u.Lp * 2, 1024);
     size_t rows = 0;
-    for (int g = 0; g < n; ++g) rows += (size_t)(p->kernel_size[g] / 64) * 2 * u.NP;
+    for (int g = 0; g < n; ++g) rows += (size_t)(cq_eff_k(p->kernel_size[g]) / 64) * 2 * u.NP;
     u.total_rows = rows;
     u.filter_bytes = align_up(rows * 128, 1024);
+    u.fmeta_bytes = align_up(sizeof(CqFilterMeta) + (size_t)p->n_bins * 4, 1024);     // CqFilterMeta | inv_bin (F f32)
+    u.meta_bytes = align_up(sizeof(CqMeta) + 16 + (size_t)p->batch * 8, 1024);        // CqMeta | item_max | inv_item
     u.ok = true;
     return u;
 }
 
 bool cqt_umma_eligible(const cpc_cqt_params* p) { return cqt_umma_plan(p).ok; }
 int cqt_umma_tensor_groups(const cpc_cqt_params* p) { return cqt_umma_plan(p).n_tensor_groups; }
+size_t cqt_umma_packed_filter_bytes(const cpc_cqt_params* p) {
+    CqtUmmaPlan u = cqt_umma_plan(p);
+    return u.ok ? u.filter_bytes + u.fmeta_bytes + 1024 : 0;
+}
 size_t cqt_umma_workspace(const cpc_cqt_params* p) {
     CqtUmmaPlan u = cqt_umma_plan(p);
-    return u.ok ? u.audio_bytes + u.filter_bytes + 256 + 1024 : 0;
+    return u.ok ? u.audio_bytes + u.meta_bytes + 1024 + cqt_umma_packed_filter_bytes(p) : 0;
 }
 
-// Computes groups [0, n_tensor_groups) straight into `out` in the requested mode.
-int cqt_umma_launch(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale, float* out,
-                    const cpc_cqt_params* p, void* workspace, size_t workspace_bytes, cudaStream_t s) {
-    CqtUmmaPlan u = cqt_umma_plan(p);
-    if (!u.ok) return CPC_ERR_UNSUPPORTED;
-    if (!workspace || workspace_bytes < cqt_umma_workspace(p)) return CPC_ERR_WORKSPACE;
-    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + u.audio_bytes);
-    int* counter = reinterpret_cast<int*>(ws + u.audio_bytes + u.filter_bytes);
-    if (cudaMemsetAsync(counter, 0, sizeof(int), s) != cudaSuccess) return CPC_ERR_CUDA;
-    {
-        const long groups = (long)p->batch * (u.Lp / 8);
-        int blocks = (int)((groups + 255) / 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        cqt_pack_audio_kernel<<<blocks, 256, 0, s>>>(x, xp, p->batch, p->n_samples, p->x_pitch, u.Lp);
-        CPC_LAUNCH_CHECK();
-    }
-    CqtUmma k{};
+static void cq_fill_groups(const cpc_cqt_params* p, const CqtUmmaPlan& u, CqtUmma& k) {
     int row0 = 0;
     for (int g = 0; g < u.n_tensor_groups; ++g) {
         CqGroup& q = k.g[g];
-        q.K = p->kernel_size[g];
+        q.K = cq_eff_k(p->kernel_size[g]);
         q.off = (p->kernel_size[0] - q.K) / 2;
         q.n_g = p->bin_hi[g] - p->bin_lo[g];
         q.bin_lo = p->bin_lo[g];
         q.n_chunks = q.K / 64;
         q.w_row0 = row0;
-        const long total = (long)q.n_chunks * u.NP * 64;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > 148 * 4) blocks = 148 * 4;
-        cqt_pack_filters_kernel<<<blocks, 256, 0, s>>>(weights + p->weight_offset[g], wp, q.K, 2 * q.n_g, u.NP, row0);
-        CPC_LAUNCH_CHECK();
+        q.wide = (q.K >= CQ_WIDE_MIN_K && 2 * u.NP <= CQ_ACC_COLS) ? 1 : 0;
+        q.n_seg = q.K >= CQ_SEG4_MIN_K ? 4 : (q.K >= CQ_SEG2_MIN_K ? 2 : 1);
+        while (q.n_seg > 1 && q.n_seg * (q.wide ? 2 : 1) * u.NP > CQ_ACC_COLS) q.n_seg >>= 1;
         row0 += q.n_chunks * 2 * u.NP;
     }
-    // sets: consecutive groups, each at most 512 / NP accumulators, greedily balanced towards equal tap counts
+}
+
+// Packs the filterbank of groups [0, n_tensor_groups) into `packed` (cqt_umma_packed_filter_bytes): fp16 hi / lo rows,
+// per-bin scales and the live tap range of every group.  The result only depends on the weights: callers keep it.
+int cqt_umma_pack_filters(const float* weights, void* packed, const cpc_cqt_params* p, cudaStream_t s) {
+    CqtUmmaPlan u = cqt_umma_plan(p);
+    if (!u.ok) return CPC_ERR_UNSUPPORTED;
+    uint8_t* pk = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(packed) + 1023) & ~(uintptr_t)1023);
+    __half* wp = reinterpret_cast<__half*>(pk);
+    CqFilterMeta* fm = reinterpret_cast<CqFilterMeta*>(pk + u.filter_bytes);
+    float* inv_bin = reinterpret_cast<float*>(pk + u.filter_bytes + sizeof(CqFilterMeta));
+    CqtUmma k{};
+    cq_fill_groups(p, u, k);
+    cqt_init_filter_meta_kernel<<<1, 32, 0, s>>>(fm);
+    CPC_LAUNCH_CHECK();
+    for (int g = 0; g < u.n_tensor_groups; ++g) {
+        const CqGroup& q = k.g[g];
+        const int k_src = p->kernel_size[g];
+        cqt_pack_filters_kernel<<<u.NP / 2, 256, 0, s>>>(weights + p->weight_offset[g], wp, inv_bin, fm, g, q.K, k_src,
+                                                        (q.K - k_src) / 2, q.n_g, u.NP, q.w_row0, q.bin_lo);
+        CPC_LAUNCH_CHECK();
+    }
+    count_launch(1 + u.n_tensor_groups);
+    return CPC_OK;
+}
+
+// Computes groups [0, n_tensor_groups) straight into `out` in the requested mode.  `packed_filters` (optional): the
+// caller's copy made by cqt_umma_pack_filters; without it the filters are packed into the workspace on every call.
+int cqt_umma_launch(const float* x, const float* weights, const void* packed_filters, const float* phase_fixed,
+                    const float* phase_scale, float* out, const cpc_cqt_params* p, void* workspace, size_t workspace_bytes,
+                    cudaStream_t s) {
+    CqtUmmaPlan u = cqt_umma_plan(p);
+    if (!u.ok) return CPC_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < cqt_umma_workspace(p)) return CPC_ERR_WORKSPACE;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    __half* xp = reinterpret_cast<__half*>(ws);
+    uint8_t* mb = ws + u.audio_bytes;
+    CqMeta* meta = reinterpret_cast<CqMeta*>(mb);
+    uint32_t* item_max = reinterpret_cast<uint32_t*>(mb + 16);
+    float* inv_item = reinterpret_cast<float*>(item_max + p->batch);
+    if (!packed_filters) {
+        void* own = ws + u.audio_bytes + u.meta_bytes;
+        const int st = cqt_umma_pack_filters(weights, own, p, s);
+        if (st != CPC_OK) return st;
+        packed_filters = own;
+    }
+    const uint8_t* pk = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(packed_filters) + 1023) & ~(uintptr_t)1023);
+    const __half* wp = reinterpret_cast<const __half*>(pk);
+    const CqFilterMeta* fm = reinterpret_cast<const CqFilterMeta*>(pk + u.filter_bytes);
+    const float* inv_bin = reinterpret_cast<const float*>(pk + u.filter_bytes + sizeof(CqFilterMeta));
+    {
+        cqt_init_meta_kernel<<<ceil_div(p->batch, 256), 256, 0, s>>>(meta, item_max, p->batch);
+        CPC_LAUNCH_CHECK();
+        int bx = ceil_div(p->n_samples, 256 * 4 * 8);                 // ~8 float4 loads per thread
+        if (bx < 1) bx = 1;
+        cqt_item_max_kernel<<<dim3(bx, p->batch), 256, 0, s>>>(x, item_max, p->n_samples, p->x_pitch);
+        CPC_LAUNCH_CHECK();
+        const long groups = (long)p->batch * (u.Lp / 8);
+        int blocks = (int)((groups + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cqt_pack_audio_kernel<<<blocks, 256, 0, s>>>(x, xp, item_max, inv_item, p->batch, p->n_samples, p->x_pitch, u.Lp);
+        CPC_LAUNCH_CHECK();
+    }
+    CqtUmma k{};
+    cq_fill_groups(p, u, k);
+    // sets: consecutive groups whose accumulator columns fit one TMEM buffer, greedily balanced towards equal tap counts
     {
         long total = 0;
         for (int g = 0; g < u.n_tensor_groups; ++g) total += k.g[g].K;
-        const int max_per_set = CQ_ACC_COLS / u.NP;
         const long target = (total + 2) / 3;
         int g = 0;
         k.n_sets = 0;
         while (g < u.n_tensor_groups) {
-            int cnt = 0;
+            int cnt = 0, cols = 0;
             long acc = 0;
             const bool last_slot = k.n_sets == CQ_MAX_SETS - 1;
-            while (g + cnt < u.n_tensor_groups && cnt < max_per_set && (cnt == 0 || last_slot || acc + k.g[g + cnt].K <= target)) {
-                acc += k.g[g + cnt].K;
+            while (g + cnt < u.n_tensor_groups) {
+                const CqGroup& q = k.g[g + cnt];
+                const int need = q.n_seg * (q.wide ? 2 * u.NP : u.NP);
+                if (cols + need > CQ_ACC_COLS) break;
+                if (cnt > 0 && !last_slot && acc + q.K > target) break;
+                k.g[g + cnt].col = cols;
+                cols += need;
+                acc += q.K;
                 ++cnt;
             }
-            if (last_slot && g + cnt < u.n_tensor_groups) return CPC_ERR_UNSUPPORTED;
+            if (cnt == 0 || (last_slot && g + cnt < u.n_tensor_groups)) return CPC_ERR_UNSUPPORTED;
             k.set_first[k.n_sets] = g;
             k.set_count[k.n_sets] = cnt;
             ++k.n_sets;
@@ -446,6 +685,7 @@ int cqt_umma_launch(const float* x, const float* weights, const float* phase_fix
     }
     CUtensorMap tx, tw;
     {
+        // 16-bit elements: the tensor maps only move bytes, so the bf16 encoder serves the fp16 planes
         const uint64_t dims[4] = {(uint64_t)p->hop, (uint64_t)u.S, (uint64_t)p->batch, 2};
         const uint64_t strides[3] = {(uint64_t)p->hop * 2, (uint64_t)u.Lp * 2, (uint64_t)u.Lp * 2 * p->batch};
         const uint32_t box[4] = {64, CQ_SLAB_ROWS, 1, 2};
@@ -456,6 +696,7 @@ int cqt_umma_launch(const float* x, const float* weights, const float* phase_fix
         if (!make_tmap_bf16(&tw, wp, 3, wd, wsr, wbox)) return CPC_ERR_CUDA;
     }
     k.B = p->batch; k.T = p->n_frames; k.F = p->n_bins; k.hop = p->hop; k.halves = u.halves; k.NP = u.NP;
+    k.n_groups = u.n_tensor_groups;
     k.mode = p->mode;
     k.fpb = p->mode == CPC_CQT_LOGPOW_PHASE ? 127 : 128;
     const int t_out = p->mode == CPC_CQT_LOGPOW_PHASE ? p->n_frames - 1 : p->n_frames;
@@ -463,15 +704,15 @@ int cqt_umma_launch(const float* x, const float* weights, const float* phase_fix
     k.n_blocks = ceil_div(t_out, k.fpb);
     k.n_tiles = k.n_sets * k.B * k.n_blocks;
     k.eps = p->eps; k.log_offset = p->log_offset; k.norm = p->norm; k.power = p->power;
-    { const char* e = std::getenv("CPC_CQT_BASE_OFFSET"); k.base_offset = (e && e[0] == '1') ? 1 : 0; }
-    k.phase_fixed = phase_fixed; k.phase_scale = phase_scale; k.out = out; k.counter = counter;
+    k.phase_fixed = phase_fixed; k.phase_scale = phase_scale; k.out = out; k.meta = meta; k.fmeta = fm;
+    k.inv_item = inv_item; k.inv_bin = inv_bin;
     const size_t smem_bytes = (size_t)u.halves * 2 * CQ_SLAB_PLANE + (size_t)CQ_BSTAGES * 2 * u.NP * 128 + sizeof(CqBarriers) + 1024;
     if (cudaFuncSetAttribute(cqt_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int grid = k.n_tiles < 148 ? k.n_tiles : 148;
     cqt_umma_kernel<<<grid, CQ_THREADS, smem_bytes, s>>>(tx, tw, k);
     CPC_LAUNCH_CHECK();
-    count_launch(2 + u.n_tensor_groups);
+    count_launch(4);
     return CPC_OK;
 }
 

@@ -26,10 +26,9 @@ int nce_umma_fwd(const float* pred, const float* targets, float* out, float* lse
 int nce_umma_bwd(const float* pred, const float* targets, const float* lse, const float* grad_loss, float* d_pred,
                  float* d_targets, const cpc_infonce_params* p, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
-// CPC_NO_TENSOR_INFONCE=1 keeps everything on the CUDA-core kernels (A/B switch for tests)
+// flags & CPC_INFONCE_FLAG_NO_TENSOR keeps everything on the CUDA-core kernels (A/B switch for tests)
 static bool nce_tensor_path(const cpc_infonce_params* p, int which) {
-    const char* e = std::getenv("CPC_NO_TENSOR_INFONCE");
-    if (e && e[0] == '1') return false;
+    if (p->flags & CPC_INFONCE_FLAG_NO_TENSOR) return false;
     return nce_umma_eligible(p, which);
 }
 

@@ -85,13 +85,25 @@ typedef struct cpc_cqt_params {
     float log_offset;       /* added after log                                                       */
     float norm;             /* multiplied after the offset                                           */
     float power;            /* exponent applied last (1 = skipped)                                   */
+    int32_t flags;          /* CPC_CQT_FLAG_*: kernel selection switches (A/B tests); 0 = default     */
 } cpc_cqt_params;
+#define CPC_CQT_FLAG_NO_TENSOR 1   /* every octave group on the fp32 CUDA-core kernels                  */
 
 size_t cpc_cqt_workspace_bytes(const cpc_cqt_params* p);
 /* x (B, x_pitch) fp32; weights: packed group blocks, fp32; phase_fixed / phase_scale: (n_bins) fp32, only
  * read in CPC_CQT_LOGPOW_PHASE (PhaseDifference, constant_q_transform.py:275-286); out: see cpc_cqt_mode. */
 int cpc_cqt_fwd(const float* x, const float* weights, const float* phase_fixed, const float* phase_scale,
                 float* out, const cpc_cqt_params* p, void* workspace, size_t workspace_bytes, void* stream);
+/* The tensor-core filterbank reads the filters as scaled fp16 hi/lo planes.  That form only depends on the weights
+ * (fixed after CQT.__init__, constant_q_transform.py:141-146, unless trainable): cpc_cqt_pack_filters writes it once
+ * into a caller-owned buffer of cpc_cqt_packed_filter_bytes (0 = this configuration has no tensor-core path) and
+ * cpc_cqt_fwd_ex takes it back on every call (packed_filters == NULL: packed into the workspace per call, as cpc_cqt_fwd
+ * does).  The packed form depends on the filterbank fields of p only (groups, bins, hop), not on batch / length. */
+size_t cpc_cqt_packed_filter_bytes(const cpc_cqt_params* p);
+int cpc_cqt_pack_filters(const float* weights, void* packed, const cpc_cqt_params* p, void* stream);
+int cpc_cqt_fwd_ex(const float* x, const float* weights, const void* packed_filters, const float* phase_fixed,
+                   const float* phase_scale, float* out, const cpc_cqt_params* p, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 2. Strided convolution, forward / data gradient / weight gradient.  conv1d is h = 1.
@@ -110,7 +122,12 @@ typedef struct cpc_conv_params {
                                     folded in here); bottom / right padding is implied by h_out / w_out   */
     int32_t relu;                /* forward only: fuse max(.,0) into the epilogue                          */
     int32_t precision;           /* 0 = fp32-faithful (error <= 1e-5 relative), 1 = bf16 operands           */
+    int32_t flags;               /* CPC_CONV_FLAG_*: kernel selection switches (A/B tests); 0 = default     */
 } cpc_conv_params;
+#define CPC_CONV_FLAG_CUDA_CORE 1        /* no tensor-core kernel at all: the fp32 CUDA-core kernels          */
+#define CPC_CONV_FLAG_NO_TALL 2          /* kh x 1 convolutions on the generic tcgen05 kernel                 */
+#define CPC_CONV_FLAG_NO_SMALLK 4        /* tiny-K convolutions on the tiled kernels                          */
+#define CPC_CONV_FLAG_NO_FUSED_DGRAD 8   /* stride-2 data gradient as one launch per parity class             */
 
 size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which /* 0 fwd, 1 dgrad, 2 wgrad */);
 /* y = conv(x, w) + bias (bias may be NULL). */
@@ -229,7 +246,9 @@ typedef struct cpc_infonce_params {
     float regularization;   /* lambda of  lambda * mean((mean_k S)^2)  (:141) */
     int64_t tgt_stride_b, tgt_stride_e, tgt_stride_k;   /* in elements */
     int32_t precision;      /* as in cpc_conv_params */
+    int32_t flags;          /* CPC_INFONCE_FLAG_*; 0 = default */
 } cpc_infonce_params;
+#define CPC_INFONCE_FLAG_NO_TENSOR 1     /* everything on the fp32 CUDA-core kernels                          */
 
 /* Layout of the forward's `out` (fp32): [0] loss, [1] max score, [2] loss without regulariser,
  * [3] mean score; `lse`: per softmax column, all_steps ? (B*K) indexed t*K+k' : (K*B) indexed k*B+t.

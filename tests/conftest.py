@@ -19,6 +19,8 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    torch.backends.cudnn.allow_tf32 = False                     # every comparison in here is against fp32 references
+    torch.backends.cuda.matmul.allow_tf32 = False
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

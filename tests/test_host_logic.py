@@ -77,6 +77,7 @@ def test_conv_dispatch_table_for_the_baseline_layers(built_lib):
     """Host-side dispatch (no device needed): which kernel family serves forward / dgrad / wgrad of every arch-7 conv at
     the BASELINE sizes, and the size of the canonical packed operands -- two dy replicas exactly for the strided convs
     whose data gradient reads column-shifted copies."""
+    import cpc_b200
     from cpc_b200 import _lib
     lib = _lib.load()
 
@@ -113,12 +114,21 @@ def test_conv_dispatch_table_for_the_baseline_layers(built_lib):
     p.precision = 1
     assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 4                   # row-streaming kernels are fp32-faithful only
     p.precision = 0
+    p.flags = _lib.CONV_FLAG_CUDA_CORE                                           # per-call switch in the struct: no global state
+    assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 0
+    assert lib.cpc_conv_packed_bytes(ctypes.byref(p), 1) == 0
+    p.flags = _lib.CONV_FLAG_NO_TALL
+    assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 4
+    # ... and the environment is NOT consulted by the library (header: "no global state")
+    p.flags = 0
     os.environ["CPC_FORCE_CUDA_CORE_CONV"] = "1"
     try:
-        assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 0
-        assert lib.cpc_conv_packed_bytes(ctypes.byref(p), 1) == 0
+        assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 2
+        # the host mirror turns the same names into flags at call time
+        assert cpc_b200.ops._conv_flags() & _lib.CONV_FLAG_CUDA_CORE
     finally:
         del os.environ["CPC_FORCE_CUDA_CORE_CONV"]
+    assert cpc_b200.ops._conv_flags() == 0
 
 
 def test_second_order_switch_and_block_tail_gate():

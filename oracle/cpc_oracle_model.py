@@ -108,6 +108,34 @@ class OracleE24(nn.Module):
         return pred, targets
 
 
+class OracleRawWave(nn.Module):
+    """BASELINE configs[0]: AudioEncoder (audio_model.py:14-44, default dict: 512 channels, strides 5,4,2,2,2) ->
+    AudioGRUModel(512, 256) (audio_model.py:47-77: a GRUCell unrolled over the visible steps) -> Linear(256 -> K*512)."""
+
+    def __init__(self, visible_steps=100, prediction_steps=12, channels=512, ar_size=256):
+        super().__init__()
+        self.kernel_sizes, self.strides = [10, 8, 4, 4, 4], [5, 4, 2, 2, 2]
+        widths = [1] + (list(channels) if isinstance(channels, (list, tuple)) else [channels] * 5)
+        channels = widths[-1]
+        self.convs = nn.ModuleList(nn.Conv1d(widths[i], widths[i + 1], k, stride=s)
+                                   for i, (k, s) in enumerate(zip(self.kernel_sizes, self.strides)))
+        self.gru = nn.GRUCell(channels, ar_size)
+        self.v, self.k, self.e = visible_steps, prediction_steps, channels
+        self.predict = nn.Linear(ar_size, self.k * self.e, bias=False)
+        rf, ds = O.audio_encoder_geometry(self.kernel_sizes, self.strides)
+        self.item_length = rf + (visible_steps + prediction_steps) * ds
+
+    def forward(self, audio):
+        z = O.audio_encoder_forward(audio.unsqueeze(1), [c.weight for c in self.convs], [c.bias for c in self.convs],
+                                    self.strides)
+        targets, vis = O.predictive_split(z, self.v, self.k)
+        h = None
+        for t in range(vis.shape[2]):
+            h = self.gru(vis[:, :, t], h)
+        pred = self.predict(h).view(-1, self.k, self.e)
+        return pred, targets
+
+
 def train_steps(model, audio_batches, lr=1e-4, all_steps=True, kind='linear', regularization=0.0):
     """Runs one optimiser step per batch; returns the list of loss values."""
     opt = torch.optim.Adam(model.parameters(), lr=lr)

@@ -1225,3 +1225,22 @@ def test_adam_state_dict_round_trip_and_flat_gradients(cpc):
     for a, b in zip(p_ref, p_new):
         assert torch.allclose(a, b, rtol=2e-6, atol=2e-7)
     assert float(new.state_dict()['state'][0]['step']) == 6.0
+
+
+def test_two_rank_nccl_parity(cpc):
+    """SURVEY 8e on hardware (needs two GPUs, skips otherwise): one process per GPU over NCCL, contiguous shards, per-GPU
+    negatives; per-rank loss / gradients against the CPU oracle on that shard, averaged gradients against the mean of the
+    per-shard oracle gradients, and the in-graph overlapped bucket all-reduce against the mean of per-rank gradients
+    (tests/nccl_parity_worker.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nccl_parity_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29733", worker],
+                         capture_output=True, text=True, timeout=300)
+    print(out.stdout[-3000:])
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "RANK_OK 0" in out.stdout and "RANK_OK 1" in out.stdout

@@ -140,7 +140,7 @@ def cpu_reference_arm(workload, steps, warmup, batch=None):
     return {"value": audio_s / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
             "sample": "%d steps of the same %s training step at batch %d (%.1f audio-s per step), torch CPU fp32, "
                       "%d threads, anomaly mode off" % (steps, workload, batch, audio_s, cores),
-            "ms_per_step": dt * 1e3, "item_length": model.item_length}
+            "ms_per_step": dt * 1e3, "item_length": int(model.item_length)}
 
 
 def workload_config(workload, n_gpus, batch, item_length):
@@ -243,8 +243,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model, pre, tkw, lr = build_workload(args.workload, dev)
     ddp.broadcast_parameters(model, 0)
-    length = model.item_length
-    b = args.batch or w["batch"]
+    length = int(model.item_length)
+    b = int(args.batch or w["batch"])
     trainer = cpc_b200.ContrastiveEstimationTrainer(model=model, dataset=None, device=dev, verbose=False, **tkw)
     optimizer = trainer.make_optimizer(lr)                      # torch.optim.Adam -> cpc_b200.optim.Adam (one kernel per step)
     use_graph = not args.no_graph

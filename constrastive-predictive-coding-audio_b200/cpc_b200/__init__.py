@@ -7,6 +7,7 @@ Public surface mirrors the reference's modules:
     ar_models: AudioGRUModel, ConvolutionalArModel, AttentionModel        (stock PyTorch, caller-side)
     trainer  : ContrastiveEstimationTrainer, linear/softplus/difference_score_function
     sampler  : FileBatchSampler, SyntheticAudioDataset
+    audio_dataset: AudioDataset, AudioTestingDataset (WAV folders as one item stream)
     ddp      : one-process-per-GPU gradient averaging
     optim    : Adam (torch.optim.Adam semantics, one kernel per step)
     snapshots: state_dict of the reference's whole-model snapshot pickles, without importing reference code
@@ -23,6 +24,7 @@ from .ar_models import AttentionModel, AudioGRUModel, ConvolutionalArBlock, Conv
 from .trainer import (ContrastiveEstimationTrainer, DeterministicSampler, GraphedTrainStep, difference_score_function,  # noqa: F401
                       linear_score_function, softplus_score_function)
 from .sampler import FileBatchSampler, SyntheticAudioDataset                  # noqa: F401
+from .audio_dataset import AudioDataset, AudioTestingDataset, list_all_audio_files  # noqa: F401
 from . import configs, ddp, optim, snapshots                                                    # noqa: F401
 
 __version__ = "0.1.0"

@@ -82,6 +82,9 @@ SIGNATURES = {
     "cpc_conv_fwd": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_dgrad": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
     "cpc_conv_wgrad": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ConvParams), _P, ctypes.c_size_t, _P]),
+    "cpc_dwconv_fwd": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P]),
+    "cpc_dwconv_dgrad": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P]),
+    "cpc_dwconv_wgrad": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(ConvParams), _P]),
     "cpc_conv_kernel_family": (ctypes.c_int, [ctypes.POINTER(ConvParams), ctypes.c_int]),
     "cpc_conv_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvParams), ctypes.c_int]),
     "cpc_conv_pack": (ctypes.c_int, [_P, _P, ctypes.POINTER(ConvParams), ctypes.c_int, _P]),

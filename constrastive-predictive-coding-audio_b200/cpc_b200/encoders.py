@@ -78,7 +78,7 @@ def _run_modules(modules, x):
             else:
                 pending_top += top
             continue
-        if isinstance(m, Conv2d):
+        if isinstance(m, (Conv2d, Conv2dSeparable)):
             x = m(x, extra_top=pending_top)
             pending_top = 0
             continue
@@ -118,8 +118,9 @@ class AudioEncoder(nn.Module):
 
 
 class Conv2dSeparable(nn.Module):
-    """scalogram_model.py:532-544 (depthwise + 1x1).  The depthwise half (groups = in_channels) has no B200
-    kernel yet; no shipped config sets ``separable=True``."""
+    """scalogram_model.py:532-544: depthwise conv (groups = in_channels, no bias) followed by a 1x1 conv.  Same
+    sub-module names (``conv``, ``conv_1x1``) and therefore state_dict keys; the depthwise half runs on
+    ``cpc_dwconv_*`` (memory-bound CUDA-core kernels), the 1x1 half on the implicit-GEMM kernels."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
         super().__init__()
@@ -131,8 +132,11 @@ class Conv2dSeparable(nn.Module):
     def weight(self):
         return self.conv.weight
 
-    def forward(self, x):
-        raise NotImplementedError("separable (depthwise) convolutions are not implemented on the B200 path")
+    def forward(self, x, extra_top=0):
+        dw = self.conv
+        if dw.dilation != (1, 1) or dw.padding_mode != 'zeros' or isinstance(dw.padding, str):
+            raise NotImplementedError("cpc_b200.Conv2dSeparable supports dilation=1, zero padding")
+        return self.conv_1x1(ops.depthwise_conv2d(x, dw.weight, dw.stride, dw.padding, extra_top))
 
 
 class ScalogramEncoder(nn.Module):

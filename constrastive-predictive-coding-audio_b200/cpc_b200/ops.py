@@ -374,6 +374,73 @@ def conv_transpose1d(x, weight, stride=1, padding=0, precision=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# depthwise convolution (the first half of Conv2dSeparable)
+# --------------------------------------------------------------------------------------------------
+
+class _DepthwiseConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad_top, pad_left, out_hw):
+        _require_cuda(x, weight)
+        lib = _lib.load()
+        x, w = x.contiguous(), weight.contiguous()
+        if x.dtype != torch.float32 or w.dtype != torch.float32:
+            raise _lib.CpcError("depthwise conv expects fp32 tensors")
+        c = x.shape[1]
+        p = _conv_params(tuple(x.shape), (c, c, w.shape[2], w.shape[3]), stride, pad_top, pad_left, out_hw, False, "fp32")
+        y = torch.empty((x.shape[0], c, out_hw[0], out_hw[1]), dtype=torch.float32, device=x.device)
+        taps = w.shape[2] * w.shape[3]
+        with torch.cuda.device(x.device):
+            _call("cpc_dwconv_fwd b%d %dx%dx%d k%dx%d" % (x.shape[0], c, x.shape[2], x.shape[3], w.shape[2], w.shape[3]),
+                  2.0 * taps * y.numel(), lib.cpc_dwconv_fwd, _ptr(x), _ptr(w), _ptr(y), ctypes.byref(p), _stream(),
+                  nbytes=4.0 * (x.numel() + y.numel()))
+        ctx.geom = (tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw)
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    @once_differentiable                                         # second-order mode uses F.conv2d(groups=C) instead
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        lib = _lib.load()
+        x_shape, w_shape, stride, pad_top, pad_left, out_hw = ctx.geom
+        c = x_shape[1]
+        p = _conv_params(x_shape, (c, c, w_shape[2], w_shape[3]), stride, pad_top, pad_left, out_hw, False, "fp32")
+        dy = dy.contiguous()
+        dx = dw = None
+        tag = "b%d %dx%dx%d k%dx%d" % (x_shape[0], c, x_shape[2], x_shape[3], w_shape[2], w_shape[3])
+        with torch.cuda.device(dy.device):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
+                _call("cpc_dwconv_dgrad " + tag, 0.0, lib.cpc_dwconv_dgrad, _ptr(dy), _ptr(w), _ptr(dx), ctypes.byref(p),
+                      _stream(), nbytes=4.0 * (dx.numel() + dy.numel()))
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
+                _call("cpc_dwconv_wgrad " + tag, 0.0, lib.cpc_dwconv_wgrad, _ptr(x), _ptr(dy), _ptr(dw), ctypes.byref(p),
+                      _stream(), nbytes=4.0 * (x.numel() + dy.numel()))
+        return dx, dw, None, None, None, None
+
+
+def depthwise_conv2d(x, weight, stride=(1, 1), padding=(0, 0), extra_top=0):
+    """F.conv2d(zero_pad_top(x, extra_top), weight, None, stride, padding, groups=C) for weight (C, 1, kh, kw)."""
+    if isinstance(stride, int):
+        stride = (stride, stride)
+    if isinstance(padding, int):
+        padding = (padding, padding)
+    b, c, h, w_in = x.shape
+    if weight.shape[0] != c or weight.shape[1] != 1:
+        raise ValueError("depthwise weight must be (C, 1, kh, kw) with C = %d, got %s" % (c, tuple(weight.shape)))
+    kh, kw = weight.shape[2], weight.shape[3]
+    oh = (h + extra_top + 2 * padding[0] - kh) // stride[0] + 1
+    ow = (w_in + 2 * padding[1] - kw) // stride[1] + 1
+    if oh <= 0 or ow <= 0:
+        raise ValueError("conv output would be empty: input %s kernel %s" % (tuple(x.shape), (kh, kw)))
+    if _second_order:
+        import torch.nn.functional as F
+        return F.conv2d(F.pad(x, (0, 0, extra_top, 0)) if extra_top else x, weight, None, stride, padding, groups=c)
+    return _DepthwiseConvFunction.apply(x, weight, tuple(stride), extra_top + padding[0], padding[1], (oh, ow))
+
+
+# --------------------------------------------------------------------------------------------------
 # fused BatchNorm2d + ReLU (+ cropped residual add + ReLU)
 # --------------------------------------------------------------------------------------------------
 

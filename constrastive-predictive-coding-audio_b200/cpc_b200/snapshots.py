@@ -10,8 +10,10 @@ reference's attribute names, the *state_dict* of a snapshot maps one to one onto
     model, pre, _ = cpc_b200.configs.setup_model(...)          # same experiment dicts as the reference run
     step = cpc_b200.snapshots.load_reference_snapshot(model, "snapshots/e24_120000")
 
-Unknown classes inside the pickle are materialised as inert stand-ins (``nn.Module`` subclasses for modules, plain
-objects otherwise); only tensors, containers and torch's own classes are ever instantiated.
+Reference classes inside the pickle are materialised as inert stand-ins (``nn.Module`` subclasses for modules, plain
+objects otherwise).  Every other global must be on an exact allow-list (tensor / storage rebuild functions, dtypes,
+``torch.nn.modules.*`` layer classes, containers, numpy array reconstruction); anything else -- including callables that
+are merely reachable under the ``torch`` package -- is refused.
 """
 import collections
 import io
@@ -50,10 +52,23 @@ def _stub_class(module, name, is_module=True):
 _NON_MODULES = {"ActivationRegister"}
 
 
-# everything else a model pickle legitimately needs; any other global is refused (a pickle can name arbitrary callables)
-_ALLOWED_ROOTS = ("torch", "collections", "numpy", "_codecs", "copyreg")
-_ALLOWED_BUILTINS = {"set", "frozenset", "dict", "list", "tuple", "slice", "range", "complex", "bytearray", "getattr",
-                     "object", "int", "float", "bool", "str", "bytes"}
+# Everything else a model pickle legitimately needs, as EXACT globals (a pickle can name any importable callable, and
+# re-exports such as torch.serialization.os or torch.hub.load live under the torch root, so roots are not enough).
+_ALLOWED_GLOBALS = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"), ("collections", "deque"),
+    ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch._utils", "_rebuild_qtensor"),
+    ("torch._utils", "_rebuild_device_tensor_from_numpy"), ("torch.storage", "_load_from_bytes"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "dtype"), ("torch.nn.parameter", "Parameter"),
+    ("torch.nn.parameter", "Buffer"), ("torch._tensor", "_rebuild_from_type_v2"), ("torch", "Tensor"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("_codecs", "encode"), ("copyreg", "_reconstructor"),
+}
+_ALLOWED_BUILTINS = {"set", "frozenset", "dict", "list", "tuple", "slice", "range", "complex", "bytearray", "object",
+                     "int", "float", "bool", "str", "bytes"}
+_TORCH_STORAGES = re.compile(r"^(Untyped|Float|Double|Half|BFloat16|Long|Int|Short|Char|Byte|Bool|Complex(Float|Double))Storage$")
+_TORCH_DTYPES = re.compile(r"^(float(16|32|64)|bfloat16|half|float|double|u?int(8|16|32|64)|long|int|short|bool|complex(64|128))$")
 
 
 class _SnapshotUnpickler(pickle.Unpickler):
@@ -61,10 +76,18 @@ class _SnapshotUnpickler(pickle.Unpickler):
         root = module.split(".")[0]
         if root in REFERENCE_MODULES or root == "__main__":
             return _stub_class(module, name, is_module=name not in _NON_MODULES)
-        if root in _ALLOWED_ROOTS or (root in ("builtins", "__builtin__") and name in _ALLOWED_BUILTINS):
-            return super().find_class(module, name)
-        raise pickle.UnpicklingError("snapshot names %s.%s, which is neither a reference class nor a torch / numpy / "
-                                     "container type" % (module, name))
+        allowed = ((module, name) in _ALLOWED_GLOBALS
+                   or (module in ("builtins", "__builtin__") and name in _ALLOWED_BUILTINS)
+                   or (module == "torch" and (_TORCH_STORAGES.match(name) or _TORCH_DTYPES.match(name))))
+        if not allowed and module.startswith("torch.nn.modules.") and "." not in name:
+            candidate = super().find_class(module, name)         # stock layers inside the model: nn.Module classes only
+            allowed = isinstance(candidate, type) and issubclass(candidate, nn.Module)
+        if allowed:
+            found = super().find_class(module, name)
+            if not isinstance(found, type(re)):                  # never hand out a module object
+                return found
+        raise pickle.UnpicklingError("snapshot names %s.%s, which is neither a reference class nor one of the torch / numpy "
+                                     "/ container globals a model pickle needs" % (module, name))
 
 
 class _PickleModule:

@@ -140,6 +140,13 @@ int cpc_conv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_pa
 int cpc_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, const cpc_conv_params* p,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Depthwise convolution (groups = channels, c_out == c_in, weight (C, 1, kh, kw), no bias): the first half of
+ * Conv2dSeparable (scalogram_model.py:532-544; the 1x1 half is cpc_conv_*).  Same geometry fields as above;
+ * relu / precision / flags are ignored (fp32 CUDA-core arithmetic, memory-bound). */
+int cpc_dwconv_fwd(const float* x, const float* w, float* y, const cpc_conv_params* p, void* stream);
+int cpc_dwconv_dgrad(const float* dy, const float* w, float* dx, const cpc_conv_params* p, void* stream);
+int cpc_dwconv_wgrad(const float* x, const float* dy, float* dw, const cpc_conv_params* p, void* stream);
+
 /* Which kernel family serves this configuration (for profiling / reporting; which: 0 fwd, 1 dgrad, 2 wgrad):
  * 0 tiled fp32 CUDA-core GEMM, 1 direct small-K kernel, 2 row-streaming tcgen05 (32 -> 32 channels, conv_tall.cu),
  * 3 row-streaming tcgen05 (128 output channels, conv_tall128.cu), 4 generic implicit-GEMM tcgen05; -1 bad params. */

@@ -95,6 +95,28 @@ def golden_cqt(ref):
     np.savez_compressed(os.path.join(OUT, "cqt.npz"), **out)
 
 
+def golden_cqt_high_res(ref):
+    """The high-resolution filterbank of experiments e27 ... e32 (configs/cqt_configs.py:9-12: 44.1 kHz, 292 bins, hop 256;
+    11 octave groups from 65 536 taps down to 64): CQT.forward and the PreprocessingModule variants those experiments use
+    (phase scalogram; offset_zero + pooling [1, 2] of scalogram_resnet_architecture_8 / 9), on a few frames."""
+    import importlib
+    sm = ref["scalogram_model"]
+    cq = ref["constant_q_transform"]
+    cc = importlib.import_module("configs.cqt_configs")
+    d = dict(cc.cqt_high_res_dict)
+    g = torch.Generator().manual_seed(2024)
+    cqt = cq.CQT(sr=d['sample_rate'], fmin=d['fmin'], n_bins=d['n_bins'], bins_per_octave=d['bins_per_octave'],
+                 filter_scale=d['filter_scale'], hop_length=d['hop_length'])
+    x = 0.1 * torch.randn(2, 1, cqt.conv_kernel_sizes[0] + 1 + d['hop_length'] * 6 + 17, generator=g)
+    out = {"x": x.numpy(), "kernel_sizes": np.array(cqt.conv_kernel_sizes),
+           "ranges": np.array([[r.start, r.stop] for r in cqt.conv_index_ranges]),
+           "cfg": np.array(json.dumps({k: v for k, v in d.items()})), "complex": cqt(x).numpy()}
+    out["phase"] = sm.PreprocessingModule(d, phase=True)(x).numpy()
+    out["offset_pool"] = sm.PreprocessingModule(d, phase=False, offset_zero=True, pooling=[1, 2])(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "cqt_high_res.npz"), **out)
+    print("high-res CQT: kernel sizes", cqt.conv_kernel_sizes, "frames", out["complex"].shape)
+
+
 def golden_cqt_grad(ref):
     """Gradients THROUGH the front end: d/d(audio) and d/d(filterbank) of the trainable CQT and
     of the phase scalogram, plus InverseCQT and PhaseAccumulation outputs (constant_q_transform.py:155-260, 294-313).
@@ -295,12 +317,12 @@ def golden_scalogram_encoder(ref):
     pad / conv / pool / ReLU / BatchNorm stack.  Small stacks, both input variants; forward, parameter gradients."""
     sm = ref["scalogram_model"]
     out = {}
-    for tag, phase in (("m", False), ("p", True)):
+    for tag, phase, separable in (("m", False, False), ("p", True, False), ("s", False, True)):
         torch.manual_seed(8)
         cfg = dict(sm.cqt_default_dict)
         cfg.update({'kernel_sizes': [(9, 1), (5, 5), (5, 1), (3, 3)], 'top_padding': [8, 0, 0, 0],
                     'channel_count': [1, 8, 8, 16, 24], 'pooling': [1, 2, 1, 2], 'stride': [1, 1, 1, 1], 'bias': True,
-                    'batch_norm': True, 'phase': phase, 'separable': False, 'lowpass_init': 0., 'instance_norm': False,
+                    'batch_norm': True, 'phase': phase, 'separable': separable, 'lowpass_init': 0., 'instance_norm': False,
                     'dropout': 0.})
         enc = sm.ScalogramEncoder(cfg)
         enc.train()
@@ -590,6 +612,56 @@ def golden_e24(ref):
     print("e24 golden: audio seed", audio_seed, "losses", logger.losses, "max scores", logger.scores, "order", order)
 
 
+AUDIO_DATASET_FILES = [("b_second.wav", 5000), ("a_first.wav", 1234), ("sub/c_third.wav", 8000), ("d_last.wav", 300)]
+
+
+def golden_audio_dataset(ref):
+    """The reference's AudioDataset / AudioTestingDataset index arithmetic and cross-file item assembly (audio_dataset.py:
+    75-165) with only ``load_file`` replaced (it calls a torchaudio 0.2 API that no longer exists): file k holds the samples
+    k*100000 + position, so an item lists exactly which (file, position) pairs the reference reads."""
+    import tempfile
+    ad = ref["audio_dataset"]
+    lengths = {}
+
+    def fake_loader(base):
+        class Stub(base):
+            def load_file(self, file, frames=-1, start=0):
+                name = os.path.relpath(str(file), str(self.location)).replace(os.sep, "/")
+                k = [n for n, _ in AUDIO_DATASET_FILES].index(name)
+                n = lengths[name]
+                stop = n if frames == -1 else min(n, int(start) + int(frames))
+                return (k * 100000 + torch.arange(int(start), stop)).type(self.dtype)
+        return Stub
+
+    out = {"files": AUDIO_DATASET_FILES, "cases": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, n in AUDIO_DATASET_FILES:
+            os.makedirs(os.path.dirname(os.path.join(tmp, name)), exist_ok=True)
+            open(os.path.join(tmp, name), "wb").close()
+            lengths[name] = n
+        for cls_name, item, unique in (("AudioDataset", 1000, 400), ("AudioDataset", 700, 700), ("AudioDataset", 1500, 64),
+                                       ("AudioTestingDataset", 250, 100)):
+            ds = fake_loader(getattr(ad, cls_name))(tmp, item_length=item, unique_length=unique)
+            case = {"class": cls_name, "item_length": item, "unique_length": unique, "len": len(ds),
+                    "order": [os.path.relpath(str(f), tmp).replace(os.sep, "/") for f in ds.files],
+                    "start_samples": [int(v) for v in ds.start_samples],
+                    "counts": [int(v) for v in ds.get_example_count_per_file()], "items": {}}
+            for idx in sorted(set([0, 1, 2, len(ds) // 3, len(ds) // 2, len(ds) - 2, len(ds) - 1] + list(range(10, 16)))):
+                if 0 <= idx < len(ds):
+                    item_value = ds[idx]
+                    label = None
+                    if cls_name == "AudioTestingDataset":
+                        item_value, label = item_value[0], int(item_value[1])
+                    v = item_value.long()
+                    case["items"][str(idx)] = {"first": int(v[0]), "last": int(v[-1]), "n": int(v.numel()),
+                                               "sum": int(v.sum()), "label": label,
+                                               "breaks": [int(i) for i in (v[1:] - v[:-1] != 1).nonzero().flatten()]}
+            out["cases"].append(case)
+    with open(os.path.join(OUT, "audio_dataset.json"), "w") as fh:
+        json.dump(out, fh)
+    print("audio dataset golden:", [(c["class"], c["len"], c["counts"]) for c in out["cases"]])
+
+
 def golden_sampler(ref):
     ad = ref["audio_dataset"]
     out, cases = {}, []
@@ -671,7 +743,9 @@ def main():
     ref = ref_shim.load_reference()
     golden_configs()
     golden_sampler(ref)
+    golden_audio_dataset(ref)
     golden_cqt(ref)
+    golden_cqt_high_res(ref)
     golden_audio_encoder(ref)
     golden_resnet_encoder(ref)
     golden_infonce(ref)

@@ -67,6 +67,26 @@ def test_cqt_complex_and_scalograms_match_reference_golden(cpc):
     assert rel_err(cqt2(torch.from_numpy(g["x2"]).to(DEV)), g["complex2"]) < TOL
 
 
+def test_high_res_cqt_matches_reference_golden(cpc):
+    """The filterbank of experiments e27 ... e32 (cqt_high_res_dict: 44.1 kHz, 292 bins, hop 256, 11 groups up to 65 536
+    taps) against the reference: complex transform, phase scalogram, offset + time-pooled scalogram."""
+    g = load_golden("cqt_high_res.npz")
+    cfg = json.loads(str(g["cfg"]))
+    x = torch.from_numpy(g["x"]).to(DEV)
+    cqt = cpc.CQT(sr=cfg["sample_rate"], fmin=cfg["fmin"], n_bins=cfg["n_bins"], bins_per_octave=cfg["bins_per_octave"],
+                  filter_scale=cfg["filter_scale"], hop_length=cfg["hop_length"]).to(DEV)
+    assert list(cqt.conv_kernel_sizes) == list(g["kernel_sizes"])
+    assert rel_err(cqt(x), g["complex"]) < TOL
+    pre = cpc.PreprocessingModule(dict(cfg), phase=True).to(DEV)
+    y = pre(x)
+    assert tuple(y.shape) == g["phase"].shape
+    assert rel_err(y[:, 0], g["phase"][:, 0]) < TOL
+    scale = pre.phase_diff.scaling.reshape(-1).cpu()
+    assert phase_err_fraction(y[:, 1], g["phase"][:, 1], scale) < 2e-3
+    y = cpc.PreprocessingModule(dict(cfg), phase=False, offset_zero=True, pooling=[1, 2]).to(DEV)(x)
+    assert rel_err(y, g["offset_pool"]) < TOL
+
+
 def test_cqt_matches_oracle_on_fresh_input_and_ragged_lengths(cpc):
     plan = O.CqtPlan(16000, 30, 256, 32, 0.5, 128)
     cqt = cpc.CQT(filter_scale=0.5).to(DEV)
@@ -412,7 +432,7 @@ def test_residual_encoder_matches_reference_golden(cpc):
 
 
 @pytest.mark.parametrize("tensor_cqt", [False, True])
-@pytest.mark.parametrize("tag,phase", [("m", False), ("p", True)])
+@pytest.mark.parametrize("tag,phase", [("m", False), ("p", True), ("s", False)])
 def test_scalogram_encoder_matches_reference_golden(cpc, monkeypatch, tag, phase, tensor_cqt):
     """ScalogramEncoder (scalogram_model.py:129-227): own CQT -> log power (+ phase difference) ->
     ZeroPad / conv / pool / ReLU / BatchNorm stack, forward and parameter gradients against the reference.  Held to 1e-3
@@ -424,8 +444,8 @@ def test_scalogram_encoder_matches_reference_golden(cpc, monkeypatch, tag, phase
     cfg = dict(cpc.cqt_default_dict)
     cfg.update({'kernel_sizes': [(9, 1), (5, 5), (5, 1), (3, 3)], 'top_padding': [8, 0, 0, 0],
                 'channel_count': [1, 8, 8, 16, 24], 'pooling': [1, 2, 1, 2], 'stride': [1, 1, 1, 1], 'bias': True,
-                'batch_norm': True, 'phase': phase, 'separable': False, 'lowpass_init': 0., 'instance_norm': False,
-                'dropout': 0.})
+                'batch_norm': True, 'phase': phase, 'separable': tag == "s", 'lowpass_init': 0., 'instance_norm': False,
+                'dropout': 0.})                                # tag "s": Conv2dSeparable layers (scalogram_model.py:532-544)
     enc = cpc.ScalogramEncoder(dict(cfg, channel_count=list(cfg['channel_count'])))
     assert enc.receptive_field == int(g["rf"]) and int(enc.downsampling_factor) == int(g["ds"])
     sd = {k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("p.")}
@@ -454,7 +474,7 @@ def test_scalogram_encoder_matches_reference_golden(cpc, monkeypatch, tag, phase
         if k.endswith("running_mean") or k.endswith("running_var"):
             assert rel_err(enc.state_dict()[k], g["p." + k]) < tol, k
     # a trainable filterbank takes the differentiable front end: same values
-    if not tensor_cqt:
+    if not tensor_cqt and tag != "s":
         enc_t = cpc.ScalogramEncoder(dict(cfg, channel_count=list(cfg['channel_count']), trainable_cqt=True))
         enc_t.load_state_dict(sd, strict=False)
         enc_t.to(DEV).train()
@@ -467,6 +487,30 @@ def test_scalogram_encoder_matches_reference_golden(cpc, monkeypatch, tag, phase
 # ---------------------------------------------------------------------------------------------------
 # max pooling
 # ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", [
+    dict(b=2, c=8, h=40, w=37, kh=9, kw=1, stride=(1, 1), pad=(0, 0), top=8),
+    dict(b=3, c=5, h=21, w=30, kh=5, kw=5, stride=(1, 1), pad=(0, 0), top=0),
+    dict(b=2, c=16, h=33, w=41, kh=3, kw=3, stride=(2, 2), pad=(1, 1), top=0),
+    dict(b=1, c=32, h=70, w=64, kh=63, kw=1, stride=(1, 1), pad=(0, 0), top=0),
+])
+def test_depthwise_conv_matches_torch(cpc, shape):
+    """cpc_dwconv_* (the depthwise half of Conv2dSeparable) against F.conv2d(groups=C) in float64: forward, data and
+    weight gradients."""
+    sh = shape
+    gen = torch.Generator().manual_seed(13)
+    x = torch.randn(sh['b'], sh['c'], sh['h'], sh['w'], generator=gen)
+    w = torch.randn(sh['c'], 1, sh['kh'], sh['kw'], generator=gen) / math.sqrt(sh['kh'] * sh['kw'])
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = F.conv2d(F.pad(xr, (0, 0, sh['top'], 0)), wr, None, sh['stride'], sh['pad'], groups=sh['c'])
+    gy = torch.randn(yr.shape, generator=gen)
+    (yr * gy.double()).sum().backward()
+    xg, wg = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    y = cpc.ops.depthwise_conv2d(xg, wg, sh['stride'], sh['pad'], extra_top=sh['top'])
+    assert tuple(y.shape) == tuple(yr.shape)
+    (y * gy.to(DEV)).sum().backward()
+    assert rel_err(y, yr) < 1e-5 and rel_err(xg.grad, xr.grad) < 1e-5 and rel_err(wg.grad, wr.grad) < 1e-5
+
 
 @pytest.mark.parametrize("shape,k,ceil", [((2, 3, 9, 11), 2, True), ((2, 3, 9, 11), 2, False), ((1, 5, 12, 12), 3, True),
                                           ((3, 2, 7, 5), 4, True), ((2, 4, 127, 314), 2, True), ((1, 2, 6, 8), 1, False),

@@ -467,3 +467,73 @@ def test_preprocessing_identity_and_geometry_without_kernels():
         assert not pre.cqt.needs_autograd(x)
     with pytest.raises(NotImplementedError):
         cpc_b200.PreprocessingModule(d, pooling=[2, 2])
+
+
+def test_audio_dataset_matches_reference_index_logic(tmp_path):
+    """AudioDataset / AudioTestingDataset (audio_dataset.py:16-199) on real WAV files against the reference's
+    own index arithmetic and cross-file item assembly (tests/golden/audio_dataset.json: the reference classes with only the
+    decoder stubbed, oracle/make_golden.py::golden_audio_dataset), plus the native PCM reader and FileBatchSampler on top."""
+    import wave
+    import cpc_b200
+    g = load_golden("audio_dataset.json")
+    names = [n for n, _ in g["files"]]
+    lengths = dict((n, l) for n, l in g["files"])
+
+    def pcm(k, pos):                                             # int16 content of file k at position pos
+        return ((np.asarray(pos, dtype=np.int64) * 7 + k * 1000) % 30000 - 15000).astype(np.int16)
+
+    for k, (name, n) in enumerate(g["files"]):
+        path = tmp_path / name
+        path.parent.mkdir(parents=True, exist_ok=True)
+        with wave.open(str(path), "wb") as fh:
+            fh.setnchannels(2)
+            fh.setsampwidth(2)
+            fh.setframerate(16000)
+            stereo = np.stack([pcm(k, np.arange(n)), np.zeros(n, dtype=np.int16)], axis=1)   # channel 0 is what is read
+            fh.writeframes(stereo.tobytes())
+    for case in g["cases"]:
+        ds = getattr(cpc_b200, case["class"])(str(tmp_path), item_length=case["item_length"], unique_length=case["unique_length"])
+        order = [os.path.relpath(str(f), str(tmp_path)).replace(os.sep, "/") for f in ds.files]
+        assert order == case["order"]
+        assert [int(v) for v in ds.start_samples] == case["start_samples"]
+        assert len(ds) == case["len"] and [int(v) for v in ds.get_example_count_per_file()] == case["counts"]
+        for idx, want in case["items"].items():
+            item = ds[int(idx)]
+            if case["class"] == "AudioTestingDataset":
+                item, label = item
+                assert int(label) == want["label"]
+            assert item.dtype == torch.float32 and item.numel() == want["n"] == case["item_length"]
+            # rebuild the (file, position) sequence the reference read: runs of consecutive positions, a new file at a break
+            k, pos = divmod(want["first"], 100000)
+            expect, at, total = [], 0, 0
+            for brk in want["breaks"] + [want["n"] - 1]:
+                count = brk + 1 - at
+                expect.append(pcm(k, pos + np.arange(count)))
+                total += int((k * 100000 + pos + np.arange(count)).sum())
+                if brk != want["n"] - 1:
+                    k, pos, at = names.index(order[order.index(names[k]) + 1]), 0, brk + 1
+            assert total == want["sum"]
+            assert np.array_equal(item.numpy(), np.concatenate(expect).astype(np.float32) / 32768.0), (case["class"], idx)
+    # the sampler the trainer puts on top consumes the per-file counts
+    ds = cpc_b200.AudioDataset(str(tmp_path), item_length=1000, unique_length=400)
+    batches = list(cpc_b200.FileBatchSampler(ds.get_example_count_per_file(), batch_size=8, file_batch_size=4, seed=0))
+    assert batches and all(len(b) == 8 and max(b) < len(ds) for b in batches)
+    ds.dummy_load = True
+    assert ds[0].shape[0] == 1000
+    assert lengths["d_last.wav"] == 300 and cpc_b200.audio_dataset.read_wav(tmp_path / "d_last.wav", 5, 298).numel() == 2
+
+
+def test_snapshot_unpickler_refuses_globals_outside_the_allow_list():
+    """A snapshot may only name reference classes (stand-ins) and an exact list of torch / numpy / container globals:
+    `getattr`, re-exported modules under the torch root (torch.serialization.os) and arbitrary torch callables are refused."""
+    import io
+    import pickle
+    from cpc_b200 import snapshots
+    for payload in (b"cbuiltins\ngetattr\n.", b"ctorch.serialization\nos\n.", b"ctorch.hub\nload\n.",
+                    b"ctorch.utils.cpp_extension\nload\n.", b"cos\nsystem\n.", b"ctorch.nn.modules.module\n_addindent\n."):
+        with pytest.raises(pickle.UnpicklingError):
+            snapshots._SnapshotUnpickler(io.BytesIO(payload)).load()
+    assert snapshots._SnapshotUnpickler(io.BytesIO(b"ccollections\nOrderedDict\n.")).load() is __import__("collections").OrderedDict
+    assert snapshots._SnapshotUnpickler(io.BytesIO(b"ctorch.nn.modules.conv\nConv2d\n.")).load() is torch.nn.Conv2d
+    stub = snapshots._SnapshotUnpickler(io.BytesIO(b"caudio_model\nAudioEncoder\n.")).load()
+    assert issubclass(stub, torch.nn.Module) and stub.__name__ == "AudioEncoder"

@@ -43,6 +43,19 @@ def test_cqt_matches_reference(plan):
     assert rel_err(O.cqt_forward(torch.from_numpy(g["x2"]), plan2), g["complex2"]) < 1e-6
 
 
+def test_high_res_cqt_matches_reference():
+    """cqt_high_res_dict (configs/cqt_configs.py:9-12; experiments e27 ... e32): 11 octave groups, 65 536 ... 64 taps."""
+    g = load_golden("cqt_high_res.npz")
+    cfg = json.loads(str(g["cfg"]))
+    plan = O.CqtPlan(cfg["sample_rate"], cfg["fmin"], cfg["n_bins"], cfg["bins_per_octave"], cfg["filter_scale"], cfg["hop_length"])
+    assert plan.kernel_sizes == list(g["kernel_sizes"]) and [list(r) for r in plan.ranges] == g["ranges"].tolist()
+    x = torch.from_numpy(g["x"])
+    assert rel_err(O.cqt_forward(x, plan), g["complex"]) < 1e-6
+    y = O.preprocess(x, plan, phase=True)
+    assert rel_err(y[:, 0], g["phase"][:, 0]) < 1e-6
+    assert rel_err(O.preprocess(x, plan, offset_zero=True, pooling=[1, 2]), g["offset_pool"]) < 1e-6
+
+
 def test_cqt_input_gradients_match_reference():
     """d/d(audio) through the oracle's CQT and phase scalogram against the reference's autograd (cqt_grad.npz); also the
     PhaseAccumulation formula (constant_q_transform.py:306-313) restated inline."""

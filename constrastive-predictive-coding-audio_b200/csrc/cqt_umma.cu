@@ -25,9 +25,10 @@
 // The three products of a K step are TWO MMAs: the filter planes are stacked along N, [W_hi | W_lo], so that
 // X_hi * [W_hi | W_lo] fetches the audio window once for both (these MMAs are bound by the shared-memory operand
 // fetch, not by the tensor pipe), then X_lo * W_hi accumulates onto the W_lo columns; the epilogue adds the two column
-// blocks.  Short groups (K < 1024, 4 % of the work) use three N = NP MMAs into one column block instead, which lets
-// several of them share a tile.  Long groups split their tap range over up to four accumulator segments (see CQ_SEG4_MIN_K:
-// the tensor core's accumulator truncates), so a tile owns all 512 TMEM columns and tiles are not double-buffered.  64-tap chunks in which every filter of the group is zero (the centre-padding of
+// blocks.  Short groups (K < 512, 2 % of the work) use three N = NP MMAs into one column block instead, which lets
+// several of them share a tile.  Long groups accumulate in rounds of 16 chunks whose partial sums are added in registers
+// (see CQ_ROUND_CHUNKS: the tensor core's accumulator truncates); rounds alternate between two TMEM buffers, which also
+// overlaps the epilogue of a tile with the MMAs of the next.  64-tap chunks in which every filter of the group is zero (the centre-padding of
 // constant_q_transform.py:132-140: 25 % of the longest group) are found while packing the filters and skipped.
 #include "common.cuh"
 #include "umma.cuh"
@@ -38,22 +39,25 @@ namespace cpc {
 using namespace umma;
 
 constexpr int CQ_THREADS = 384;                        // 4 control warps + 2 x 4 epilogue warps
-constexpr int CQ_ACC_COLS = 512;                       // TMEM columns of a tile's accumulators (all of TMEM, one buffer)
+constexpr int CQ_ACC_COLS = 256;                       // TMEM columns per accumulator buffer (two buffers)
 constexpr int CQ_SLAB_ROWS = 256;
 constexpr int CQ_SLAB_PLANE = CQ_SLAB_ROWS * 128;        // 32 KB: one column half, one plane
 constexpr int CQ_BSTAGES = 5;
 constexpr int CQ_MAX_SETS = 8;
-constexpr int CQ_WIDE_MIN_K = 1024;                    // groups at least this long stack [W_hi | W_lo] along N
+constexpr int CQ_WIDE_MIN_K = 512;                     // groups at least this long stack [W_hi | W_lo] along N
 // The tensor core adds into its fp32 accumulator with truncation (measured: every accumulating MMA shrinks the running sum
 // by ~2^-26 of its magnitude, coherently, so the relative error of a group grows linearly with its number of K steps:
-// 1.05e-5 after the 768 steps of the 16384-tap group against 1.8e-6 for an fp32 FMA chain).  Long groups therefore
-// accumulate their tap range in CQ_SEG* separate column blocks ("segments") which the epilogue adds in registers.
-constexpr int CQ_SEG4_MIN_K = 8192, CQ_SEG2_MIN_K = 2048;
+// 1.05e-5 after the 768 steps of the 16384-tap group against 1.8e-6 for an fp32 FMA chain -- and being a coherent shrink
+// per bin it shifts the log-power scalogram by a per-bin constant, which hurts more than random noise of that size).
+// Sets of at most two (wide) groups therefore accumulate in ROUNDS of CQ_ROUND_CHUNKS 64-tap chunks (16: measured 0.64 ms /
+// 1.3e-6 on the longest group; 8: 0.70 ms / 7e-7; one round: 0.58 ms / 1.05e-5): a round starts a
+// fresh accumulator in one of the two TMEM buffers, and while the tensor core works on the next round in the other
+// buffer the epilogue warps pull the finished partial sums into registers and add them there (fp32, round to nearest).
+constexpr int CQ_ROUND_CHUNKS = 16;
 
 struct CqGroup {
     int K, off, n_g, bin_lo, n_chunks, w_row0;           // w_row0: first row of the group in the packed filters
-    int wide, col, n_seg;                                // wide: [main | correction] column blocks; col: first TMEM column;
-                                                         // n_seg: accumulator segments along the tap axis
+    int wide, col;                                       // wide: [main | correction] column blocks; col: first TMEM column
 };
 
 // Per-call device bookkeeping (workspace): the tile scheduler's counter.
@@ -70,6 +74,7 @@ struct CqtUmma {
     int B, T, F, hop, halves, n_blocks, fpb;             // fpb: new frames per tile (127 in phase mode, else 128)
     int NP;                                              // padded channel count per group (multiple of 16, <= 64)
     int n_sets, set_first[CQ_MAX_SETS], set_count[CQ_MAX_SETS];
+    int set_round[CQ_MAX_SETS];                          // chunks per group and round (CQ_ROUND_CHUNKS, or "all" = 1 << 20)
     int n_tiles;
     CqGroup g[CPC_CQT_MAX_GROUPS];
     int n_groups;
@@ -85,7 +90,7 @@ struct CqtUmma {
 };
 
 struct __align__(8) CqBarriers {
-    uint64_t bfull[CQ_BSTAGES], bempty[CQ_BSTAGES], slab_full, slab_empty, acc_full, acc_empty, sfull[2], sempty[2];
+    uint64_t bfull[CQ_BSTAGES], bempty[CQ_BSTAGES], slab_full, slab_empty, acc_full[2], acc_empty[2], sfull[2], sempty[2];
     uint32_t tmem_base;
     int tile_id[2];
     int c_lo[CPC_CQT_MAX_GROUPS], c_hi[CPC_CQT_MAX_GROUPS];   // live 64-tap chunk range of every group
@@ -268,9 +273,9 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
         for (int s = 0; s < CQ_BSTAGES; ++s) { mbar_init(&bars->bfull[s], 1); mbar_init(&bars->bempty[s], 1); }
         mbar_init(&bars->slab_full, 1);
         mbar_init(&bars->slab_empty, 1);
-        mbar_init(&bars->acc_full, 1);
-        mbar_init(&bars->acc_empty, 8);
         for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->acc_full[s], 1);
+            mbar_init(&bars->acc_empty[s], 8);
             mbar_init(&bars->sfull[s], 1);
             mbar_init(&bars->sempty[s], 9);
         }
@@ -292,6 +297,18 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
+    // rounds of a tile: every group of the set contributes its live chunks [c_lo + r*R, c_lo + (r+1)*R) to round r
+    auto set_rounds = [&](int set) {
+        const int R = p.set_round[set];
+        int n = 1;
+        for (int gi = 0; gi < p.set_count[set]; ++gi) {
+            const int gidx = p.set_first[set] + gi;
+            const int live = bars->c_hi[gidx] - bars->c_lo[gidx];
+            n = max(n, (live + R - 1) / R);
+        }
+        return n;
+    };
+
     if (warp == 0) {
         // ===== scheduler + TMA producer =====
         if (lane == 0) {
@@ -311,17 +328,19 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                 for (int h = 0; h < p.halves; ++h)
                     tma_load_4d(slab + h * 2 * CQ_SLAB_PLANE, &tmap_x, &bars->slab_full, h * 64, blk * p.fpb, b, 0);
                 ++tn;
-                for (int gi = 0; gi < p.set_count[set]; ++gi) {
-                    const int gidx = p.set_first[set] + gi;
-                    const CqGroup& g = p.g[gidx];
-                    const int c_hi = bars->c_hi[gidx];
-                    for (int c = bars->c_lo[gidx]; c < c_hi; ++c, ++bn) {
-                        const int stage = bn % CQ_BSTAGES;
-                        mbar_wait(&bars->bempty[stage], ((bn / CQ_BSTAGES) & 1) ^ 1);
-                        mbar_expect_tx(&bars->bfull[stage], (uint32_t)b_stage);
-                        tma_load_3d(b_ring + stage * b_stage, &tmap_w, &bars->bfull[stage], 0, g.w_row0 + c * 2 * p.NP, 0);
+                const int R = p.set_round[set], n_rounds = set_rounds(set);
+                for (int r = 0; r < n_rounds; ++r)
+                    for (int gi = 0; gi < p.set_count[set]; ++gi) {
+                        const int gidx = p.set_first[set] + gi;
+                        const CqGroup& g = p.g[gidx];
+                        const int c0 = bars->c_lo[gidx] + r * R, c1 = min(bars->c_hi[gidx], c0 + R);
+                        for (int c = c0; c < c1; ++c, ++bn) {
+                            const int stage = bn % CQ_BSTAGES;
+                            mbar_wait(&bars->bempty[stage], ((bn / CQ_BSTAGES) & 1) ^ 1);
+                            mbar_expect_tx(&bars->bfull[stage], (uint32_t)b_stage);
+                            tma_load_3d(b_ring + stage * b_stage, &tmap_w, &bars->bfull[stage], 0, g.w_row0 + c * 2 * p.NP, 0);
+                        }
                     }
-                }
             }
         }
     } else if (warp == 1) {
@@ -330,7 +349,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             const uint32_t idesc_np = make_idesc_f16(128, p.NP), idesc_2np = make_idesc_f16(128, 2 * p.NP);
             const uint32_t slab_addr = smem_u32(slab);
             const uint32_t hop_shift = p.hop == 64 ? 6 : 7;                  // hop is 64 or 128
-            uint32_t bn = 0, tn = 0;
+            uint32_t bn = 0, tn = 0, rc = 0;                                 // rc: rounds issued so far (buffer = rc & 1)
             for (uint32_t i = 0;; ++i) {
                 const int slot = i & 1;
                 mbar_wait(&bars->sfull[slot], (i >> 1) & 1);
@@ -340,68 +359,157 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                 if (tile < 0) break;
                 int set, b, blk;
                 cq_tile(p, tile, set, b, blk);
-                mbar_wait(&bars->acc_empty, (tn & 1) ^ 1);
-                mbar_wait(&bars->slab_full, tn & 1);
-                tc_fence_after();
-                for (int gi = 0; gi < p.set_count[set]; ++gi) {
-                    const int gidx = p.set_first[set] + gi;
-                    const CqGroup& g = p.g[gidx];
-                    const int c_lo = bars->c_lo[gidx], c_hi = bars->c_hi[gidx];
-                    const int seg_len = (c_hi - c_lo + g.n_seg - 1) / g.n_seg;
-                    const uint32_t seg_cols = (uint32_t)(g.wide ? 2 * p.NP : p.NP);
-                    int seg = 0, in_seg = 0;
-                    for (int c = c_lo; c < c_hi; ++c, ++bn) {
-                        const int stage = bn % CQ_BSTAGES;
-                        mbar_wait(&bars->bfull[stage], (bn / CQ_BSTAGES) & 1);
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (uint32_t)g.col + (uint32_t)seg * seg_cols;
-                        const uint32_t so = (uint32_t)(g.off + c * 64);        // sample offset of this tap chunk
-                        const uint32_t m = so >> hop_shift, half = (so & (p.hop - 1)) >> 6;
-                        const uint32_t a_hi = slab_addr + half * 2 * CQ_SLAB_PLANE + m * 128;
-                        const uint32_t b_hi = smem_u32(b_ring + stage * b_stage);
-                        if (elect_one()) {
-                            // K-major SWIZZLE_128B; the audio window may start on any 128-byte row of the slab (the
-                            // swizzle follows absolute address bits, so no descriptor base offset is needed)
-                            const uint64_t a_d_hi = make_smem_desc(a_hi, 16, 1024), a_d_lo = make_smem_desc(a_hi + CQ_SLAB_PLANE, 16, 1024);
-                            const uint64_t b_d_hi = make_smem_desc(b_hi, 16, 1024), b_d_lo = make_smem_desc(b_hi + p.NP * 128, 16, 1024);
-                            const uint32_t first = (uint32_t)in_seg;           // 0 on the first chunk of a segment: overwrite
-                            if (g.wide) {
+                const int R = p.set_round[set], n_rounds = set_rounds(set);
+                for (int r = 0; r < n_rounds; ++r, ++rc) {
+                    const uint32_t buf = rc & 1;
+                    mbar_wait(&bars->acc_empty[buf], ((rc >> 1) & 1) ^ 1);
+                    if (r == 0) mbar_wait(&bars->slab_full, tn & 1);
+                    tc_fence_after();
+                    for (int gi = 0; gi < p.set_count[set]; ++gi) {
+                        const int gidx = p.set_first[set] + gi;
+                        const CqGroup& g = p.g[gidx];
+                        const uint32_t d_tmem = tmem_base + buf * CQ_ACC_COLS + (uint32_t)g.col;
+                        const int c0 = bars->c_lo[gidx] + r * R, c1 = min(bars->c_hi[gidx], c0 + R);
+                        for (int c = c0; c < c1; ++c, ++bn) {
+                            const int stage = bn % CQ_BSTAGES;
+                            mbar_wait(&bars->bfull[stage], (bn / CQ_BSTAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t so = (uint32_t)(g.off + c * 64);    // sample offset of this tap chunk
+                            const uint32_t m = so >> hop_shift, half = (so & (p.hop - 1)) >> 6;
+                            const uint32_t a_hi = slab_addr + half * 2 * CQ_SLAB_PLANE + m * 128;
+                            const uint32_t b_hi = smem_u32(b_ring + stage * b_stage);
+                            if (elect_one()) {
+                                // K-major SWIZZLE_128B; the audio window may start on any 128-byte row of the slab (the
+                                // swizzle follows absolute address bits, so no descriptor base offset is needed)
+                                const uint64_t a_d_hi = make_smem_desc(a_hi, 16, 1024), a_d_lo = make_smem_desc(a_hi + CQ_SLAB_PLANE, 16, 1024);
+                                const uint64_t b_d_hi = make_smem_desc(b_hi, 16, 1024), b_d_lo = make_smem_desc(b_hi + p.NP * 128, 16, 1024);
+                                const uint32_t first = (uint32_t)(c - c0);     // 0 on the first chunk of the round: overwrite
+                                if (g.wide) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {                  // +32 B per K step = +2 in the address field
-                                    // X_hi * [W_hi | W_lo] -> both column blocks; X_lo * W_hi -> onto the second block
-                                    mma_bf16(d_tmem, a_d_hi + (uint64_t)(2 * k), b_d_hi + (uint64_t)(2 * k), idesc_2np, first | (uint32_t)k);
-                                    mma_bf16(d_tmem + (uint32_t)p.NP, a_d_lo + (uint64_t)(2 * k), b_d_hi + (uint64_t)(2 * k), idesc_np, 1u);
+                                    for (int k = 0; k < 4; ++k) {              // +32 B per K step = +2 in the address field
+                                        // X_hi * [W_hi | W_lo] -> both column blocks; X_lo * W_hi -> onto the second block
+                                        mma_bf16(d_tmem, a_d_hi + (uint64_t)(2 * k), b_d_hi + (uint64_t)(2 * k), idesc_2np, first | (uint32_t)k);
+                                        mma_bf16(d_tmem + (uint32_t)p.NP, a_d_lo + (uint64_t)(2 * k), b_d_hi + (uint64_t)(2 * k), idesc_np, 1u);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int cb = 0; cb < 3; ++cb) {           // (hi,hi) (hi,lo) (lo,hi) into one column block
+                                        const uint64_t ad = cb == 2 ? a_d_lo : a_d_hi, bd = cb == 1 ? b_d_lo : b_d_hi;
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_np, first | (uint32_t)(cb | k));
+                                    }
                                 }
-                            } else {
-#pragma unroll
-                                for (int cb = 0; cb < 3; ++cb) {               // (hi,hi) (hi,lo) (lo,hi) into one column block
-                                    const uint64_t ad = cb == 2 ? a_d_lo : a_d_hi, bd = cb == 1 ? b_d_lo : b_d_hi;
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_np, first | (uint32_t)(cb | k));
-                                }
+                                tc_commit(&bars->bempty[stage]);
                             }
-                            tc_commit(&bars->bempty[stage]);
+                            __syncwarp();
                         }
-                        __syncwarp();
-                        if (++in_seg == seg_len) { in_seg = 0; ++seg; }
                     }
+                    if (elect_one()) {
+                        if (r == n_rounds - 1) tc_commit(&bars->slab_empty);
+                        tc_commit(&bars->acc_full[buf]);
+                    }
+                    __syncwarp();
                 }
-                if (elect_one()) {
-                    tc_commit(&bars->slab_empty);
-                    tc_commit(&bars->acc_full);
-                }
-                __syncwarp();
                 ++tn;
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: (re, im) -> output format =====
+        // ===== epilogue: partial sums of every round -> registers; after the last round (re, im) -> output format =====
         const int ew = warp & 3;                                               // TMEM lane quarter
         const int eset = (warp - 4) >> 2;                                      // warp set 0 / 1: even / odd groups
-        const int r = ew * 32 + lane;
+        const int row = ew * 32 + lane;
         const float kPi = 3.14159265358979323846f;
-        uint32_t tn = 0, xb = 0;
+        uint32_t rc = 0, xb = 0;
+
+        // adds 32 accumulator columns into dst (assigns when `assign`)
+        auto pull_part = [&](uint32_t col, uint32_t (&dst)[32], bool assign) {
+            if (assign) {
+                tmem_ld32(col, dst);
+                tmem_ld_wait();
+            } else {
+                uint32_t cr[32];
+                tmem_ld32(col, cr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[j] = __float_as_uint(__uint_as_float(dst[j]) + __uint_as_float(cr[j]));
+            }
+        };
+        // adds the accumulator block(s) of group g in buffer `buf` into re / im (assigns when `fresh`)
+        auto pull = [&](const CqGroup& g, uint32_t buf, int j0, uint32_t (&re)[32], uint32_t (&im)[32], bool fresh) {
+            const uint32_t base = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * CQ_ACC_COLS + (uint32_t)(g.col + j0);
+            pull_part(base, re, fresh);                                       // main block: real | imaginary columns
+            pull_part(base + (uint32_t)(p.NP >> 1), im, fresh);
+            if (g.wide) {                                                     // the hi*lo + lo*hi correction block
+                pull_part(base + (uint32_t)p.NP, re, false);
+                pull_part(base + (uint32_t)(p.NP + (p.NP >> 1)), im, false);
+            }
+        };
+
+        // (re, im) of bins [g.bin_lo + j0, +32) at this thread's frame -> output
+        auto emit = [&](const CqGroup& g, int j0, uint32_t (&re)[32], uint32_t (&im)[32], int b, int t, float inv_item) {
+            const int nb = min(32, g.n_g - j0);
+            // undo the two power-of-two scalings (exact)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float sc = __ldg(p.inv_bin + g.bin_lo + j0 + (j < nb ? j : 0));
+                re[j] = __float_as_uint(__uint_as_float(re[j]) * inv_item * sc);
+                im[j] = __float_as_uint(__uint_as_float(im[j]) * inv_item * sc);
+            }
+            if (p.mode == CPC_CQT_COMPLEX) {
+                if (t < p.T) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nb) {
+                            float2* o = reinterpret_cast<float2*>(p.out) + ((size_t)b * p.F + g.bin_lo + j0 + j) * p.T + t;
+                            *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                        }
+                }
+            } else if (p.mode == CPC_CQT_LOGPOW) {
+                if (t < p.T) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nb) {
+                            const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
+                            float amp = (logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
+                            if (p.power != 1.f) amp = powf(amp, p.power);
+                            p.out[((size_t)b * p.F + g.bin_lo + j0 + j) * p.To + t] = amp;
+                        }
+                }
+            } else {
+                // phase difference needs frame t - 1: previous lane, or lane 31 of the previous warp
+                float ph[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ph[j] = fast_atan2(__uint_as_float(im[j]), __uint_as_float(re[j]));
+                float* ex = &bars->exch[eset][xb & 1][0][0];
+                if (lane == 31) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) ex[ew * 32 + j] = ph[j];
+                }
+                epi_bar(1 + eset);
+                ++xb;
+                const bool put = row >= 1 && t < p.T;
+                const int to = t - 1;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float prev = __shfl_up_sync(0xffffffffu, ph[j], 1);
+                    if (lane == 0 && ew > 0) prev = ex[(ew - 1) * 32 + j];
+                    if (put && j < nb) {
+                        const int f = g.bin_lo + j0 + j;
+                        const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
+                        float amp = (logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
+                        float pd = ph[j] - prev + __ldg(p.phase_fixed + f);
+                        if (pd > kPi) pd -= 2.f * kPi;
+                        if (pd < -kPi) pd += 2.f * kPi;
+                        float phv = pd * __ldg(p.phase_scale + f) * p.norm;
+                        if (p.power != 1.f) { amp = powf(amp, p.power); phv = powf(phv, p.power); }
+                        p.out[(((size_t)b * 2 + 0) * p.F + f) * p.To + to] = amp;
+                        p.out[(((size_t)b * 2 + 1) * p.F + f) * p.To + to] = phv;
+                    }
+                }
+            }
+        };
+
         for (uint32_t i = 0;; ++i) {
             const int slot = i & 1;
             mbar_wait(&bars->sfull[slot], (i >> 1) & 1);
@@ -411,106 +519,49 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             if (tile < 0) break;
             int set, b, blk;
             cq_tile(p, tile, set, b, blk);
-            const int t = blk * p.fpb + r;                                     // frame of this thread
-            mbar_wait(&bars->acc_full, tn & 1);
-            tc_fence_after();
-            const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+            const int t = blk * p.fpb + row;                                   // frame of this thread
             const float inv_item = __ldg(p.inv_item + b);
-            for (int gi = eset; gi < p.set_count[set]; gi += 2) {
-                const int gidx = p.set_first[set] + gi;
-                const CqGroup& g = p.g[gidx];
-                // segments that received taps (the MMA warp's split of the live chunk range)
-                const int n_live = bars->c_hi[gidx] - bars->c_lo[gidx];
-                const int seg_len = (n_live + g.n_seg - 1) / g.n_seg;
-                const int used = (n_live + seg_len - 1) / seg_len;
-                const int seg_cols = g.wide ? 2 * p.NP : p.NP;
-                for (int j0 = 0; j0 < g.n_g; j0 += 32) {
-                    uint32_t re[32], im[32];
-                    tmem_ld32(lane_base + (uint32_t)(g.col + j0), re);
-                    tmem_ld32(lane_base + (uint32_t)(g.col + (p.NP >> 1) + j0), im);
-                    tmem_ld_wait();
-                    // further accumulator blocks of the group: the segments' main blocks, and (wide groups) every segment's
-                    // correction block (hi*lo + lo*hi); added here in fp32 with round-to-nearest
-                    const int blocks = used * (g.wide ? 2 : 1);
-                    for (int q = 1; q < blocks; ++q) {
-                        const int seg = g.wide ? (q >> 1) : q;
-                        const int cbase = g.col + seg * seg_cols + ((g.wide && (q & 1)) ? p.NP : 0);
-                        uint32_t cr[32];
-                        tmem_ld32(lane_base + (uint32_t)(cbase + j0), cr);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) re[j] = __float_as_uint(__uint_as_float(re[j]) + __uint_as_float(cr[j]));
-                        tmem_ld32(lane_base + (uint32_t)(cbase + (p.NP >> 1) + j0), cr);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) im[j] = __float_as_uint(__uint_as_float(im[j]) + __uint_as_float(cr[j]));
-                    }
-                    const int nb = min(32, g.n_g - j0);
-                    // undo the two power-of-two scalings (exact)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sc = __ldg(p.inv_bin + g.bin_lo + j0 + (j < nb ? j : 0));
-                        re[j] = __float_as_uint(__uint_as_float(re[j]) * inv_item * sc);
-                        im[j] = __float_as_uint(__uint_as_float(im[j]) * inv_item * sc);
-                    }
-                    if (p.mode == CPC_CQT_COMPLEX) {
-                        if (t < p.T) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nb) {
-                                    float2* o = reinterpret_cast<float2*>(p.out) + ((size_t)b * p.F + g.bin_lo + j0 + j) * p.T + t;
-                                    *o = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
-                                }
-                        }
-                    } else if (p.mode == CPC_CQT_LOGPOW) {
-                        if (t < p.T) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nb) {
-                                    const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
-                                    float amp = (logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
-                                    if (p.power != 1.f) amp = powf(amp, p.power);
-                                    p.out[((size_t)b * p.F + g.bin_lo + j0 + j) * p.To + t] = amp;
-                                }
-                        }
-                    } else {
-                        // phase difference needs frame t - 1: previous lane, or lane 31 of the previous warp
-                        float ph[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) ph[j] = fast_atan2(__uint_as_float(im[j]), __uint_as_float(re[j]));
-                        float* ex = &bars->exch[eset][xb & 1][0][0];
-                        if (lane == 31) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) ex[ew * 32 + j] = ph[j];
-                        }
-                        epi_bar(1 + eset);
-                        ++xb;
-                        const bool emit = r >= 1 && t < p.T;
-                        const int to = t - 1;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float prev = __shfl_up_sync(0xffffffffu, ph[j], 1);
-                            if (lane == 0 && ew > 0) prev = ex[(ew - 1) * 32 + j];
-                            if (emit && j < nb) {
-                                const int f = g.bin_lo + j0 + j;
-                                const float x = __uint_as_float(re[j]), y = __uint_as_float(im[j]);
-                                float amp = (logf(fmaf(x, x, y * y) + p.eps) + p.log_offset) * p.norm;
-                                float pd = ph[j] - prev + __ldg(p.phase_fixed + f);
-                                if (pd > kPi) pd -= 2.f * kPi;
-                                if (pd < -kPi) pd += 2.f * kPi;
-                                float phv = pd * __ldg(p.phase_scale + f) * p.norm;
-                                if (p.power != 1.f) { amp = powf(amp, p.power); phv = powf(phv, p.power); }
-                                p.out[(((size_t)b * 2 + 0) * p.F + f) * p.To + to] = amp;
-                                p.out[(((size_t)b * 2 + 1) * p.F + f) * p.To + to] = phv;
-                            }
-                        }
+            const int R = p.set_round[set], n_rounds = set_rounds(set);
+            if (n_rounds == 1) {
+                // the whole tap range sits in one buffer: any number of groups, handled alternately by the two warp sets
+                const uint32_t buf = rc & 1;
+                mbar_wait(&bars->acc_full[buf], (rc >> 1) & 1);
+                tc_fence_after();
+                for (int gi = eset; gi < p.set_count[set]; gi += 2) {
+                    const CqGroup& g = p.g[p.set_first[set] + gi];
+                    for (int j0 = 0; j0 < g.n_g; j0 += 32) {
+                        uint32_t re[32], im[32];
+                        pull(g, buf, j0, re, im, true);
+                        emit(g, j0, re, im, b, t, inv_item);
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                ++rc;
+            } else {
+                // several rounds (host side: such sets hold at most two groups of at most 32 bins, one per warp set): the
+                // partial sums of a round are added in registers and its buffer is released at once
+                const bool mine = eset < p.set_count[set];
+                const int gidx = p.set_first[set] + (mine ? eset : 0);
+                const CqGroup& g = p.g[gidx];
+                const int c_lo = bars->c_lo[gidx], c_hi = bars->c_hi[gidx];
+                uint32_t re[32], im[32];
+                bool fresh = true;
+                for (int r = 0; r < n_rounds; ++r, ++rc) {
+                    const uint32_t buf = rc & 1;
+                    mbar_wait(&bars->acc_full[buf], (rc >> 1) & 1);
+                    tc_fence_after();
+                    if (mine && c_lo + r * R < c_hi) {
+                        pull(g, buf, 0, re, im, fresh);
+                        fresh = false;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                }
+                if (mine) emit(g, 0, re, im, b, t, inv_item);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc_empty);
-            ++tn;
         }
     }
     tc_fence_before();
@@ -586,8 +637,6 @@ static void cq_fill_groups(const cpc_cqt_params* p, const CqtUmmaPlan& u, CqtUmm
         q.n_chunks = q.K / 64;
         q.w_row0 = row0;
         q.wide = (q.K >= CQ_WIDE_MIN_K && 2 * u.NP <= CQ_ACC_COLS) ? 1 : 0;
-        q.n_seg = q.K >= CQ_SEG4_MIN_K ? 4 : (q.K >= CQ_SEG2_MIN_K ? 2 : 1);
-        while (q.n_seg > 1 && q.n_seg * (q.wide ? 2 : 1) * u.NP > CQ_ACC_COLS) q.n_seg >>= 1;
         row0 += q.n_chunks * 2 * u.NP;
     }
 }
@@ -655,7 +704,9 @@ int cqt_umma_launch(const float* x, const float* weights, const void* packed_fil
     }
     CqtUmma k{};
     cq_fill_groups(p, u, k);
-    // sets: consecutive groups whose accumulator columns fit one TMEM buffer, greedily balanced towards equal tap counts
+    // sets: consecutive groups whose accumulator columns fit one TMEM buffer, greedily balanced towards equal tap counts.
+    // Sets of one or two wide groups accumulate in rounds (one group per epilogue warp set keeps its partial sums in
+    // registers); a wide group never shares a set with more than one other group.
     {
         long total = 0;
         for (int g = 0; g < u.n_tensor_groups; ++g) total += k.g[g].K;
@@ -665,20 +716,26 @@ int cqt_umma_launch(const float* x, const float* weights, const void* packed_fil
         while (g < u.n_tensor_groups) {
             int cnt = 0, cols = 0;
             long acc = 0;
+            bool any_wide = false;
             const bool last_slot = k.n_sets == CQ_MAX_SETS - 1;
             while (g + cnt < u.n_tensor_groups) {
                 const CqGroup& q = k.g[g + cnt];
-                const int need = q.n_seg * (q.wide ? 2 * u.NP : u.NP);
+                const int need = q.wide ? 2 * u.NP : u.NP;
                 if (cols + need > CQ_ACC_COLS) break;
                 if (cnt > 0 && !last_slot && acc + q.K > target) break;
+                if ((any_wide || q.wide) && cnt >= 2) break;               // rounds: at most two groups
+                if (any_wide && !q.wide) break;                            // keep round sets homogeneous
                 k.g[g + cnt].col = cols;
                 cols += need;
                 acc += q.K;
+                any_wide = any_wide || q.wide;
                 ++cnt;
             }
             if (cnt == 0 || (last_slot && g + cnt < u.n_tensor_groups)) return CPC_ERR_UNSUPPORTED;
             k.set_first[k.n_sets] = g;
             k.set_count[k.n_sets] = cnt;
+            const int round_override = (p->flags >> 8) & 0xff;              // experiments: flags bits 8..15 = chunks per round
+            k.set_round[k.n_sets] = any_wide ? (round_override ? round_override : CQ_ROUND_CHUNKS) : (1 << 20);
             ++k.n_sets;
             g += cnt;
         }

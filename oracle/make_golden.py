@@ -335,6 +335,18 @@ def golden_scalogram_encoder(ref):
                     tag + ".rf": np.array(enc.receptive_field), tag + ".ds": np.array(enc.downsampling_factor)})
         out.update({tag + ".p." + k: v for k, v in sd_np(enc).items() if not k.startswith("cqt.")})
         out.update({tag + ".g." + n: p.grad.numpy() for n, p in enc.named_parameters() if p.grad is not None})
+        # conditioning probe: the reference's own gradients when its CQT output moves by 1e-6 relative (the error level of
+        # any independent fp32 evaluation of a 16 384-tap filter).  log / atan2 of near-silent cells and the ReLU gates behind
+        # them amplify it; tests hold each gradient to max(1e-3, 3 x this self-noise)
+        base = {n: p.grad.detach().clone() for n, p in enc.named_parameters() if p.grad is not None}
+        noise_gen = torch.Generator().manual_seed(3)
+        hook = enc.cqt.register_forward_hook(lambda m, i, o: o * (1 + 1e-6 * torch.randn(o.shape, generator=noise_gen)))
+        enc.zero_grad()
+        (enc(x) * gy).sum().backward()
+        hook.remove()
+        for n, p in enc.named_parameters():
+            if p.grad is not None:
+                out[tag + ".sn." + n] = np.array(float((p.grad - base[n]).norm() / base[n].norm().clamp_min(1e-30)))
     np.savez_compressed(os.path.join(OUT, "scalogram_encoder.npz"), **out)
 
 

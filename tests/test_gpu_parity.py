@@ -469,7 +469,8 @@ def test_scalogram_encoder_matches_reference_golden(cpc, monkeypatch, tag, phase
     for n, p in enc.named_parameters():
         if n.startswith("cqt.") or n.startswith("phase_diff."):
             continue
-        assert grad_err(p.grad, g["g." + n]) < tol, n
+        # max(tol, 3 x the reference's own gradient noise under a 1e-6 relative change of its CQT output, make_golden.py)
+        assert grad_err(p.grad, g["g." + n]) < max(tol, 3.0 * float(g["sn." + n])), (n, float(g["sn." + n]))
     for k in own:
         if k.endswith("running_mean") or k.endswith("running_var"):
             assert rel_err(enc.state_dict()[k], g["p." + k]) < tol, k
@@ -929,9 +930,12 @@ def test_cuda_graph_step_reproduces_eager_steps(cpc, fused_adam):
     # conv biases in front of a batch norm have zero true gradient: Adam turns their rounding noise (atomics order)
     # into lr-sized steps, so they are not comparable between two runs of ANY implementation
     noise_only = bn_shadowed_biases(model.state_dict().keys())
+    # ... and an entry whose gradient passes through zero during these steps takes Adam updates that differ by a few
+    # percent of lr between two runs: parameters are compared with that absolute slack (2 % of three lr-sized steps)
     for (n, p), (_, q) in zip(model.named_parameters(), model2.named_parameters()):
         if n not in noise_only:
-            assert rel_err(q, p) < 1e-4, n
+            slack = 1e-4 * float(p.detach().abs().max()) + 0.02 * 3 * 1e-3
+            assert float((q.detach() - p.detach()).abs().max()) < slack, (n, float((q.detach() - p.detach()).abs().max()), slack)
 
 
 @pytest.mark.parametrize("name", ["e24", "e25", "e20"])

@@ -62,7 +62,8 @@ def second_order_enabled():
 # variables of the same names, read at call time.
 kernel_switches = {}
 _CONV_SWITCHES = (("CPC_FORCE_CUDA_CORE_CONV", _lib.CONV_FLAG_CUDA_CORE), ("CPC_NO_TALL_CONV", _lib.CONV_FLAG_NO_TALL),
-                  ("CPC_NO_SMALLK_CONV", _lib.CONV_FLAG_NO_SMALLK), ("CPC_NO_FUSED_DGRAD", _lib.CONV_FLAG_NO_FUSED_DGRAD))
+                  ("CPC_NO_SMALLK_CONV", _lib.CONV_FLAG_NO_SMALLK), ("CPC_NO_FUSED_DGRAD", _lib.CONV_FLAG_NO_FUSED_DGRAD),
+                  ("CPC_NO_MMA_SMALL_WGRAD", _lib.CONV_FLAG_NO_MMA_SMALL_WGRAD))
 
 
 def _switch(name):
@@ -172,6 +173,17 @@ def _workspace(nbytes, device):
 # convolution
 # --------------------------------------------------------------------------------------------------
 
+_OVERLAP_MAX_FLOPS = 60e9                                     # ~0.15 ms at the generic kernel's rate
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, relu, precision):
     p = _lib.ConvParams()
     p.batch, p.c_in, p.h_in, p.w_in = x_shape
@@ -253,20 +265,31 @@ class _ConvFunction(torch.autograd.Function):
                           _stream(), nbytes=4.0 * dy.numel() + float(nbytes))
                 else:
                     packed_dy = _pack_operand(lib, dy, p, 1)
+            # data and weight gradient are independent: when both are small (neither fills the 148 SMs for long) the weight
+            # gradient runs on a side stream next to the data gradient (fork / join inside this call, so every buffer
+            # the side stream touches outlives the join; under graph capture the fork becomes a parallel branch)
+            side = None
+            if need_dx and need_dw and _profiler is None and _conv_flops(p) < _OVERLAP_MAX_FLOPS and not _switch("CPC_NO_BWD_OVERLAP"):
+                side = _side_stream(dy.device)
+                side.wait_stream(torch.cuda.current_stream(dy.device))
+            ws_d = ws_w = None
             if need_dx:
                 dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
-                ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
+                ws_d = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
                 _call(_conv_key("cpc_conv_dgrad", p), _conv_flops(p), lib.cpc_conv_dgrad_ex, _ptr(dy), _ptr(w), _ptr(dx),
-                      ctypes.byref(p), _ptr(packed_dy), _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+                      ctypes.byref(p), _ptr(packed_dy), _ptr(ws_d), ws_d.numel() if ws_d is not None else 0, _stream())
             if need_dw:
                 dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
                 db_here = None                                   # bias gradient still to be computed by the wgrad call
                 if ctx.has_bias and db is None:
                     db = db_here = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device)
-                ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
-                _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad_ex, _ptr(x), _ptr(dy), _ptr(dw),
-                      _ptr(db_here), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws),
-                      ws.numel() if ws is not None else 0, _stream())
+                ws_w = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                    _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad_ex, _ptr(x), _ptr(dy), _ptr(dw),
+                          _ptr(db_here), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws_w),
+                          ws_w.numel() if ws_w is not None else 0, _stream())
+            if side is not None:
+                torch.cuda.current_stream(dy.device).wait_stream(side)
         return dx, dw, db, None, None, None, None, None, None
 
 

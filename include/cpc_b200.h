@@ -128,6 +128,7 @@ typedef struct cpc_conv_params {
 #define CPC_CONV_FLAG_NO_TALL 2          /* kh x 1 convolutions on the generic tcgen05 kernel                 */
 #define CPC_CONV_FLAG_NO_SMALLK 4        /* tiny-K convolutions on the tiled kernels                          */
 #define CPC_CONV_FLAG_NO_FUSED_DGRAD 8   /* stride-2 data gradient as one launch per parity class             */
+#define CPC_CONV_FLAG_NO_MMA_SMALL_WGRAD 16 /* tiny-K weight gradient on the FMA kernel instead of mma.sync      */
 
 size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which /* 0 fwd, 1 dgrad, 2 wgrad */);
 /* y = conv(x, w) + bias (bias may be NULL). */

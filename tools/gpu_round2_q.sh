@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/r2q_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2q_tests.log
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r2q_bench.json 2> gpurun_out/r2q_bench.err
+tail -3 gpurun_out/r2q_tests.log; grep -a "FAILED\|^E  " gpurun_out/r2q_tests.log | head
+python -c "
+import json
+d=json.load(open('gpurun_out/r2q_bench.json')); print(d['ms_per_step'], d['value'], d['e2e']['ms_per_step'])
+for k in d['kernels']:
+    if 'small_k' in k['key']: print(k['key'], round(k['avg_ms'],3))"

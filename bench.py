@@ -113,7 +113,7 @@ class ClockSampler:
 # CPU arm: the oracle port of the same training step on the host cores
 # --------------------------------------------------------------------------------------------------------------------
 
-def cpu_reference_arm(workload, steps, warmup, batch=None):
+def cpu_reference_arm(workload, steps, warmup, batch=None, components_too=False):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import cpc_oracle_model as M
@@ -137,10 +137,44 @@ def cpu_reference_arm(workload, steps, warmup, batch=None):
     M.train_steps(model, [x] * steps, **kw)
     dt = (time.perf_counter() - t0) / steps
     audio_s = batch * model.item_length / SR
-    return {"value": audio_s / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+    components = cpu_components(workload, batch, model.item_length) if components_too else None
+    return {"value": audio_s / dt, "unit": "audio-s/s", "cores": cores, "kind": "port", "components": components,
             "sample": "%d steps of the same %s training step at batch %d (%.1f audio-s per step), torch CPU fp32, "
                       "%d threads, anomaly mode off" % (steps, workload, batch, audio_s, cores),
             "ms_per_step": dt * 1e3, "item_length": int(model.item_length)}
+
+
+def cpu_components(workload, batch, item_length):
+    """the two stand-alone stages on the host cores -- PreprocessingModule.forward (CQT +
+    log-power + phase) at the CPU batch, and the InfoNCE score + loss block forward + backward at the GPU's native size
+    (B = 64), the largest the CPU path materialises comfortably ((B K)^2 scores)."""
+    import torch
+    import cpc_oracle as O
+    w = WORKLOADS[workload]
+    out = {}
+    if workload != "raw_wave":
+        plan = O.CqtPlan(16000, 30, 256, 32, 0.5, 128)
+        x = 0.1 * torch.randn(batch, 1, item_length, generator=torch.Generator().manual_seed(1))
+        O.preprocess(x, plan, phase=True)
+        t0 = time.perf_counter()
+        O.preprocess(x, plan, phase=True)
+        dt = time.perf_counter() - t0
+        out["cqt_scalogram_ms"] = dt * 1e3
+        out["cqt_audio_s_per_s"] = batch * item_length / SR / dt
+    k, e, b = w["prediction"], 512, 64
+    all_steps, kind, reg = (False, "softplus", 1.0) if workload == "raw_wave" else (True, "linear", 0.0)
+    g = torch.Generator().manual_seed(2)
+    pred = (torch.randn(b, k, e, generator=g) / e ** 0.5).requires_grad_(True)
+    tgt = torch.randn(b, e, k, generator=g).requires_grad_(True)
+    for i in range(2):
+        t0 = time.perf_counter()
+        loss, _ = O.infonce_loss(pred, tgt, all_steps, kind, reg)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        pred.grad = tgt.grad = None
+    out["infonce_fwd_bwd_ms"] = dt * 1e3
+    out["infonce_shape"] = "B=%d K=%d E=%d %s %s" % (b, k, e, "all-steps" if all_steps else "per-step", kind)
+    return out
 
 
 def workload_config(workload, n_gpus, batch, item_length):
@@ -444,7 +478,7 @@ def run_ours(args):
         "conv_tensor_frac_by_family": {f["family"]: f["tflops"] / peaks["tensor"] for f in fam_list
                                        if f["flops"] > 0 and "conv" in f["family"]},
     }
-    cpu = cpu_reference_arm(args.workload, 2, 1) if world == 1 else None
+    cpu = cpu_reference_arm(args.workload, 2, 1, components_too=True) if world == 1 else None
     line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
@@ -455,7 +489,7 @@ def run_ours(args):
                     "result_read": "every step's (loss, max score) copied to pinned host memory and read by the host "
                                    "inside the timed region, one step late (asynchronous logging)"},
             "roofline": roofline, "metrics": metrics,
-            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "components")} if cpu else None),
             "kernel_families": [{k: f[k] for k in ("family", "share", "ms", "launches", "tflops", "gbs")} for f in fam_list],
             "kernels": top[:40]}
     if world > 1:

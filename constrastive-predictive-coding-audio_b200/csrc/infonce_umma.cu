@@ -33,6 +33,8 @@ constexpr int NU_BSTAGES = 2;                     // backward ring
 struct NuGeom {
     int B, K, E, all, kind;
     int Bp, nprob, nT, EC;                        // rows per problem, problems, 128-row tiles, 64-wide E chunks
+    int passes;                                   // MMA passes per product: 3 = fp32-faithful (hi*hi + hi*lo + lo*hi),
+                                                  // 1 = bf16 operand mode (precision = 1: the hi planes only)
     float lambda;
 };
 
@@ -44,6 +46,7 @@ static NuGeom nu_geom(const cpc_infonce_params* p) {
     g.nT = ceil_div(g.Bp, 128);
     g.EC = g.E / 64;
     g.lambda = p->regularization;
+    g.passes = p->precision == 0 ? 3 : 1;
     return g;
 }
 
@@ -73,8 +76,17 @@ __global__ void __launch_bounds__(256) nu_pack_kernel(NuSrc src, __nv_bfloat16* 
     }
 }
 
-__device__ __forceinline__ float nu_softplus(float u) { return u > 20.f ? u : log1pf(expf(u)); }
-__device__ __forceinline__ float nu_sigmoid(float u) { return 1.f / (1.f + expf(-u)); }
+// softplus(u) = max(u, 0) + log1p(e), sigmoid(u) = (u >= 0 ? 1 : e) / (1 + e) with e = exp(-|u|) in (0, 1]: one ex2, one lg2
+// and one reciprocal on the special-function unit per score (the epilogues are bound by it: the libm versions,
+// log1pf(expf(u)) and 1 / (1 + expf(-u)), made the softplus sweep 2.3x slower than the linear one).  Relative error
+// ~1e-6; log1p switches to its series below 1e-3, where 1 + e would round the information away.
+__device__ __forceinline__ float nu_log1p_small(float e) { return e < 1e-3f ? e * fmaf(e, fmaf(e, 0.33333333f, -0.5f), 1.f) : __logf(1.f + e); }
+__device__ __forceinline__ float nu_softplus(float u) { return fmaxf(u, 0.f) + nu_log1p_small(__expf(-fabsf(u))); }
+__device__ __forceinline__ void nu_softplus_sigmoid(float u, float& sp, float& sg) {
+    const float e = __expf(-fabsf(u));
+    sp = fmaxf(u, 0.f) + nu_log1p_small(e);
+    sg = __fdividef(u >= 0.f ? 1.f : e, 1.f + e);
+}
 
 // ---- forward ------------------------------------------------------------------------------------------------
 struct __align__(8) NuFwdBarriers {
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_fwd_kernel(const __gri
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smem + stage * 2 * NU_TILE), b0 = a0 + NU_TILE;
 #pragma unroll
-                    for (int cb = 0; cb < 3; ++cb) {                         // (hi,hi) (hi,lo) (lo,hi)
+                    for (int cb = 0; cb < g.passes; ++cb) {                         // (hi,hi) (hi,lo) (lo,hi)
                         const uint32_t a_addr = a0 + (cb == 2 ? 128 * 128 : 0);
                         const uint32_t b_addr = b0 + (cb == 1 ? 128 * 128 : 0);
 #pragma unroll
@@ -354,7 +366,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(ring + stage * 2 * NU_TILE), b0 = a0 + NU_TILE;
 #pragma unroll
-                    for (int cb = 0; cb < 3; ++cb) {
+                    for (int cb = 0; cb < g.passes; ++cb) {
                         const uint32_t a_addr = a0 + (cb == 2 ? 128 * 128 : 0);
                         const uint32_t b_addr = b0 + (cb == 1 ? 128 * 128 : 0);
 #pragma unroll
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                     const uint32_t b0 = smem_u32(ring + stage * 2 * NU_TILE + NU_TILE);
                     const uint32_t d_tmem = tmem_base + 256 + (uint32_t)a * 64;
 #pragma unroll
-                    for (int cb = 0; cb < 3; ++cb) {                         // (G hi, X hi) (G hi, X lo) (G lo, X hi)
+                    for (int cb = 0; cb < g.passes; ++cb) {                         // (G hi, X hi) (G hi, X lo) (G lo, X hi)
                         const uint32_t ga = gs_addr + (cb == 2 ? NU_TILE : 0);           // lo plane of G
                         const uint32_t ba = b0 + (cb == 1 ? 128 * 128 : 0);
 #pragma unroll
@@ -419,12 +431,52 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                 tmem_ld32(lane_base + (uint32_t)((st & 1) * 128 + n0), raw);
                 tmem_ld_wait();
                 float gv[32];
+                float sg[32];                                                 // d softplus / du (softplus scores only)
+                if (g.lambda == 0.f) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float u = __uint_as_float(raw[j]);
-                    const float sc = KIND == CPC_SCORE_SOFTPLUS ? nu_softplus(u) : u;
-                    const float l = p.owner_is_target ? lse_own : lrow[n0 + j];
-                    gv[j] = w_ce * __expf(sc - l);
+                    for (int j = 0; j < 32; ++j) {
+                        const float u = __uint_as_float(raw[j]);
+                        float sc = u;
+                        if (KIND == CPC_SCORE_SOFTPLUS) nu_softplus_sigmoid(u, sc, sg[j]);
+                        const float l = p.owner_is_target ? lse_own : lrow[n0 + j];
+                        gv[j] = w_ce * __expf(sc - l);
+                    }
+                } else {
+                    // all-steps regulariser lambda * mean_{d,t,k'} ((1/K) sum_k S[d,k,t,k'])^2 (:141):
+                    // dL/dS[d,k,t,k'] += 2 lambda / (B^2 K^3) * sum_k S[d,k,t,k'].  Prediction rows are ordered (d, k), so the
+                    // K-sum runs over K consecutive columns (owner = targets: inside this thread's registers) or over K
+                    // consecutive lanes (owner = predictions: warp shuffles); K is a power of two <= 32 (host side).
+                    const float w_reg = __ldg(p.grad_loss) * 2.f * g.lambda / ((float)g.B * (float)g.B * (float)g.K * (float)g.K * (float)g.K);
+                    float sc[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float u = __uint_as_float(raw[j]);
+                        sc[j] = u;
+                        if (KIND == CPC_SCORE_SOFTPLUS) nu_softplus_sigmoid(u, sc[j], sg[j]);
+                        const float l = p.owner_is_target ? lse_own : lrow[n0 + j];
+                        gv[j] = w_ce * __expf(sc[j] - l);
+                    }
+                    if (p.owner_is_target) {
+#pragma unroll
+                        for (int lg = 0; lg < 5; ++lg) {                      // butterfly over the K-aligned column group
+                            constexpr int kOne = 1;
+                            const int o = kOne << lg;                         // compile-time after unrolling: register indexing
+                            if (o < g.K) {
+                                float nx[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) nx[j] = sc[j] + sc[j ^ o];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) sc[j] = nx[j];
+                            }
+                        }
+                    } else {
+                        for (int o = 1; o < g.K; o <<= 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) gv[j] = fmaf(w_reg, sc[j], gv[j]);
                 }
                 if (st == ot && n0 == (rl & 96)) {                           // - w on the diagonal element
 #pragma unroll
@@ -432,7 +484,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                 }
                 if (KIND == CPC_SCORE_SOFTPLUS) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) gv[j] *= nu_sigmoid(__uint_as_float(raw[j]));
+                    for (int j = 0; j < 32; ++j) gv[j] *= sg[j];
                 }
                 if (!own_ok || n0 + 32 > n_valid) {                          // rows outside the problem contribute nothing
 #pragma unroll
@@ -493,15 +545,15 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
 // ---- host side ----------------------------------------------------------------------------------------------
 // which: 0 forward, 1 backward
 bool nce_umma_eligible(const cpc_infonce_params* p, int which) {
-    if (p->precision != 0 || p->enc % 64 != 0 || p->enc < 64 || p->enc > 4096) return false;
+    if (p->enc % 64 != 0 || p->enc < 64 || p->enc > 4096) return false;
     const long bp = p->all_steps ? (long)p->batch * p->steps : p->batch;
     if (bp < 128 || bp > (1 << 24)) return false;                          // tiny problems are latency-bound either way
     // one CTA per 128 owner rows: a single all-steps problem needs >= 8 row tiles to beat
     // the CUDA-core kernel does (measured cross-over, tools/infonce_sweep.py); per-step mode has K problems
     if (p->all_steps && bp < 1024) return false;
     if (p->regularization != 0.f) {
-        if (which == 1) return false;                                       // regulariser gradient: CUDA-core kernel
-        if (!p->all_steps || 128 % p->steps != 0) return false;            // forward needs whole K-groups inside a tile
+        if (!p->all_steps || 128 % p->steps != 0) return false;            // whole K-groups inside a tile (K a power of two)
+        if (which == 1 && p->steps > 32) return false;                     // backward sums K consecutive lanes with shuffles
     }
     return true;
 }

@@ -658,6 +658,31 @@ def test_infonce_tensor_core_path_matches_oracle_and_cuda_core_path(cpc, b, k, e
             assert rel_err(dz[:, :, -k:], 2.0 * want_dz) < TOL, (flag, kind)
         assert abs(res["0"][2] - res["1"][2]) < 1e-4 * max(1.0, abs(res["1"][2]))
         assert rel_err(res["0"][3], res["1"][3]) < 1e-4 and rel_err(res["0"][4], res["1"][4]) < 1e-4
+        # the regulariser (reference default 0.01; exaggerated here) and its gradient on the tensor path: all-steps mode with
+        # whole K-groups inside a 128-row tile
+        if all_steps and 128 % k == 0:
+            want = O.infonce_with_grads(pred, z[:, :, -k:], all_steps, kind, 0.7)
+            got = {}
+            for flag in ("0", "1"):
+                os.environ["CPC_NO_TENSOR_INFONCE"] = flag
+                try:
+                    pg = pred.clone().to(DEV).requires_grad_(True)
+                    zg = z.clone().to(DEV).requires_grad_(True)
+                    loss, _, _, _ = cpc.ops.infonce(pg, zg[:, :, -k:], all_steps, kind, 0.7)
+                    (2.0 * loss).backward()
+                    got[flag] = (loss.item(), pg.grad.clone(), zg.grad[:, :, -k:].clone())
+                finally:
+                    os.environ["CPC_NO_TENSOR_INFONCE"] = "0"
+                assert abs(got[flag][0] - float(want[0])) < TOL * max(1.0, abs(float(want[0]))), (flag, kind)
+                assert rel_err(got[flag][1], 2.0 * want[2]) < TOL and rel_err(got[flag][2], 2.0 * want[3]) < TOL, (flag, kind)
+            assert rel_err(got["0"][1], got["1"][1]) < 1e-4 and rel_err(got["0"][2], got["1"][2]) < 1e-4
+        # bf16 operand mode on the tensor path (one MMA per product instead of three): stated bound 1e-2
+        pg = pred.clone().to(DEV).requires_grad_(True)
+        zg = z.clone().to(DEV).requires_grad_(True)
+        loss, mx, _, _ = cpc.ops.infonce(pg, zg[:, :, -k:], all_steps, kind, 0.0, precision="bf16")
+        (2.0 * loss).backward()
+        assert abs(loss.item() - float(want_loss)) < 1e-2 * max(1.0, abs(float(want_loss))), kind
+        assert rel_err(pg.grad, 2.0 * want_dp) < 1e-2 and rel_err(zg.grad[:, :, -k:], 2.0 * want_dz) < 1e-2, kind
 
 
 def test_infonce_full_size_property(cpc):

@@ -14,6 +14,7 @@ Workloads (``--workload``; the default is the one BASELINE.json's metric is quot
                kernels (fp32 accumulate, fp32 batch norm / loss), batch 64 per GPU.
   long_context BASELINE configs[4]: the e24 model with visible_steps=112 (items of 150 272 samples = 9.39 s, 1046 CQT
                frames), batch 64 per GPU.
+  e29          the reference's default experiment (high-res CQT, arch 9, attention AR, gradient penalty), batch 16, eager.
   infonce_sweep BASELINE configs[3]: the fused InfoNCE forward + backward alone over candidates 128...8192 x K 4...32.
 
 One "step" = one full training step (CQT -> encoder -> AR -> InfoNCE forward/backward -> Adam) on synthetic white-noise
@@ -50,6 +51,10 @@ WORKLOADS = {
                  "text": "e20_bf16: CQT(256 bins, phase) + ScalogramResidualEncoder arch7 + AttentionModel "
                          "(attention_architecture_1) + InfoNCE linear/all-steps K=16, conv kernels in bf16-operand mode, "
                          "full train step incl. Adam (BASELINE configs[2])"},
+    "e29": {"batch": 16, "cpu_batch": None, "visible": 43, "prediction": 16, "dtype": "f32", "sr": 44100, "graph": False,
+            "text": "e29 (the reference's default experiment, train_script.py:11): high-res CQT (44.1 kHz, 292 bins, hop 256) + "
+                    "offset/pooled scalogram + resnet arch 9 + AttentionModel + InfoNCE linear/all-steps K=16 with the "
+                    "Wasserstein gradient penalty (second-order autograd), batch 16 as configured, eager submission"},
     "long_context": {"batch": 64, "cpu_batch": 4, "visible": 112, "prediction": 16, "dtype": "f32",
                      "text": "long_context: the e24 model with visible_steps=112: items of 150 272 samples (9.39 s, 1046 "
                              "CQT frames x 256 bins), full train step incl. Adam (BASELINE configs[4])"},
@@ -180,8 +185,10 @@ def cpu_components(workload, batch, item_length):
 def workload_config(workload, n_gpus, batch, item_length):
     w = WORKLOADS[workload]
     return {"workload": w["text"], "batch_per_gpu": batch, "global_batch": batch * n_gpus,
-            "samples_per_item": item_length, "sample_rate": SR, "parallelism": "dp%d" % n_gpus, "negatives": "per-GPU",
-            "submission": "whole step captured in CUDA graphs (cpc_b200.GraphedTrainStep)",
+            "samples_per_item": item_length, "sample_rate": w.get("sr", SR), "parallelism": "dp%d" % n_gpus,
+            "negatives": "per-GPU",
+            "submission": ("whole step captured in CUDA graphs (cpc_b200.GraphedTrainStep)" if w.get("graph", True)
+                           else "kernels submitted eagerly"),
             "l2": "activations (>300 MB per layer at batch 64) exceed the 126 MB L2; no explicit flush",
             "first_layer_dgrad": "skipped: the reference marks the scalogram requires_grad (contrastive_estimation_training"
                                  ".py:102) but only the gradient penalty reads that gradient; the CPU arm computes it",
@@ -227,14 +234,20 @@ def build_workload(name, dev):
         kw = dict(regularization=1.0, score_over_all_timesteps=False, score_function=cpc_b200.softplus_score_function,
                   preprocessing=None, prediction_steps=w["prediction"])
         return model, None, kw, 1e-4
-    exp = configs.experiment("e20" if name == "e20_bf16" else "e24")
+    if name == "e29":
+        with open(os.path.join(ROOT, "tests", "golden", "configs.json")) as fh:      # the reference's dicts as imported
+            exp = configs.experiment_from_plain(json.load(fh)["e29"])
+    else:
+        exp = configs.experiment("e20" if name == "e20_bf16" else "e24")
     tc = dict(exp["training_config"], visible_steps=w["visible"], prediction_steps=w["prediction"])
     if name == "e20_bf16":
         ops.set_default_precision("bf16")
         exp["ar_model_config"]["sequence_length"] = max(exp["ar_model_config"]["sequence_length"], w["visible"])
     model, pre, _ = configs.setup_model(exp["cqt_config"], exp["encoder_config"], exp["ar_model_config"], tc, device=dev)
     kw = dict(regularization=tc["regularization"], score_over_all_timesteps=tc["score_over_all_timesteps"],
-              score_function=tc["score_function"], preprocessing=pre, prediction_steps=tc["prediction_steps"])
+              score_function=tc["score_function"], preprocessing=pre, prediction_steps=tc["prediction_steps"],
+              wasserstein_gradient_penalty=tc["wasserstein_gradient_penalty"],
+              gradient_penalty_factor=tc["gradient_penalty_factor"])
     return model, pre, kw, tc["learning_rate"]
 
 
@@ -281,7 +294,7 @@ def run_ours(args):
     b = int(args.batch or w["batch"])
     trainer = cpc_b200.ContrastiveEstimationTrainer(model=model, dataset=None, device=dev, verbose=False, **tkw)
     optimizer = trainer.make_optimizer(lr)                      # torch.optim.Adam -> cpc_b200.optim.Adam (one kernel per step)
-    use_graph = not args.no_graph
+    use_graph = not args.no_graph and w.get("graph", True)
     model.train()
 
     g = torch.Generator().manual_seed(1234 + rank)
@@ -404,7 +417,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     top = prof.summary()
 
-    audio_s_step = world * b * length / SR
+    sr = w.get("sr", SR)
+    audio_s_step = world * b * length / sr
     value = audio_s_step / (ms_dev * 1e-3)
     e2e_value = audio_s_step / (ms_e2e * 1e-3)
     if world > 1:

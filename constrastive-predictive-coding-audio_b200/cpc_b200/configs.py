@@ -102,6 +102,31 @@ def experiment(name):
     raise KeyError(name)
 
 
+def experiment_from_plain(plain):
+    """An experiment dict whose classes / functions are given by NAME (tests/golden/configs.json: the reference's
+    experiment dicts as imported, dumped by oracle/make_golden.py) -> the same dict with cpc_b200 objects."""
+    from . import encoders, ar_models, trainer
+    names = {"ScalogramResidualEncoder": encoders.ScalogramResidualEncoder, "ScalogramEncoder": encoders.ScalogramEncoder,
+             "AudioEncoder": encoders.AudioEncoder, "ConvolutionalArModel": ar_models.ConvolutionalArModel,
+             "AttentionModel": ar_models.AttentionModel, "AudioGRUModel": ar_models.AudioGRUModel,
+             "Adam": torch.optim.Adam, "SGD": torch.optim.SGD,
+             "linear_score_function": trainer.linear_score_function,
+             "softplus_score_function": trainer.softplus_score_function,
+             "difference_score_function": trainer.difference_score_function}
+
+    def convert(key, value):
+        if isinstance(value, dict):
+            return {k: convert(k, v) for k, v in value.items()}
+        if isinstance(value, list):
+            value = [convert(key, v) for v in value]
+            return tuple(value) if key.startswith("kernel_size") else value
+        if key in ("model", "optimizer", "score_function") and isinstance(value, str):
+            return names[value]
+        return value
+
+    return {k: convert(k, v) for k, v in plain.items()}
+
+
 def setup_model(cqt_params=None, encoder_params=None, ar_params=None, trainer_args=None, device=None,
                 visible_steps=60, prediction_steps=16, trace_model=False, use_all_GPUs=True,
                 activation_register=None):

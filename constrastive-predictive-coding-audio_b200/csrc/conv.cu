@@ -40,6 +40,8 @@ int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv
 bool smallk_eligible(const cpc_conv_params* p, int which);
 int smallk_launch(int which, const float* x, const float* w, const float* bias, const float* dy, float* out,
                   const cpc_conv_params* p, cudaStream_t s);
+bool small_dgrad_eligible(const cpc_conv_params* p);
+int small_dgrad_launch(const float* dy, const float* w, float* dx, const cpc_conv_params* p, cudaStream_t s);
 static bool smallk_path(const cpc_conv_params* p, int which) {
     if (p->flags & CPC_CONV_FLAG_NO_SMALLK) return false;       // A/B switch: keep tiny-K convs on the tiled kernels
     return smallk_eligible(p, which);
@@ -291,6 +293,7 @@ extern "C" size_t cpc_conv_workspace_bytes(const cpc_conv_params* p, int which) 
 // Which kernel family serves (p, which): 0 tiled CUDA-core, 1 direct small-K, 2 tall 32ch, 3 tall 128, 4 generic tcgen05
 static int conv_family(const cpc_conv_params* p, int which) {
     if ((which == 0 || which == 2) && smallk_path(p, which)) return 1;
+    if (which == 1 && !(p->flags & CPC_CONV_FLAG_NO_SMALLK) && small_dgrad_eligible(p)) return 1;
     if (const int tp = tall_path(p, which)) return tp == 1 ? 2 : 3;
     return tensor_core_path(p, which) ? 4 : 0;
 }
@@ -416,6 +419,7 @@ extern "C" int cpc_conv_dgrad_ex(const float* dy, const float* w, float* dx, con
     if ((st = check_device()) != CPC_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     switch (conv_family(p, 1)) {
+        case 1: return small_dgrad_launch(dy, w, dx, p, s);
         case 2: return tall_conv_launch(dy, w, nullptr, dx, p, 1, packed_dy, workspace, workspace_bytes, s);
         case 3: return tall128_conv_launch(dy, w, nullptr, dx, p, 1, packed_dy, workspace, workspace_bytes, s);
         case 4: return umma_conv_launch(dy, w, nullptr, dx, p, 1, packed_dy, workspace, workspace_bytes, s);

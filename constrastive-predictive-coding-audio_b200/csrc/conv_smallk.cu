@@ -297,6 +297,72 @@ static void small_wgrad_mma_launch(const float* x, const float* dy, float* dw, c
     small_wgrad_mma_kernel<NT><<<dim3(blocks, ceil_div(g.Cout, 32)), 256, 0, s>>>(x, dy, dw, g, (int)units, segs);
 }
 
+// ---- data gradient towards a tiny number of input channels ---------------------------------------------------------
+// dx[b, ci, h, w] = sum_{co, i, j} dy[b, co, (h + pt - i) / sh, (w + pl - j) / sw] * w[co, ci, i, j]   (taps that divide).
+// As a GEMM its N is C_in (1 or 2): the tiled kernels run it at 1/64 of their rate (28 ms for the first e29 layer, whose
+// data gradient the gradient penalty needs).  Here: one thread per input pixel and all C_in channels, the whole weight
+// tensor in shared memory (broadcast reads), dy read through L1 (a block owns a 32 x 8 patch, so the rows it re-reads per
+// vertical tap stay resident).
+constexpr int SD_MAX_CIN = 4;
+constexpr int SD_MAX_W = 12288;                                   // floats of shared memory for the weights (48 KB)
+template <int CI>
+__global__ void __launch_bounds__(256) small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                         float* __restrict__ dx, SmallGeom g) {
+    extern __shared__ float ws[];                                 // [co][ci][i][j] as in global memory
+    const int n_w = g.Cout * g.Cin * g.kh * g.kw;
+    for (int idx = threadIdx.y * 32 + threadIdx.x; idx < n_w; idx += 256) ws[idx] = __ldg(w + idx);
+    __syncthreads();
+    const int b = blockIdx.z;
+    const int ww = blockIdx.x * 32 + threadIdx.x, h = blockIdx.y * 8 + threadIdx.y;
+    if (ww >= g.W || h >= g.H) return;
+    float acc[CI];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) acc[c] = 0.f;
+    const float* dyb = dy + (size_t)b * g.Cout * g.ohow;
+    const int khkw = g.kh * g.kw;
+    for (int i = 0; i < g.kh; ++i) {
+        const int th = h + g.pt - i;
+        if (th < 0 || th % g.sh) continue;
+        const int oh = th / g.sh;
+        if (oh >= g.OH) continue;
+        for (int j = 0; j < g.kw; ++j) {
+            const int tw = ww + g.pl - j;
+            if (tw < 0 || tw % g.sw) continue;
+            const int ow = tw / g.sw;
+            if (ow >= g.OW) continue;
+            const float* pd = dyb + (size_t)oh * g.OW + ow;
+            const float* pw = ws + i * g.kw + j;
+#pragma unroll 4
+            for (int co = 0; co < g.Cout; ++co) {
+                const float d = __ldg(pd + (size_t)co * g.ohow);
+#pragma unroll
+                for (int c = 0; c < CI; ++c)
+                    if (c < g.Cin) acc[c] = fmaf(d, pw[(co * g.Cin + c) * khkw], acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CI; ++c)
+        if (c < g.Cin) dx[(((size_t)b * g.Cin + c) * g.H + h) * g.W + ww] = acc[c];
+}
+
+bool small_dgrad_eligible(const cpc_conv_params* p) {
+    return p->c_in <= SD_MAX_CIN && (int64_t)p->c_out * p->c_in * p->kh * p->kw <= SD_MAX_W && p->batch <= 65535;
+}
+
+int small_dgrad_launch(const float* dy, const float* w, float* dx, const cpc_conv_params* p, cudaStream_t s) {
+    if (!small_dgrad_eligible(p)) return CPC_ERR_UNSUPPORTED;
+    const SmallGeom g = small_geom(p);
+    const dim3 grid(ceil_div(g.W, 32), ceil_div(g.H, 8), g.B), block(32, 8);
+    const size_t smem = sizeof(float) * (size_t)g.Cout * g.Cin * g.kh * g.kw;
+    if (g.Cin == 1) small_dgrad_kernel<1><<<grid, block, smem, s>>>(dy, w, dx, g);
+    else if (g.Cin == 2) small_dgrad_kernel<2><<<grid, block, smem, s>>>(dy, w, dx, g);
+    else small_dgrad_kernel<SD_MAX_CIN><<<grid, block, smem, s>>>(dy, w, dx, g);
+    if (cudaGetLastError() != cudaSuccess) return CPC_ERR_CUDA;
+    count_launch();
+    return CPC_OK;
+}
+
 bool smallk_eligible(const cpc_conv_params* p, int which) {
     if (which == 1) return false;                                   // data gradient stays on the generic kernels
     const int64_t k = (int64_t)p->c_in * p->kh * p->kw;

@@ -446,7 +446,7 @@ def golden_validate(ref):
     np.savez_compressed(os.path.join(OUT, "validate.npz"), **out)
 
 
-def _run_e24(ref, audio_seed, perturb=0.0, batch=4, layer_noise=0.0):
+def _run_e24(ref, audio_seed, perturb=0.0, batch=4, layer_noise=0.0, experiment='e24', steps=2, no_dropout=False):
     """One run of the reference on experiments['e24']: setup_model, seeded weights, train() for two Adam steps.
     ``perturb`` > 0 multiplies the scalogram by (1 + perturb * randn): the conditioning probe (see golden_e24)."""
     import importlib
@@ -471,8 +471,10 @@ def _run_e24(ref, audio_seed, perturb=0.0, batch=4, layer_noise=0.0):
     saved_forward = am.ConvolutionalArBlock.forward
     am.ConvolutionalArBlock.forward = ar_block_forward
     try:
-        e = cfg.experiments['e24']
+        e = cfg.experiments[experiment]
         tc = e['training_config']
+        if no_dropout and 'dropout' in e['ar_model_config']:
+            e['ar_model_config']['dropout'] = 0.                  # the attention AR model's dropout draws from torch's RNG
         torch.manual_seed(0)
         model, pre, _ = sf.setup_model(cqt_params=e['cqt_config'], encoder_params=e['encoder_config'],
                                        ar_params=e['ar_model_config'], trainer_args=tc, device=None)
@@ -534,13 +536,38 @@ def _run_e24(ref, audio_seed, perturb=0.0, batch=4, layer_noise=0.0):
                                                    preprocessing=preprocessing, prediction_steps=tc['prediction_steps'],
                                                    ar_size=model.ar_size)
         random.seed(0)
-        trainer.train(batch_size=batch, epochs=1, lr=tc['learning_rate'], num_workers=0, max_steps=1 if (perturb > 0 or layer_noise > 0) else 2)
+        trainer.train(batch_size=batch, epochs=1, lr=tc['learning_rate'], num_workers=0,
+                      max_steps=1 if (perturb > 0 or layer_noise > 0) else steps)
         for h in hooks:
             h.remove()
         run["items"] = items
     finally:
         am.ConvolutionalArBlock.forward = saved_forward
     return run
+
+
+def golden_e29(ref):
+    """The reference's DEFAULT experiment (train_script.py:11): high-resolution CQT (44.1 kHz, 292 bins, hop 256), offset +
+    time-pooled scalogram, resnet arch 9, attention AR model, linear all-steps scoring with the Wasserstein gradient penalty.
+    One training step of setup_model(experiments['e29']) + train() at the full item length (367 616 samples), batch 2, with
+    the attention dropout set to 0 (it draws from torch's RNG) and the seeded weights / audio of golden_e24: the logged loss
+    (InfoNCE + penalty), max score and the encoder output."""
+    run = _run_e24(ref, 1234, batch=2, experiment='e29', steps=1, no_dropout=True)
+    model, tc, logger, captured = run["model"], run["tc"], run["logger"], run["captured"]
+    out = {"item_length": np.array(model.item_length), "batch": np.array(2), "order": np.array(run["order"]),
+           "losses": np.array(logger.losses), "max_scores": np.array(logger.scores), "z": captured["z"].numpy(),
+           "audio_check": run["items"][:, ::4099].numpy().copy(), "scal_shape": np.array(captured["scal"].shape),
+           "gradient_penalty_factor": np.array(float(tc["gradient_penalty_factor"])),
+           "names": np.array(json.dumps(run["names"]))}
+    # conditioning of the penalised loss: the penalty is a function of d(scores)/d(scalogram), i.e. of the ReLU gate pattern.
+    # The reference's own loss under the probes of golden_e24 (every conv / linear output * (1 + eps randn)):
+    for tag, eps in (("loss_snl", 2e-6), ("loss_snl5", 5e-6)):
+        probe = _run_e24(ref, 1234, batch=2, experiment='e29', steps=1, no_dropout=True, layer_noise=eps)
+        out[tag] = np.array(abs(probe["logger"].losses[0] - logger.losses[0]) / abs(logger.losses[0]))
+        out[tag + "_z"] = np.array(float((probe["captured"]["z"] - captured["z"]).norm() / captured["z"].norm()))
+        print(tag, float(out[tag]), "encoder output moves by", float(out[tag + "_z"]))
+    np.savez_compressed(os.path.join(OUT, "e29_step.npz"), **out)
+    print("e29 golden: loss", logger.losses, "max score", logger.scores, "z", tuple(captured["z"].shape))
 
 
 def golden_e24(ref):
@@ -704,7 +731,7 @@ def golden_configs():
         return getattr(v, "__name__", str(v))
 
     dump = {}
-    for name in ("e24", "e25", "e20"):
+    for name in ("e24", "e25", "e20", "e29", "e32"):          # e29: the reference's default experiment (train_script.py:11)
         e = cfg.experiments[name]
         dump[name] = {k: clean(e[k]) for k in ("cqt_config", "encoder_config", "ar_model_config", "training_config")}
     with open(os.path.join(OUT, "configs.json"), "w") as fh:
@@ -769,6 +796,7 @@ def main():
     golden_snapshot(ref)
     golden_scalogram_encoder(ref)
     golden_e24(ref)
+    golden_e29(ref)
     golden_configs_all(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

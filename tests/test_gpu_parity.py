@@ -994,6 +994,87 @@ def test_experiment_configs_train_one_step(cpc, name):
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
 
 
+@pytest.mark.parametrize("name", ["e29", "e32"])
+def test_high_res_experiments_train_one_step(cpc, name):
+    """The reference's DEFAULT experiment (e29, train_script.py:11) and the last one (e32), built from the reference's own
+    experiment dicts as imported (tests/golden/configs.json): 44.1 kHz / 292-bin / hop-256 filterbank (11 octave groups up
+    to 65 536 taps), offset + pooled scalogram, resnet arch 9, attention AR, Wasserstein gradient penalty (second-order
+    autograd through the conv kernels).  One optimisation step at the full item length, batch 2."""
+    plain = load_golden("configs.json")[name]
+    exp = cpc.configs.experiment_from_plain(plain)
+    tc = exp["training_config"]
+    torch.manual_seed(0)
+    dev = torch.device(DEV)
+    model, pre, _ = cpc.configs.setup_model(exp["cqt_config"], exp["encoder_config"], exp["ar_model_config"], tc, device=dev)
+    want = load_golden("configs_all.json")[name]
+    assert model.item_length == want["item_length"]
+    assert {n: list(p.shape) for n, p in model.named_parameters()} == want["params"]
+    trainer = cpc.ContrastiveEstimationTrainer(model=model, dataset=None, device=dev, regularization=tc["regularization"],
+                                               score_over_all_timesteps=tc["score_over_all_timesteps"],
+                                               score_function=tc["score_function"], preprocessing=pre,
+                                               prediction_steps=tc["prediction_steps"],
+                                               wasserstein_gradient_penalty=tc["wasserstein_gradient_penalty"],
+                                               gradient_penalty_factor=tc["gradient_penalty_factor"], verbose=False)
+    opt = trainer.make_optimizer(tc["learning_rate"])
+    model.train()
+    x = 0.1 * torch.randn(2, model.item_length, generator=torch.Generator().manual_seed(3))
+    losses = []
+    for _ in range(2):
+        loss, max_score = trainer.loss_on_batch(x.to(DEV))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(math.isfinite(v) for v in losses), losses
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+    print(name, "item length", model.item_length, "losses", losses, "gradient penalty", tc["wasserstein_gradient_penalty"])
+
+
+def test_e29_default_experiment_step_matches_reference_golden(cpc):
+    """The reference's default experiment e29 at the full item length (367 616 samples, batch 2): the loss the reference's
+    own setup_model + train() logs for its first step (InfoNCE + Wasserstein gradient penalty), its max score and the
+    encoder output (tests/golden/e29_step.npz, oracle/make_golden.py::golden_e29; attention dropout 0, seeded weights).
+    Covers the hop-256 filterbank (CUDA-core kernels + pooled scalogram), resnet arch 9 and the second-order path at size.
+    The penalty is a function of d(scores)/d(scalogram), i.e. of the ReLU gate pattern: its tolerance is the gate-noise
+    level discussed in DESIGN.md section 2, the forward quantities keep 1e-3."""
+    import cpc_oracle_model as OM
+    g = load_golden("e29_step.npz")
+    plain = load_golden("configs.json")["e29"]
+    plain["ar_model_config"]["dropout"] = 0.0
+    exp = cpc.configs.experiment_from_plain(plain)
+    tc = exp["training_config"]
+    torch.manual_seed(0)
+    dev = torch.device(DEV)
+    model, pre, _ = cpc.configs.setup_model(exp["cqt_config"], exp["encoder_config"], exp["ar_model_config"], tc, device=dev)
+    assert model.item_length == int(g["item_length"])
+    assert [n for n, _ in model.named_parameters()] == json.loads(str(g["names"]))
+    OM.reseed_parameters(model.named_parameters())
+    trainer = cpc.ContrastiveEstimationTrainer(model=model, dataset=None, device=dev, regularization=tc["regularization"],
+                                               score_over_all_timesteps=tc["score_over_all_timesteps"],
+                                               score_function=tc["score_function"], preprocessing=pre,
+                                               prediction_steps=tc["prediction_steps"],
+                                               wasserstein_gradient_penalty=tc["wasserstein_gradient_penalty"],
+                                               gradient_penalty_factor=tc["gradient_penalty_factor"], verbose=False)
+    batch, order = int(g["batch"]), [int(i) for i in g["order"]]
+    audio = OM.e24_audio(2 * batch, model.item_length, seed=1234)
+    assert np.array_equal(audio[:, ::4099].numpy(), g["audio_check"])
+    model.train()
+    seen = {}
+    hook = model.encoder.register_forward_hook(lambda m, i, o: seen.__setitem__("z", o.detach().clone()))
+    loss, mx = trainer.loss_on_batch(audio[order[:batch]].to(dev))
+    hook.remove()
+    loss.backward()
+    print("e29 golden: loss %.6f vs %.6f, max score %.6f vs %.6f, z err %.2e" % (
+        loss.item(), float(g["losses"][0]), mx.item(), float(g["max_scores"][0]), rel_err(seen["z"], g["z"])))
+    assert rel_err(seen["z"], g["z"]) < TOL
+    assert abs(mx.item() - float(g["max_scores"][0])) < TOL * abs(float(g["max_scores"][0]))
+    # the reference's own loss moves by loss_snl (0.35 %) / loss_snl5 (1.7 %) when each of its conv outputs moves by 2e-6 / 5e-6
+    # relative (its encoder output then moves by 7e-5 / 1.8e-4; the CUDA path's differs by 1.2e-4): bound = 3 x the larger
+    bound = max(TOL, 3.0 * max(float(g["loss_snl"]), float(g["loss_snl5"])))
+    assert abs(loss.item() - float(g["losses"][0])) < bound * abs(float(g["losses"][0])), (loss.item(), float(g["losses"][0]), bound)
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+
+
 @pytest.mark.parametrize("graphed", [False, True])
 def test_e24_full_size_training_steps_match_reference_golden(cpc, graphed):
     """BASELINE configs[1] itself, at the full item length, on the path bench.py measures (tensor-core CQT, block-tail

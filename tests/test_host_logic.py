@@ -93,7 +93,7 @@ def test_conv_dispatch_table_for_the_baseline_layers(built_lib):
         return (v + 7) // 8 * 8
 
     table = {  # name: (params, families (fwd, dgrad, wgrad), dy replicas)
-        "block0 conv_a": (params(2, 256, 629, 32, 3, 3, 2), (1, 0, 1), 0),
+        "block0 conv_a": (params(2, 256, 629, 32, 3, 3, 2), (1, 1, 1), 0),      # C_in = 2: direct kernels for all three
         "block0 conv_b": (params(32, 127, 314, 32, 64, 1, 1, pt=63), (2, 2, 2), 1),
         "block1 conv_a": (params(32, 127, 314, 128, 3, 3, 2), (4, 4, 4), 2),
         "block1 conv_b": (params(128, 63, 156, 128, 30, 1, 1), (3, 3, 3), 1),

@@ -110,6 +110,7 @@ class CQT(nn.Module):
         self.trainable = trainable
         self._packed = None
         self._packed_key = None
+        self._tensor_filters = None
 
     @property
     def trainable(self):
@@ -120,6 +121,13 @@ class CQT(nn.Module):
         for p in self.parameters():
             p.requires_grad = value
         self._trainable = value
+
+    def __getstate__(self):
+        """Whole-model pickles (the reference's snapshot format) and deepcopies carry the filterbank once, as the conv
+        weights: the packed device-side copies are caches."""
+        state = dict(self.__dict__)
+        state["_packed"], state["_packed_key"], state["_tensor_filters"] = None, None, None
+        return state
 
     def kernel_plan(self):
         offsets, total = [], 0

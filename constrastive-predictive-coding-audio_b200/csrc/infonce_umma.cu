@@ -285,6 +285,8 @@ struct NuBwd {
     NuGeom g;
     int owner_is_target;          // 1: owner rows are targets (output dZ), 0: owner rows are predictions (output dP)
     int n_slices;                 // E / 256 (ceil)
+    int n_split;                  // CTAs sharing one (problem, owner tile, E slice): each takes a range of the other operand's
+                                  // tiles and adds its partial result atomically (small problems: 16 CTAs -> up to 148)
     const float* lse;             // [prob * Bp + target]
     const float* grad_loss;
     float* out;                   // d_targets (B,E,K) contiguous or d_pred (B,K,E) contiguous
@@ -303,8 +305,11 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int w = blockIdx.x;
     const int es = w % p.n_slices; w /= p.n_slices;
+    const int sp = w % p.n_split; w /= p.n_split;
     const int ot = w % g.nT;
     const int prob = w / g.nT;
+    const int st0 = (int)((long)sp * g.nT / p.n_split), st1 = (int)((long)(sp + 1) * g.nT / p.n_split);   // other tiles of this CTA
+    const int n_it = st1 - st0;
     const int e_chunks = min(4, g.EC - es * 4);                   // 64-wide E chunks in this slice
 
     if (warp == 0 && lane == 0) {
@@ -337,9 +342,9 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                     tma_load_4d(sp + NU_TILE, &tmap_other, &bars->full[stage], q * 64, st * 128, prob, 0);
                 }
             };
-            phase1(0);
-            for (int st = 0; st < g.nT; ++st) {
-                if (st + 1 < g.nT) phase1(st + 1);
+            if (n_it > 0) phase1(st0);
+            for (int st = st0; st < st1; ++st) {
+                if (st + 1 < st1) phase1(st + 1);
                 for (int a = 0; a < e_chunks; ++a, ++n) {                    // phase 3: other rows, E slice chunk a
                     const int stage = n % NU_BSTAGES;
                     mbar_wait(&bars->empty[stage], ((n / NU_BSTAGES) & 1) ^ 1);
@@ -356,9 +361,9 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
             const uint32_t gs_addr = smem_u32(gs);
             uint32_t n = 0;
             // S is double-buffered (TMEM columns 0-127 / 128-255): the score GEMM of tile st+1 overlaps the epilogue of st
-            auto phase1 = [&](int st) {
-                const uint32_t buf = st & 1;
-                mbar_wait(&bars->s_empty[buf], ((st >> 1) & 1) ^ 1);         // epilogue finished reading this S buffer
+            auto phase1 = [&](int it) {                                     // it: index inside this CTA's tile range
+                const uint32_t buf = it & 1;
+                mbar_wait(&bars->s_empty[buf], ((it >> 1) & 1) ^ 1);         // epilogue finished reading this S buffer
                 tc_fence_after();
                 for (int q = 0; q < g.EC; ++q, ++n) {
                     const int stage = n % NU_BSTAGES;
@@ -378,10 +383,10 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                 }
                 tc_commit(&bars->s_full[buf]);
             };
-            phase1(0);
-            for (int st = 0; st < g.nT; ++st) {
-                if (st + 1 < g.nT) phase1(st + 1);
-                mbar_wait(&bars->g_full, st & 1);                            // G tile written (and fenced) by the epilogue warps
+            if (n_it > 0) phase1(0);
+            for (int it = 0; it < n_it; ++it) {
+                if (it + 1 < n_it) phase1(it + 1);
+                mbar_wait(&bars->g_full, it & 1);                            // G tile written (and fenced) by the epilogue warps
                 tc_fence_after();
                 for (int a = 0; a < e_chunks; ++a, ++n) {
                     const int stage = n % NU_BSTAGES;
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                         for (int ks = 0; ks < 8; ++ks) {                     // K = 128 other rows
                             const uint64_t ad = make_smem_desc(ga + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
                             const uint64_t bd = make_smem_desc(ba + ks * (16 * 128), 64 * 128, 1024);
-                            mma_bf16(d_tmem, ad, bd, idesc_g, (uint32_t)(st | cb | ks));
+                            mma_bf16(d_tmem, ad, bd, idesc_g, (uint32_t)(it | cb | ks));
                         }
                     }
                     tc_commit(&bars->empty[stage]);
@@ -415,20 +420,21 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
         const float lse_own = (p.owner_is_target && own_ok) ? __ldg(p.lse + (size_t)prob * g.Bp + orow) : 0.f;
         const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
         uint8_t* grow = gs + (rl >> 3) * 1024 + (rl & 7) * 128;              // this owner row inside a K atom
-        for (int st = 0; st < g.nT; ++st) {
+        for (int it = 0; it < n_it; ++it) {
+            const int st = st0 + it;
             if (!p.owner_is_target) {                                        // lse of the 128 target columns of this tile
                 const int c = st * 128 + rl;
-                bars->lse_s[st & 1][rl] = c < g.Bp ? __ldg(p.lse + (size_t)prob * g.Bp + c) : 0.f;
+                bars->lse_s[it & 1][rl] = c < g.Bp ? __ldg(p.lse + (size_t)prob * g.Bp + c) : 0.f;
             }
-            mbar_wait(&bars->s_full[st & 1], (st >> 1) & 1);
+            mbar_wait(&bars->s_full[it & 1], (it >> 1) & 1);
             tc_fence_after();
-            mbar_wait(&bars->g_empty, (st & 1) ^ 1);                         // previous G tile consumed by the MMAs
+            mbar_wait(&bars->g_empty, (it & 1) ^ 1);                         // previous G tile consumed by the MMAs
             asm volatile("bar.sync 1, 128;" ::: "memory");                  // lse_s visible to all epilogue threads
             const int n_valid = min(128, g.Bp - st * 128);                   // rows of the other operand inside the problem
-            const float* lrow = bars->lse_s[st & 1];
+            const float* lrow = bars->lse_s[it & 1];
             for (int n0 = 0; n0 < 128; n0 += 32) {
                 uint32_t raw[32];
-                tmem_ld32(lane_base + (uint32_t)((st & 1) * 128 + n0), raw);
+                tmem_ld32(lane_base + (uint32_t)((it & 1) * 128 + n0), raw);
                 tmem_ld_wait();
                 float gv[32];
                 float sg[32];                                                 // d softplus / du (softplus scores only)
@@ -508,7 +514,7 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
             tc_fence_before();
             fence_proxy_async();                                             // generic-proxy smem writes -> tensor core
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&bars->g_full); mbar_arrive(&bars->s_empty[st & 1]); }
+            if (lane == 0) { mbar_arrive(&bars->g_full); mbar_arrive(&bars->s_empty[it & 1]); }
         }
         // flush the accumulator: rows = owner rows, columns = E slice
         mbar_wait(&bars->acc_full, 0);
@@ -524,16 +530,26 @@ __global__ void __launch_bounds__(NU_THREADS, 1) nce_umma_bwd_kernel(const __gri
                     // d_targets (B, E, K) contiguous: target row (t, k') -> ((t*E + e)*K + k')
                     const int t = g.all ? orow / g.K : orow, kk = g.all ? orow - t * g.K : prob;
                     float* o = p.out + ((size_t)t * g.E + e0) * g.K + kk;
+                    if (p.n_split > 1) {                                     // partial result: the output was zeroed
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) o[(size_t)j * g.K] = __uint_as_float(raw[j]);
+                        for (int j = 0; j < 32; ++j) atomicAdd(o + (size_t)j * g.K, __uint_as_float(raw[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[(size_t)j * g.K] = __uint_as_float(raw[j]);
+                    }
                 } else {
                     // d_pred (B, K, E) contiguous: prediction row (d, k) -> (d*K + k)*E + e
                     const size_t r = g.all ? (size_t)orow : (size_t)orow * g.K + prob;
-                    float4* o = reinterpret_cast<float4*>(p.out + r * g.E + e0);
+                    if (p.n_split > 1) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
-                                           __uint_as_float(raw[4 * j + 3]));
+                        for (int j = 0; j < 32; ++j) atomicAdd(p.out + r * g.E + e0 + j, __uint_as_float(raw[j]));
+                    } else {
+                        float4* o = reinterpret_cast<float4*>(p.out + r * g.E + e0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            o[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                                               __uint_as_float(raw[4 * j + 3]));
+                    }
                 }
             }
     }
@@ -638,7 +654,16 @@ int nce_umma_bwd(const float* pred, const float* targets, const float* lse, cons
     NuBwd k{};
     k.g = g; k.lse = lse; k.grad_loss = grad_loss;
     k.n_slices = ceil_div(g.EC, 4);
-    const int grid = g.nprob * g.nT * k.n_slices;
+    // small problems (the native e24 size is 16 CTAs): split the loop over the other operand's tiles across CTAs
+    k.n_split = 148 / (g.nprob * g.nT * k.n_slices);
+    if (k.n_split > g.nT) k.n_split = g.nT;
+    if (k.n_split < 1) k.n_split = 1;
+    const int grid = g.nprob * g.nT * k.n_split * k.n_slices;
+    if (k.n_split > 1) {
+        const size_t n_out = (size_t)g.B * g.K * g.E;
+        if (cudaMemsetAsync(d_targets, 0, n_out * sizeof(float), s) != cudaSuccess ||
+            cudaMemsetAsync(d_pred, 0, n_out * sizeof(float), s) != cudaSuccess) return CPC_ERR_CUDA;
+    }
     auto launch = [&](auto kern) -> int {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return CPC_ERR_CUDA;
         k.owner_is_target = 1; k.out = d_targets;

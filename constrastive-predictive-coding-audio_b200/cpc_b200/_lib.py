@@ -18,7 +18,7 @@ CONV_FLAG_CUDA_CORE, CONV_FLAG_NO_TALL, CONV_FLAG_NO_SMALLK, CONV_FLAG_NO_FUSED_
 CONV_FLAG_NO_MMA_SMALL_WGRAD = 16
 INFONCE_FLAG_NO_TENSOR = 1
 INFONCE_OUT_FLOATS = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class CqtParams(ctypes.Structure):
@@ -99,6 +99,10 @@ SIGNATURES = {
     "cpc_bn_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(BnParams)]),
     "cpc_bn_relu_fwd_packed": (ctypes.c_int, [_P] * 9 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
     "cpc_bn_relu_bwd_packed": (ctypes.c_int, [_P] * 12 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
+    "cpc_bn_mask_bytes": (ctypes.c_size_t, [ctypes.POINTER(BnParams)]),
+    "cpc_bn_relu_fwd_mask": (ctypes.c_int, [_P] * 10 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
+    "cpc_bn_relu_bwd_mask": (ctypes.c_int, [_P] * 12 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
+    "cpc_bn_relu_bwd_packed_mask": (ctypes.c_int, [_P] * 13 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
     "cpc_maxpool_fwd": (ctypes.c_int, [_P, _P, ctypes.POINTER(PoolParams), _P]),
     "cpc_maxpool_bwd": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(PoolParams), _P]),
     "cpc_infonce_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(InfoNceParams), ctypes.c_int]),

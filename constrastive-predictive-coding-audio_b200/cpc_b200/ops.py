@@ -478,6 +478,15 @@ def _bn_params(x_shape, res_shape, res_off, relu, outer_relu, training, eps, mom
     return p
 
 
+def _bn_mask(lib, p, device):
+    """Bit-mask buffer for the ReLU behind the residual add of (p), or None when the shape has none (or the switch
+    CPC_NO_BN_MASK asks for the recomputing kernels)."""
+    if _switch("CPC_NO_BN_MASK"):
+        return None
+    n = int(lib.cpc_bn_mask_bytes(ctypes.byref(p)))
+    return torch.empty(n, dtype=torch.uint8, device=device) if n else None
+
+
 def _bn_key(tag, p):
     return "%s b%d %dx%dx%d%s" % (tag, p.batch, p.channels, p.height, p.width, " +res" if p.res_height else "")
 
@@ -503,20 +512,23 @@ class _BnReluFunction(torch.autograd.Function):
         save_rstd = torch.empty(c, dtype=torch.float32, device=x.device)
         ws = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p)), x.device)
         n = x.numel()
+        mask = _bn_mask(lib, p, x.device) if any(ctx.needs_input_grad) else None
         with torch.cuda.device(x.device):
-            _call(_bn_key("cpc_bn_relu_fwd", p), 0.0, lib.cpc_bn_relu_fwd, _ptr(x), _ptr(gamma), _ptr(beta),
+            _call(_bn_key("cpc_bn_relu_fwd", p), 0.0, lib.cpc_bn_relu_fwd_mask, _ptr(x), _ptr(gamma), _ptr(beta),
                   _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(out), _ptr(save_mean), _ptr(save_rstd),
-                  ctypes.byref(p), _ptr(ws), ws.numel(), _stream(),
+                  _ptr(mask), ctypes.byref(p), _ptr(ws), ws.numel(), _stream(),
                   nbytes=4.0 * n * ((3 if training else 2) + (1 if residual is not None else 0)))
         ctx.cfg = (tuple(x.shape), None if residual is None else tuple(residual.shape), res_off, relu, outer_relu,
                    training, eps, momentum)
-        ctx.save_for_backward(x, gamma, beta, save_mean, save_rstd, residual)
+        ctx.has_residual = residual is not None
+        # with the saved mask the residual's values are not needed again: keep only what autograd must return
+        ctx.save_for_backward(x, gamma, beta, save_mean, save_rstd, residual if mask is None else None, mask)
         return out
 
     @staticmethod
     @once_differentiable                                         # second-order mode uses the literal modules instead
     def backward(ctx, dout):
-        x, gamma, beta, save_mean, save_rstd, residual = ctx.saved_tensors
+        x, gamma, beta, save_mean, save_rstd, residual, mask = ctx.saved_tensors
         lib = _lib.load()
         x_shape, res_shape, res_off, relu, outer_relu, training, eps, momentum = ctx.cfg
         p = _bn_params(x_shape, res_shape, res_off, relu, outer_relu, training, eps, momentum)
@@ -524,13 +536,16 @@ class _BnReluFunction(torch.autograd.Function):
         dx = torch.empty_like(x)
         dgamma = torch.empty_like(gamma) if gamma is not None else None
         dbeta = torch.empty_like(beta) if beta is not None else None
-        d_res = torch.empty_like(residual) if (residual is not None and ctx.needs_input_grad[5]) else None
+        d_res = (torch.empty(res_shape, dtype=torch.float32, device=x.device)
+                 if (ctx.has_residual and ctx.needs_input_grad[5]) else None)
         ws = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p)), x.device)
         n = x.numel()
+        # the residual pointer only says "there is a residual" when the mask is given; x stands in for it
+        res_arg = residual if residual is not None else (x if ctx.has_residual else None)
         with torch.cuda.device(x.device):
-            _call(_bn_key("cpc_bn_relu_bwd", p), 0.0, lib.cpc_bn_relu_bwd, _ptr(dout), _ptr(x), _ptr(gamma), _ptr(beta),
-                  _ptr(save_mean), _ptr(save_rstd), _ptr(residual), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(d_res),
-                  ctypes.byref(p), _ptr(ws), ws.numel(), _stream(),
+            _call(_bn_key("cpc_bn_relu_bwd", p), 0.0, lib.cpc_bn_relu_bwd_mask, _ptr(dout), _ptr(x), _ptr(gamma),
+                  _ptr(beta), _ptr(save_mean), _ptr(save_rstd), _ptr(res_arg), _ptr(mask), _ptr(dx), _ptr(dgamma),
+                  _ptr(dbeta), _ptr(d_res), ctypes.byref(p), _ptr(ws), ws.numel(), _stream(),
                   nbytes=4.0 * n * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0)))
         return dx, dgamma, dbeta, None, None, d_res, None, None, None, None, None, None
 
@@ -613,33 +628,38 @@ class _BlockTailFunction(torch.autograd.Function):
                   _ptr(wsc), wsc.numel() if wsc is not None else 0, _stream())
             ws1 = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p1)), dev)
             n1 = y_b.numel()
-            _call(_bn_key("cpc_bn_relu_fwd", p1), 0.0, lib.cpc_bn_relu_fwd, _ptr(y_b), _ptr(g1), _ptr(b1), _ptr(rm1),
-                  _ptr(rv1), _ptr(residual), _ptr(out), _ptr(mean1), _ptr(rstd1), ctypes.byref(p1), _ptr(ws1), ws1.numel(),
-                  _stream(), nbytes=4.0 * n1 * ((3 if tr1 else 2) + (1 if residual is not None else 0)))
+            mask = _bn_mask(lib, p1, dev) if any(ctx.needs_input_grad) else None
+            _call(_bn_key("cpc_bn_relu_fwd", p1), 0.0, lib.cpc_bn_relu_fwd_mask, _ptr(y_b), _ptr(g1), _ptr(b1), _ptr(rm1),
+                  _ptr(rv1), _ptr(residual), _ptr(out), _ptr(mean1), _ptr(rstd1), _ptr(mask), ctypes.byref(p1), _ptr(ws1),
+                  ws1.numel(), _stream(), nbytes=4.0 * n1 * ((3 if tr1 else 2) + (1 if residual is not None else 0)))
         ctx.cfg = cfg
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(y_a, g0, b0, mean0, rstd0, packed_h, w, y_b, g1, b1, mean1, rstd1, residual)
+        ctx.res_shape = None if residual is None else tuple(residual.shape)
+        ctx.save_for_backward(y_a, g0, b0, mean0, rstd0, packed_h, w, y_b, g1, b1, mean1, rstd1,
+                              residual if mask is None else None, mask)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        y_a, g0, b0, mean0, rstd0, packed_h, w, y_b, g1, b1, mean1, rstd1, residual = ctx.saved_tensors
+        y_a, g0, b0, mean0, rstd0, packed_h, w, y_b, g1, b1, mean1, rstd1, residual, mask = ctx.saved_tensors
         (top, out_hw, res_off, outer_relu, tr0, eps0, mom0, tr1, eps1, mom1, precision) = ctx.cfg
         lib = _lib.load()
         dev = dout.device
         dout = dout.contiguous()
         B, C, H, W = y_a.shape
         co = w.shape[0]
-        p1 = _bn_params(tuple(y_b.shape), None if residual is None else tuple(residual.shape), res_off, True, outer_relu,
-                        tr1, eps1, mom1)
+        p1 = _bn_params(tuple(y_b.shape), ctx.res_shape, res_off, True, outer_relu, tr1, eps1, mom1)
+        # with the saved mask the residual is not read: y_b stands in for "there is a residual"
+        res_arg = residual if residual is not None else (y_b if ctx.res_shape is not None else None)
         pc = _conv_params((B, C, H, W), tuple(w.shape), (1, 1), top, 0, out_hw, False, precision)
         p0 = _bn_params((B, C, H, W), None, (0, 0), True, False, tr0, eps0, mom0)
         packed_dy = torch.empty(int(lib.cpc_bn_packed_bytes(ctypes.byref(p1))), dtype=torch.uint8, device=dev)
         db = torch.empty(co, dtype=torch.float32, device=dev) if ctx.has_bias else None
         dg1 = torch.empty_like(g1) if g1 is not None else None
         dbt1 = torch.empty_like(b1) if b1 is not None else None
-        d_res = torch.empty_like(residual) if (residual is not None and ctx.needs_input_grad[11]) else None
+        d_res = (torch.empty(ctx.res_shape, dtype=torch.float32, device=dev)
+                 if (ctx.res_shape is not None and ctx.needs_input_grad[11]) else None)
         dh = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
         dw = torch.empty_like(w)
         dy_a = torch.empty_like(y_a)
@@ -648,9 +668,9 @@ class _BlockTailFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws1 = _workspace(lib.cpc_bn_relu_workspace_bytes(ctypes.byref(p1)), dev)
             n1 = y_b.numel()
-            _call(_bn_key("cpc_bn_relu_bwd", p1) + " ->packed", 0.0, lib.cpc_bn_relu_bwd_packed, _ptr(dout), _ptr(y_b), _ptr(g1),
-                  _ptr(b1), _ptr(mean1), _ptr(rstd1), _ptr(residual), _ptr(packed_dy), _ptr(db), _ptr(dg1), _ptr(dbt1),
-                  _ptr(d_res), ctypes.byref(p1), _ptr(ws1), ws1.numel(), _stream(),
+            _call(_bn_key("cpc_bn_relu_bwd", p1) + " ->packed", 0.0, lib.cpc_bn_relu_bwd_packed_mask, _ptr(dout), _ptr(y_b),
+                  _ptr(g1), _ptr(b1), _ptr(mean1), _ptr(rstd1), _ptr(res_arg), _ptr(mask), _ptr(packed_dy), _ptr(db),
+                  _ptr(dg1), _ptr(dbt1), _ptr(d_res), ctypes.byref(p1), _ptr(ws1), ws1.numel(), _stream(),
                   nbytes=4.0 * n1 * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0)))
             wsd = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(pc), 1), dev)
             _call(_conv_key("cpc_conv_dgrad", pc), _conv_flops(pc), lib.cpc_conv_dgrad_ex, _ptr(None), _ptr(w), _ptr(dh),

@@ -8,7 +8,9 @@
 //
 // All kernels are HBM-bound streaming passes over NCHW planes: forward = statistics pass (1 read) + apply
 // pass (1-2 reads, 1 write); backward = reduction pass (2-3 reads) + gradient pass (2-3 reads, 1-2 writes).
-// Masks are recomputed from x (and the residual), so nothing but x, mean and rstd is saved for backward.
+// The inner ReLU mask is recomputed from x; the outer one (ReLU after the residual add) is either recomputed from x and
+// the residual, or -- *_mask entry points -- read from a bit mask the forward pass wrote (1 bit per element instead of
+// re-reading the residual in both backward passes: 2 x 327 MB for the first block of arch 7).
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -127,60 +129,76 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 
 // All streaming kernels below are two-phase per thread: issue every load of the thread's BN_PER_THREAD elements
 // first (independent, predicated), then compute and store -- one load in flight per thread is latency-bound.
+template <bool MASK>
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ affine,
                                                              const float* __restrict__ res, float* __restrict__ out,
-                                                             BnGeom g) {
+                                                             uint32_t* __restrict__ mask, BnGeom g) {
     const int plane = blockIdx.x;
     const int c = plane % g.C;
     const float sc = __ldg(affine + 2 * c), sh = __ldg(affine + 2 * c + 1);
     const float* px = x + (size_t)plane * g.HW;
     float* po = out + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
-    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
-    float xv[BN_PER_THREAD], rv[BN_PER_THREAD];
+    // the mask variant works in two half-batches: the ballots pin every load of a batch in front of them, and a full
+    // batch of 2 x 16 live values would halve the occupancy
+    constexpr int BATCH = MASK ? BN_PER_THREAD / 2 : BN_PER_THREAD;
+    uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
+#pragma unroll 1
+    for (int half = 0; half < BN_PER_THREAD / BATCH; ++half) {
+        const int i0 = blockIdx.y * BN_SEG + half * BATCH * BN_THREADS + threadIdx.x;
+        float xv[BATCH], rv[BATCH];
 #pragma unroll
-    for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * BN_THREADS;
-        xv[u] = i < g.HW ? __ldg(px + i) : 0.f;
-        rv[u] = 0.f;
-        if (pr && i < g.HW) {
-            int h, w;
-            g.d_w.divmod(i, h, w);
-            rv[u] = __ldg(pr + (size_t)h * g.RW + w);
+        for (int u = 0; u < BATCH; ++u) {
+            const int i = i0 + u * BN_THREADS;
+            xv[u] = i < g.HW ? __ldg(px + i) : 0.f;
+            rv[u] = 0.f;
+            if (pr && i < g.HW) {
+                int h, w;
+                g.d_w.divmod(i, h, w);
+                rv[u] = __ldg(pr + (size_t)h * g.RW + w);
+            }
         }
-    }
 #pragma unroll
-    for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * BN_THREADS;
-        float v = fmaf(xv[u], sc, sh);
-        if (g.relu) v = fmaxf(v, 0.f);
-        if (pr) {
-            v += rv[u];
-            if (g.outer_relu) v = fmaxf(v, 0.f);
+        for (int u = 0; u < BATCH; ++u) {
+            const int i = i0 + u * BN_THREADS;
+            float v = fmaf(xv[u], sc, sh);
+            if (g.relu) v = fmaxf(v, 0.f);
+            if (pr) {
+                v += rv[u];
+                if constexpr (MASK) {
+                    // bit (i & 31) of word i / 32 of this plane: a warp's lanes hold 32 consecutive, 32-aligned elements
+                    const unsigned bits = __ballot_sync(0xffffffffu, i < g.HW && v > 0.f);
+                    if ((threadIdx.x & 31) == 0 && i < g.HW) pm[i >> 5] = bits;
+                }
+                if (g.outer_relu) v = fmaxf(v, 0.f);
+            }
+            if (i < g.HW) po[i] = v;
         }
-        if (i < g.HW) po[i] = v;
     }
 }
 
 // Gradient entering the normalisation: g2 = dout * [outer mask] * [inner mask]; also returns xhat.
+// outer_bit: -1 = recompute the outer mask from x and the residual, 0 / 1 = the bit the forward pass saved.
 __device__ __forceinline__ float bn_grad_in(float dout, float xv, float mean, float rstd, float gam, float bet, bool has_res,
-                                            float resv, const BnGeom& g, float& xhat, float& g1) {
+                                            float resv, const BnGeom& g, float& xhat, float& g1, int outer_bit = -1) {
     xhat = (xv - mean) * rstd;
     const float y = fmaf(xhat, gam, bet);
     const float v = g.relu ? fmaxf(y, 0.f) : y;
     g1 = dout;
-    if (has_res && g.outer_relu && !(v + resv > 0.f)) g1 = 0.f;
+    if (has_res && g.outer_relu && (outer_bit >= 0 ? outer_bit == 0 : !(v + resv > 0.f))) g1 = 0.f;
     return (g.relu && !(y > 0.f)) ? 0.f : g1;
 }
 
 // sums2[c*2 + {0,1}] += sum g2, sum g2 * xhat
+template <bool MASK>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ x,
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta,
                                                                   const float* __restrict__ save_mean,
                                                                   const float* __restrict__ save_rstd,
-                                                                  const float* __restrict__ res, double* __restrict__ sums2,
-                                                                  BnGeom g) {
+                                                                  const float* __restrict__ res,
+                                                                  const uint32_t* __restrict__ mask,
+                                                                  double* __restrict__ sums2, BnGeom g) {
     __shared__ double red[BN_THREADS / 32];
     const int plane = blockIdx.x;
     const int c = plane % g.C;
@@ -189,23 +207,29 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     const float* px = x + (size_t)plane * g.HW;
     const float* pd = dout + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
-    const bool need_res = pr != nullptr && g.outer_relu;
+    const bool need_res = !MASK && pr != nullptr && g.outer_relu;
+    const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
     float s = 0.f, q = 0.f;
     for (int seg = 0; seg < BN_RED_SEGS; ++seg) {
         const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * BN_SEG + threadIdx.x;
         if (i0 - (int)threadIdx.x >= g.HW) break;
-        float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[BN_PER_THREAD];
+        float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[MASK ? 1 : BN_PER_THREAD];
+        uint32_t ob = 0;                                             // MASK: bit u = saved outer-ReLU bit of element u
 #pragma unroll
         for (int u = 0; u < BN_PER_THREAD; ++u) {
             const int i = i0 + u * BN_THREADS;
             const bool in = i < g.HW;
             xv[u] = in ? __ldg(px + i) : 0.f;
             dv[u] = in ? __ldg(pd + i) : 0.f;
-            rv[u] = 0.f;
+            if constexpr (MASK) {
+                if (in) ob |= ((__ldg(pm + (i >> 5)) >> (i & 31)) & 1u) << u;
+                continue;
+            }
+            rv[MASK ? 0 : u] = 0.f;
             if (need_res && in) {
                 int h, w;
                 g.d_w.divmod(i, h, w);
-                rv[u] = __ldg(pr + (size_t)h * g.RW + w);
+                rv[MASK ? 0 : u] = __ldg(pr + (size_t)h * g.RW + w);
             }
         }
 #pragma unroll
@@ -213,7 +237,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
             const int i = i0 + u * BN_THREADS;
             if (i < g.HW) {
                 float xhat, g1;
-                const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, rv[u], g, xhat, g1);
+                const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, MASK ? 0.f : rv[MASK ? 0 : u], g,
+                                            xhat, g1, MASK ? (int)((ob >> u) & 1u) : -1);
                 s += g2;
                 q = fmaf(g2, xhat, q);
             }
@@ -227,12 +252,14 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
 // dx = gamma * rstd * (g2 - mean(g2) - xhat * mean(g2 * xhat))   [training]
 // dx = gamma * rstd * g2                                           [running statistics]
 // d_res (inside the crop) = g1;  dgamma / dbeta written by the first block of each channel of item 0.
+template <bool MASK>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ x,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta,
                                                                  const float* __restrict__ save_mean,
                                                                  const float* __restrict__ save_rstd,
                                                                  const float* __restrict__ res,
+                                                                 const uint32_t* __restrict__ mask,
                                                                  const double* __restrict__ sums2, float* __restrict__ dx,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                  float* __restrict__ d_res, BnGeom g, double count,
@@ -256,22 +283,28 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     const float* pr = res ? res + roff : nullptr;
     float* pdr = d_res ? d_res + roff : nullptr;
     const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
-    float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[BN_PER_THREAD];
-    int ro[BN_PER_THREAD];                                           // offset inside the residual plane
-    const bool need_res = pr != nullptr && g.outer_relu;
+    float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[MASK ? 1 : BN_PER_THREAD];
+    int ro[MASK ? 1 : BN_PER_THREAD];                                // offset inside the residual plane (MASK: recomputed)
+    uint32_t ob = 0;                                                 // MASK: bit u = saved outer-ReLU bit of element u
+    const bool need_res = !MASK && pr != nullptr && g.outer_relu;
+    const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
         const int i = i0 + u * BN_THREADS;
         const bool in = i < g.HW;
         xv[u] = in ? __ldg(px + i) : 0.f;
         dv[u] = in ? __ldg(pd + i) : 0.f;
-        rv[u] = 0.f;
-        ro[u] = 0;
+        if constexpr (MASK) {
+            if (in) ob |= ((__ldg(pm + (i >> 5)) >> (i & 31)) & 1u) << u;
+            continue;
+        }
+        rv[MASK ? 0 : u] = 0.f;
+        ro[MASK ? 0 : u] = 0;
         if ((pr || pdr) && in) {
             int h, w;
             g.d_w.divmod(i, h, w);
-            ro[u] = h * g.RW + w;
-            if (need_res) rv[u] = __ldg(pr + ro[u]);
+            ro[MASK ? 0 : u] = h * g.RW + w;
+            if (need_res) rv[MASK ? 0 : u] = __ldg(pr + ro[MASK ? 0 : u]);
         }
     }
 #pragma unroll
@@ -279,9 +312,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
         const int i = i0 + u * BN_THREADS;
         if (i < g.HW) {
             float xhat, g1;
-            const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, rv[u], g, xhat, g1);
+            const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, MASK ? 0.f : rv[MASK ? 0 : u], g, xhat,
+                                        g1, MASK ? (int)((ob >> u) & 1u) : -1);
             pdx[i] = k * (g2 - m1 - xhat * m2);
-            if (pdr) pdr[ro[u]] = g1;
+            if (pdr) {
+                if constexpr (MASK) {
+                    int h, w;
+                    g.d_w.divmod(i, h, w);
+                    pdr[h * g.RW + w] = g1;
+                } else {
+                    pdr[ro[MASK ? 0 : u]] = g1;
+                }
+            }
         }
     }
 }
@@ -467,10 +509,12 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_packed_kernel(const float
     }
 }
 
+template <bool MASK>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
     const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ save_mean, const float* __restrict__ save_rstd, const float* __restrict__ res,
-    const double* __restrict__ sums2, PackedOut pk, float* __restrict__ dx_sum, float* __restrict__ dgamma,
+    const uint32_t* __restrict__ mask, const double* __restrict__ sums2, PackedOut pk, float* __restrict__ dx_sum,
+    float* __restrict__ dgamma,
     float* __restrict__ dbeta, float* __restrict__ d_res, BnGeom g, FastDiv d_w2, double count, int training) {
     const int plane = blockIdx.x;
     const int c = plane % g.C;
@@ -491,24 +535,29 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
     float* pdr = d_res ? d_res + roff : nullptr;
     const int n_pairs = g.HW >> 1;
     const int j0 = blockIdx.y * BN_PAIR_SEG + threadIdx.x;
-    float2 xv[BN_PAIRS], dv[BN_PAIRS], rv[BN_PAIRS];
+    float2 xv[BN_PAIRS], dv[BN_PAIRS], rv[MASK ? 1 : BN_PAIRS];
     int hh[BN_PAIRS], ww[BN_PAIRS];
-    const bool need_res = pr != nullptr && g.outer_relu;
+    uint32_t ob = 0;                                                 // MASK: bits 2u, 2u + 1 = saved bits of pair u
+    const bool need_res = !MASK && pr != nullptr && g.outer_relu;
+    const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
 #pragma unroll
     for (int u = 0; u < BN_PAIRS; ++u) {
         const int j = j0 + u * BN_THREADS;
         const bool in = j < n_pairs;
         xv[u] = in ? __ldg(px + j) : make_float2(0.f, 0.f);
         dv[u] = in ? __ldg(pd + j) : make_float2(0.f, 0.f);
-        rv[u] = make_float2(0.f, 0.f);
+        if constexpr (!MASK) rv[MASK ? 0 : u] = make_float2(0.f, 0.f);
         hh[u] = 0; ww[u] = 0;
+        if constexpr (MASK) {
+            if (in) ob |= ((__ldg(pm + (j >> 4)) >> ((2 * j) & 31)) & 3u) << (2 * u);   // both bits of the pair
+        }
         if (in) {
             int wp;
             d_w2.divmod(j, hh[u], wp);
             ww[u] = 2 * wp;
             if (need_res) {
                 const float* q = pr + (size_t)hh[u] * g.RW + ww[u];
-                rv[u] = make_float2(__ldg(q), __ldg(q + 1));
+                rv[MASK ? 0 : u] = make_float2(__ldg(q), __ldg(q + 1));
             }
         }
     }
@@ -518,8 +567,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
         const int j = j0 + u * BN_THREADS;
         if (j < n_pairs) {
             float xh0, xh1, g10, g11;
-            const float g20 = bn_grad_in(dv[u].x, xv[u].x, mean, rstd, gam, bet, pr != nullptr, rv[u].x, g, xh0, g10);
-            const float g21 = bn_grad_in(dv[u].y, xv[u].y, mean, rstd, gam, bet, pr != nullptr, rv[u].y, g, xh1, g11);
+            const float2 r2 = MASK ? make_float2(0.f, 0.f) : rv[MASK ? 0 : u];
+            const float g20 = bn_grad_in(dv[u].x, xv[u].x, mean, rstd, gam, bet, pr != nullptr, r2.x, g, xh0, g10,
+                                         MASK ? (int)((ob >> (2 * u)) & 1u) : -1);
+            const float g21 = bn_grad_in(dv[u].y, xv[u].y, mean, rstd, gam, bet, pr != nullptr, r2.y, g, xh1, g11,
+                                         MASK ? (int)((ob >> (2 * u + 1)) & 1u) : -1);
             const float d0 = k * (g20 - m1 - xh0 * m2), d1 = k * (g21 - m1 - xh1 * m2);
             packed_store2(pk, g, plane, hh[u], ww[u], d0, d1);
             total += d0 + d1;
@@ -554,10 +606,20 @@ extern "C" size_t cpc_bn_relu_workspace_bytes(const cpc_bn_params* p) {
     return align_up(sizeof(double) * 2 * (size_t)p->channels, 256) + align_up(sizeof(float) * 2 * (size_t)p->channels, 256);
 }
 
+// Bytes of the outer-ReLU bit mask of (p): 0 when there is nothing to save (no residual / no outer ReLU) or when the
+// small-plane kernels serve this shape (they recompute).
+extern "C" size_t cpc_bn_mask_bytes(const cpc_bn_params* p) {
+    if (bn_validate(p) != CPC_OK || p->res_height == 0 || !p->outer_relu) return 0;
+    const int64_t hw = (int64_t)p->height * p->width;
+    if (hw < BN_SMALL_HW) return 0;
+    return sizeof(uint32_t) * (size_t)p->batch * p->channels * ((hw + 31) / 32);
+}
+
 static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                        const float* residual, float* out, void* packed_out, float* save_mean, float* save_rstd,
-                       const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+                       const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream, void* relu_mask = nullptr) {
     int st = bn_validate(p);
+    if (relu_mask && cpc_bn_mask_bytes(p) == 0) return CPC_ERR_UNSUPPORTED;
     if (st != CPC_OK) return st;
     if (!x || (!out && !packed_out) || !save_mean || !save_rstd) return CPC_ERR_NULL;
     if (!p->training && (!running_mean || !running_var)) return CPC_ERR_NULL;
@@ -599,7 +661,10 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
     } else if (small) {
         bn_small_apply_kernel<<<sgrid, BN_THREADS, 0, s>>>(x, affine, residual, out, g, FastDiv(g.HW));
     } else {
-        bn_apply_kernel<<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, g);
+        if (relu_mask)
+            bn_apply_kernel<true><<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, reinterpret_cast<uint32_t*>(relu_mask), g);
+        else
+            bn_apply_kernel<false><<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, nullptr, g);
     }
     CPC_LAUNCH_CHECK();
     count_launch(launches);
@@ -612,6 +677,15 @@ extern "C" int cpc_bn_relu_fwd(const float* x, const float* gamma, const float* 
     if (!out) return CPC_ERR_NULL;
     return bn_fwd_impl(x, gamma, beta, running_mean, running_var, residual, out, nullptr, save_mean, save_rstd, p, workspace,
                        workspace_bytes, stream);
+}
+
+extern "C" int cpc_bn_relu_fwd_mask(const float* x, const float* gamma, const float* beta, float* running_mean,
+                                    float* running_var, const float* residual, float* out, float* save_mean,
+                                    float* save_rstd, void* relu_mask, const cpc_bn_params* p, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    if (!out) return CPC_ERR_NULL;
+    return bn_fwd_impl(x, gamma, beta, running_mean, running_var, residual, out, nullptr, save_mean, save_rstd, p, workspace,
+                       workspace_bytes, stream, relu_mask);
 }
 
 extern "C" int cpc_bn_relu_fwd_packed(const float* x, const float* gamma, const float* beta, float* running_mean,
@@ -632,9 +706,11 @@ extern "C" size_t cpc_bn_packed_bytes(const cpc_bn_params* p) {
 static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, const float* beta, const float* save_mean,
                        const float* save_rstd, const float* residual, float* dx, void* packed_dx, float* dx_sum,
                        float* dgamma, float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+                       size_t workspace_bytes, void* stream, const void* relu_mask = nullptr) {
     int st = bn_validate(p);
     if (st != CPC_OK) return st;
+    if (relu_mask && cpc_bn_mask_bytes(p) == 0) return CPC_ERR_UNSUPPORTED;
+    const uint32_t* mask = reinterpret_cast<const uint32_t*>(relu_mask);
     if (!dout || !x || !save_mean || !save_rstd || (!dx && !packed_dx)) return CPC_ERR_NULL;
     if ((p->res_height > 0) != (residual != nullptr)) return CPC_ERR_NULL;
     if (d_residual && !residual) return CPC_ERR_NULL;
@@ -663,23 +739,27 @@ static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, co
                                                                FastDiv(g.HW));
     } else {
         const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
-        bn_bwd_reduce_kernel<<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g);
+        if (mask)
+            bn_bwd_reduce_kernel<true><<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, g);
+        else
+            bn_bwd_reduce_kernel<false><<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, g);
     }
     CPC_LAUNCH_CHECK();
     if (packed_dx) {
         const int Wp = (g.W + 7) & ~7;
         PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_dx), (long)g.B * g.C * g.H * Wp, Wp};
         const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, BN_PAIR_SEG));
-        bn_bwd_apply_packed_kernel<<<pgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, pk,
-                                                               dx_sum, dgamma, dbeta, d_residual, g, FastDiv(g.W / 2),
-                                                               (double)g.B * g.HW, p->training);
+        auto* kern = mask ? bn_bwd_apply_packed_kernel<true> : bn_bwd_apply_packed_kernel<false>;
+        kern<<<pgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, pk, dx_sum, dgamma,
+                                         dbeta, d_residual, g, FastDiv(g.W / 2), (double)g.B * g.HW, p->training);
     } else if (small) {
         bn_small_bwd_apply_kernel<<<sgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx,
                                                               dgamma, dbeta, d_residual, g, FastDiv(g.HW), (double)g.B * g.HW,
                                                               p->training);
     } else {
-        bn_bwd_apply_kernel<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx, dgamma,
-                                                       dbeta, d_residual, g, (double)g.B * g.HW, p->training);
+        auto* kern = mask ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
+        kern<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, dx, dgamma, dbeta,
+                                        d_residual, g, (double)g.B * g.HW, p->training);
     }
     CPC_LAUNCH_CHECK();
     count_launch(2);
@@ -702,4 +782,23 @@ extern "C" int cpc_bn_relu_bwd_packed(const float* dout, const float* x, const f
     if (!packed_dx) return CPC_ERR_NULL;
     return bn_bwd_impl(dout, x, gamma, beta, save_mean, save_rstd, residual, nullptr, packed_dx, dx_sum, dgamma, dbeta,
                        d_residual, p, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cpc_bn_relu_bwd_mask(const float* dout, const float* x, const float* gamma, const float* beta,
+                                    const float* save_mean, const float* save_rstd, const float* residual,
+                                    const void* relu_mask, float* dx, float* dgamma, float* dbeta, float* d_residual,
+                                    const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!dx) return CPC_ERR_NULL;
+    return bn_bwd_impl(dout, x, gamma, beta, save_mean, save_rstd, residual, dx, nullptr, nullptr, dgamma, dbeta, d_residual,
+                       p, workspace, workspace_bytes, stream, relu_mask);
+}
+
+extern "C" int cpc_bn_relu_bwd_packed_mask(const float* dout, const float* x, const float* gamma, const float* beta,
+                                           const float* save_mean, const float* save_rstd, const float* residual,
+                                           const void* relu_mask, void* packed_dx, float* dx_sum, float* dgamma,
+                                           float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+    if (!packed_dx) return CPC_ERR_NULL;
+    return bn_bwd_impl(dout, x, gamma, beta, save_mean, save_rstd, residual, nullptr, packed_dx, dx_sum, dgamma, dbeta,
+                       d_residual, p, workspace, workspace_bytes, stream, relu_mask);
 }

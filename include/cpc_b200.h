@@ -219,6 +219,26 @@ int cpc_bn_relu_bwd_packed(const float* dout, const float* x, const float* gamma
                            float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* Saved outer-ReLU mask: with a residual operand and outer_relu, the backward pass needs sign(v + residual).  The plain
+ * entry points recompute it (re-reading the residual in both backward kernels); the *_mask variants exchange it as one
+ * bit per element -- bit (i % 32) of word plane * ceil(H*W / 32) + i / 32, i the row-major index inside a (b, c) plane --
+ * written by the forward call and read by the backward ones (residual itself is then not read).  cpc_bn_mask_bytes is
+ * the buffer size, 0 when the shape has no such mask (no residual / no outer ReLU / planes served by the small-plane
+ * kernels): pass NULL then, which makes every *_mask call identical to its plain counterpart. */
+size_t cpc_bn_mask_bytes(const cpc_bn_params* p);
+int cpc_bn_relu_fwd_mask(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                         const float* residual, float* out, float* save_mean, float* save_rstd, void* relu_mask,
+                         const cpc_bn_params* p, void* workspace, size_t workspace_bytes, void* stream);
+int cpc_bn_relu_bwd_mask(const float* dout, const float* x, const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_rstd, const float* residual, const void* relu_mask, float* dx, float* dgamma,
+                         float* dbeta, float* d_residual, const cpc_bn_params* p, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int cpc_bn_relu_bwd_packed_mask(const float* dout, const float* x, const float* gamma, const float* beta,
+                                const float* save_mean, const float* save_rstd, const float* residual,
+                                const void* relu_mask, void* packed_dx, float* dx_sum, float* dgamma, float* dbeta,
+                                float* d_residual, const cpc_bn_params* p, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 2c. Non-overlapping max pooling (kernel = stride, no padding), forward and backward.
  *    Replaces nn.MaxPool2d on the residual branch (scalogram_model.py:434-441, ceil_mode=True) and the main-path

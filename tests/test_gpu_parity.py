@@ -554,6 +554,8 @@ def _bn_reference(x, bn, res, off, relu, outer_relu):
     ((2, 4, 5, 4200), (0, 0), (0, 0), True, False, True),       # more than one segment per plane
     ((3, 7, 6, 11), (1, 0), (1, 0), False, True, True),
     ((2, 5, 8, 33), (1, 1), (0, 1), True, True, False),        # eval(): running statistics
+    ((2, 3, 5, 4201), (1, 2), (1, 1), True, True, True),        # saved outer-ReLU bit mask, ragged last mask word
+    ((2, 4, 37, 130), (2, 0), (1, 0), False, True, False),      # mask, eval()
 ])
 def test_bn_relu_matches_torch_reference(cpc, shape, res_extra, off, relu, outer, train):
     g = torch.Generator().manual_seed(7)
@@ -588,6 +590,29 @@ def test_bn_relu_matches_torch_reference(cpc, shape, res_extra, off, relu, outer
     assert rel_err(our_bn.running_mean, ref_bn.running_mean) < 1e-5
     assert rel_err(our_bn.running_var, ref_bn.running_var) < 1e-5
     assert int(our_bn.num_batches_tracked) == int(ref_bn.num_batches_tracked)
+
+
+def test_bn_saved_relu_mask_equals_recomputed_mask(cpc):
+    """The bit mask the forward pass saves for the ReLU behind the residual add gives bit-identical gradients to
+    recomputing it from x and the residual (fp32 and packed backward, via the block-tail node)."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 6, 21, 250, generator=g)
+    res = torch.randn(2, 6, 23, 252, generator=g)
+    gy = torch.randn(2, 6, 21, 250, generator=g).to(DEV)
+    outs = []
+    for no_mask in (False, True):
+        cpc.ops.kernel_switches["CPC_NO_BN_MASK"] = no_mask
+        try:
+            bn = torch.nn.BatchNorm2d(6).to(DEV)
+            xo = x.to(DEV).requires_grad_(True)
+            ro = res.to(DEV).requires_grad_(True)
+            yo = cpc.ops.bn_relu(xo, bn, residual=ro, res_off=(1, 2), relu=True, outer_relu=True)
+            (yo * gy).sum().backward()
+            outs.append((yo.detach(), xo.grad, ro.grad, bn.weight.grad, bn.bias.grad))
+        finally:
+            cpc.ops.kernel_switches.pop("CPC_NO_BN_MASK", None)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -1154,6 +1179,7 @@ def test_e24_full_size_training_steps_match_reference_golden(cpc, graphed):
     # in, hidden/out channels, conv_b kernel, top padding, residual, input (H, W), outer relu
     dict(cin=32, cout=32, k2=(9, 1), top=8, residual=True, hw=(41, 77), outer=True),      # 32-channel row-streaming kernels
     dict(cin=32, cout=32, k2=(16, 1), top=None, residual=False, hw=(70, 141), outer=False),
+    dict(cin=32, cout=32, k2=(9, 1), top=8, residual=True, hw=(70, 141), outer=True),     # planes >= 2048: saved ReLU mask
     dict(cin=16, cout=128, k2=(6, 1), top=None, residual=True, hw=(30, 41), outer=True),  # 128-channel kernels
     dict(cin=32, cout=128, k2=(4, 1), top=3, residual=True, hw=(21, 133), outer=False),
     dict(cin=32, cout=32, k2=(9, 1), top=8, residual=True, hw=(41, 75), outer=True, node=False),   # odd width: unfused chain

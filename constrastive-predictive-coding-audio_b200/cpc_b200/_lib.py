@@ -105,6 +105,7 @@ SIGNATURES = {
     "cpc_bn_relu_bwd_packed_mask": (ctypes.c_int, [_P] * 13 + [ctypes.POINTER(BnParams), _P, ctypes.c_size_t, _P]),
     "cpc_maxpool_fwd": (ctypes.c_int, [_P, _P, ctypes.POINTER(PoolParams), _P]),
     "cpc_maxpool_bwd": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(PoolParams), _P]),
+    "cpc_maxpool_bwd_accumulate": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(PoolParams), _P]),
     "cpc_infonce_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(InfoNceParams), ctypes.c_int]),
     "cpc_infonce_fwd": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(InfoNceParams), _P, ctypes.c_size_t, _P]),
     "cpc_infonce_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(InfoNceParams), _P, ctypes.c_size_t, _P]),

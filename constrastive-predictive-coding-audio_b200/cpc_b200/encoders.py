@@ -49,8 +49,12 @@ class Conv1d(nn.Conv1d):
 class Conv2d(nn.Conv2d):
     """nn.Conv2d parameters, B200 kernel forward/backward; ``extra_top`` folds a preceding ZeroPad2d."""
 
+    def supported(self):
+        return not (self.groups != 1 or self.dilation != (1, 1) or self.padding_mode != 'zeros'
+                    or isinstance(self.padding, str))
+
     def forward(self, x, extra_top=0, relu=False):
-        if self.groups != 1 or self.dilation != (1, 1) or self.padding_mode != 'zeros' or isinstance(self.padding, str):
+        if not self.supported():
             raise NotImplementedError("cpc_b200.Conv2d supports groups=1, dilation=1, zero padding")
         return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, extra_top, relu)
 
@@ -58,12 +62,15 @@ class Conv2d(nn.Conv2d):
 class MaxPool2d(nn.MaxPool2d):
     """nn.MaxPool2d whose non-overlapping, unpadded square case (all the reference uses) runs on the B200 kernels."""
 
-    def forward(self, x):
+    def runs_on_kernels(self, x):
         k = self.kernel_size if isinstance(self.kernel_size, int) else None
         stride = self.stride if isinstance(self.stride, int) else None
-        if (k is not None and stride == k and self.padding == 0 and self.dilation == 1 and not self.return_indices
-                and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and not ops.second_order_enabled()):
-            return ops.max_pool2d(x, k, self.ceil_mode)
+        return (k is not None and stride == k and self.padding == 0 and self.dilation == 1 and not self.return_indices
+                and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and not ops.second_order_enabled())
+
+    def forward(self, x):
+        if self.runs_on_kernels(x):
+            return ops.max_pool2d(x, self.kernel_size, self.ceil_mode)
         return super().forward(x)
 
 
@@ -270,9 +277,13 @@ class ScalogramEncoderBlock(nn.Module):
         return any(isinstance(m, ActivationWriter) and m.register is not None for m in self.main_modules) or \
             self.output_activation_writer.register is not None
 
-    def _residual_branch(self, x, main_shape):
-        """Residual branch output and the crop origin that centre-aligns it with ``main`` (:456-470)."""
-        res = _run_modules(self.residual_modules, x)
+    def _residual_branch(self, x, main_shape, pooled=None):
+        """Residual branch output and the crop origin that centre-aligns it with ``main`` (:456-470).  ``pooled``: output
+        of the branch's leading MaxPool2d when the caller already has it (ops.conv2d_with_pool)."""
+        if pooled is None:
+            res = _run_modules(self.residual_modules, x)
+        else:
+            res = _run_modules(self.residual_modules[1:], pooled)
         m_h, m_w = main_shape
         o_h = int((res.shape[2] - m_h + 1) / 2)
         o_w = int((res.shape[3] - m_w + 1) / 2)
@@ -304,11 +315,19 @@ class ScalogramEncoderBlock(nn.Module):
         if len(stages) != 2:
             return None
         (top_a, conv_a, bn_a), (top_b, conv_b, bn_b) = stages
-        y_a = conv_a(x, extra_top=top_a)
+        pooled = None
+        pool = self.residual_modules[0] if self.residual and len(self.residual_modules) else None
+        if (isinstance(pool, MaxPool2d) and pool.runs_on_kernels(x) and type(conv_a) is Conv2d and conv_a.supported()
+                and x.requires_grad and torch.is_grad_enabled() and not ops.switch("CPC_NO_CONV_POOL_NODE")):
+            # x feeds conv_a and the residual pooling: one node, so that backward adds the two gradients of x in place
+            y_a, pooled = ops.conv2d_with_pool(x, conv_a.weight, conv_a.bias, conv_a.stride, conv_a.padding, top_a,
+                                               pool.kernel_size, pool.ceil_mode)
+        else:
+            y_a = conv_a(x, extra_top=top_a)
         if ops.block_tail_eligible(y_a, bn_a, conv_b, top_b, bn_b):
             # bn_a + ReLU + conv_b + bn_b (+ residual) + ReLU as one autograd node with packed intermediates
             oh = y_a.shape[2] + top_b + 2 * conv_b.padding[0] - conv_b.weight.shape[2] + 1
-            res, off = (self._residual_branch(x, (oh, y_a.shape[3])) if self.residual else (None, (0, 0)))
+            res, off = (self._residual_branch(x, (oh, y_a.shape[3]), pooled) if self.residual else (None, (0, 0)))
             return ops.block_tail(y_a, bn_a, conv_b, top_b, bn_b, residual=res, res_off=off, outer_relu=outer_relu)
         h = x
         for idx, (top, conv, bn) in enumerate(stages):
@@ -318,7 +337,7 @@ class ScalogramEncoderBlock(nn.Module):
                 if idx == 1 and outer_relu:
                     h = F.relu(h)
             else:
-                res, off = self._residual_branch(x, (h.shape[2], h.shape[3]))
+                res, off = self._residual_branch(x, (h.shape[2], h.shape[3]), pooled)
                 h = ops.bn_relu(h, bn, residual=res, res_off=off, relu=True, outer_relu=outer_relu)
         return h
 

@@ -73,6 +73,9 @@ def _switch(name):
     return os.environ.get(name) == "1"
 
 
+switch = _switch
+
+
 def _conv_flags():
     flags = 0
     for name, bit in _CONV_SWITCHES:
@@ -212,85 +215,146 @@ def _pack_operand(lib, t, p, operand):
 class _ConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad_top, pad_left, out_hw, relu, precision):
-        _require_cuda(x, weight, bias)
-        lib = _lib.load()
-        x = x.contiguous()
-        w = weight.contiguous()
-        if x.dtype != torch.float32 or w.dtype != torch.float32:
-            raise _lib.CpcError("conv expects fp32 tensors (precision is a kernel-internal setting)")
-        p = _conv_params(tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, relu, precision)
-        y = torch.empty((x.shape[0], w.shape[0], out_hw[0], out_hw[1]), dtype=torch.float32, device=x.device)
-        ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 0), x.device)
-        with torch.cuda.device(x.device):
-            # the packed copy of x serves the forward pass now and the weight gradient later
-            keep = ctx.needs_input_grad[1]                      # (torch.is_grad_enabled() is always False in here)
-            packed_x = _pack_operand(lib, x, p, 0) if keep else None
-            _call(_conv_key("cpc_conv_fwd", p), _conv_flops(p), lib.cpc_conv_fwd_ex, _ptr(x), _ptr(w),
-                  _ptr(bias.contiguous() if bias is not None else None), _ptr(y), ctypes.byref(p), _ptr(packed_x),
-                  _ptr(ws), ws.numel() if ws is not None else 0, _stream())
-        ctx.params = (tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, precision)
-        ctx.has_bias = bias is not None
-        ctx.relu = relu
-        ctx.save_for_backward(x, w, y if relu else None, packed_x)
+        y, saved = _conv_forward(ctx, x, weight, bias, stride, pad_top, pad_left, out_hw, relu, precision)
+        ctx.save_for_backward(*saved)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y, packed_x = ctx.saved_tensors
+        return _conv_backward(ctx, ctx.saved_tensors, dy) + (None,) * 6
+
+
+class _ConvPoolFunction(torch.autograd.Function):
+    """(conv2d(x), max_pool2d(x)) as ONE node for an input that feeds both (the first conv and the pooled residual branch
+    of a ScalogramEncoderBlock, scalogram_model.py:446-450).  Forward is the two plain kernels; backward lets the conv's
+    data gradient write dx and the pooling add its share in place (cpc_maxpool_bwd_accumulate) instead of a zero-filled
+    pooling gradient plus autograd's add pass over the block input."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad_top, pad_left, out_hw, relu, precision, kernel, ceil_mode):
+        y, saved = _conv_forward(ctx, x, weight, bias, stride, pad_top, pad_left, out_hw, relu, precision)
         lib = _lib.load()
-        x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = ctx.params
-        if ctx.relu:
-            dy = dy * (y > 0).to(dy.dtype)
-        dy = dy.contiguous()
-        if torch.is_grad_enabled():
-            # backward under create_graph=True: record dgrad / wgrad as differentiable nodes
-            geom = (x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision)
-            dx = _ConvDgradFunction.apply(dy, w, geom) if ctx.needs_input_grad[0] else None
-            dw = _ConvWgradFunction.apply(x, dy, geom) if ctx.needs_input_grad[1] else None
-            db = dy.sum(dim=(0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-            return dx, dw, db, None, None, None, None, None, None
-        p = _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, False, precision)
+        x = saved[0]
+        p = _pool_params(tuple(x.shape), kernel, ceil_mode)
+        if p.h_out <= 0 or p.w_out <= 0:
+            raise ValueError("max_pool2d output would be empty for input %s, kernel %d" % (tuple(x.shape), kernel))
+        pooled = torch.empty((p.batch, p.channels, p.h_out, p.w_out), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _call("cpc_maxpool_fwd b%d %dx%dx%d k%d" % (p.batch, p.channels, p.h_in, p.w_in, kernel), 0.0,
+                  lib.cpc_maxpool_fwd, _ptr(x), _ptr(pooled), ctypes.byref(p), _stream(),
+                  nbytes=4.0 * (x.numel() + pooled.numel()))
+        ctx.pool = (kernel, ceil_mode)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(*saved)
+        return y, pooled
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, d_pooled):
+        saved = ctx.saved_tensors
+        x = saved[0]
+        kernel, ceil_mode = ctx.pool
+        lib = _lib.load()
         dx = dw = db = None
-        need_dx = ctx.needs_input_grad[0]
-        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
-        with torch.cuda.device(dy.device):
-            packed_dy = None
-            if need_dw:
-                nbytes = lib.cpc_conv_packed_bytes(ctypes.byref(p), 1)
-                if nbytes and ctx.has_bias:
-                    # the packing pass over dy also reduces the bias gradient (dy is read once for both)
-                    packed_dy = torch.empty(int(nbytes), dtype=torch.uint8, device=dy.device)
-                    db = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device)
-                    _call("cpc_conv_pack dy", 0.0, lib.cpc_conv_pack_dy, _ptr(dy), _ptr(packed_dy), _ptr(db), ctypes.byref(p),
-                          _stream(), nbytes=4.0 * dy.numel() + float(nbytes))
+        if dy is not None:
+            dx, dw, db = _conv_backward(ctx, saved, dy)
+        if d_pooled is not None and ctx.needs_input_grad[0]:
+            p = _pool_params(tuple(x.shape), kernel, ceil_mode)
+            d_pooled = d_pooled.contiguous()
+            with torch.cuda.device(x.device):
+                if dx is None:
+                    dx = torch.empty_like(x)
+                    _call("cpc_maxpool_bwd b%d %dx%dx%d k%d" % (p.batch, p.channels, p.h_in, p.w_in, kernel), 0.0,
+                          lib.cpc_maxpool_bwd, _ptr(x), _ptr(d_pooled), _ptr(dx), ctypes.byref(p), _stream(),
+                          nbytes=4.0 * (2 * x.numel() + d_pooled.numel()))
                 else:
-                    packed_dy = _pack_operand(lib, dy, p, 1)
-            # data and weight gradient are independent: when both are small (neither fills the 148 SMs for long) the weight
-            # gradient runs on a side stream next to the data gradient (fork / join inside this call, so every buffer
-            # the side stream touches outlives the join; under graph capture the fork becomes a parallel branch)
-            side = None
-            if need_dx and need_dw and _profiler is None and _conv_flops(p) < _OVERLAP_MAX_FLOPS and not _switch("CPC_NO_BWD_OVERLAP"):
-                side = _side_stream(dy.device)
-                side.wait_stream(torch.cuda.current_stream(dy.device))
-            ws_d = ws_w = None
-            if need_dx:
-                dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
-                ws_d = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
-                _call(_conv_key("cpc_conv_dgrad", p), _conv_flops(p), lib.cpc_conv_dgrad_ex, _ptr(dy), _ptr(w), _ptr(dx),
-                      ctypes.byref(p), _ptr(packed_dy), _ptr(ws_d), ws_d.numel() if ws_d is not None else 0, _stream())
-            if need_dw:
-                dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
-                db_here = None                                   # bias gradient still to be computed by the wgrad call
-                if ctx.has_bias and db is None:
-                    db = db_here = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device)
-                ws_w = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
-                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                    _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad_ex, _ptr(x), _ptr(dy), _ptr(dw),
-                          _ptr(db_here), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws_w),
-                          ws_w.numel() if ws_w is not None else 0, _stream())
-            if side is not None:
-                torch.cuda.current_stream(dy.device).wait_stream(side)
-        return dx, dw, db, None, None, None, None, None, None
+                    _call("cpc_maxpool_bwd b%d %dx%dx%d k%d +=" % (p.batch, p.channels, p.h_in, p.w_in, kernel), 0.0,
+                          lib.cpc_maxpool_bwd_accumulate, _ptr(x), _ptr(d_pooled), _ptr(dx), ctypes.byref(p), _stream(),
+                          nbytes=4.0 * (3 * x.numel() + d_pooled.numel()))
+        return (dx, dw, db) + (None,) * 8
+
+
+def _conv_forward(ctx, x, weight, bias, stride, pad_top, pad_left, out_hw, relu, precision):
+    """Body of the conv nodes' forward: returns y and the tensors to save."""
+    _require_cuda(x, weight, bias)
+    lib = _lib.load()
+    x = x.contiguous()
+    w = weight.contiguous()
+    if x.dtype != torch.float32 or w.dtype != torch.float32:
+        raise _lib.CpcError("conv expects fp32 tensors (precision is a kernel-internal setting)")
+    p = _conv_params(tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, relu, precision)
+    y = torch.empty((x.shape[0], w.shape[0], out_hw[0], out_hw[1]), dtype=torch.float32, device=x.device)
+    ws = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 0), x.device)
+    with torch.cuda.device(x.device):
+        # the packed copy of x serves the forward pass now and the weight gradient later
+        keep = ctx.needs_input_grad[1]                      # (torch.is_grad_enabled() is always False in here)
+        packed_x = _pack_operand(lib, x, p, 0) if keep else None
+        _call(_conv_key("cpc_conv_fwd", p), _conv_flops(p), lib.cpc_conv_fwd_ex, _ptr(x), _ptr(w),
+              _ptr(bias.contiguous() if bias is not None else None), _ptr(y), ctypes.byref(p), _ptr(packed_x),
+              _ptr(ws), ws.numel() if ws is not None else 0, _stream())
+    ctx.params = (tuple(x.shape), tuple(w.shape), stride, pad_top, pad_left, out_hw, precision)
+    ctx.has_bias = bias is not None
+    ctx.relu = relu
+    return y, (x, w, y if relu else None, packed_x)
+
+
+def _conv_backward(ctx, saved, dy):
+    """Body of the conv nodes' backward: (dx, dw, db)."""
+    x, w, y, packed_x = saved
+    lib = _lib.load()
+    x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = ctx.params
+    if ctx.relu:
+        dy = dy * (y > 0).to(dy.dtype)
+    dy = dy.contiguous()
+    if torch.is_grad_enabled():
+        # backward under create_graph=True: record dgrad / wgrad as differentiable nodes
+        geom = (x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision)
+        dx = _ConvDgradFunction.apply(dy, w, geom) if ctx.needs_input_grad[0] else None
+        dw = _ConvWgradFunction.apply(x, dy, geom) if ctx.needs_input_grad[1] else None
+        db = dy.sum(dim=(0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+    p = _conv_params(x_shape, w_shape, stride, pad_top, pad_left, out_hw, False, precision)
+    dx = dw = db = None
+    need_dx = ctx.needs_input_grad[0]
+    need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+    with torch.cuda.device(dy.device):
+        packed_dy = None
+        if need_dw:
+            nbytes = lib.cpc_conv_packed_bytes(ctypes.byref(p), 1)
+            if nbytes and ctx.has_bias:
+                # the packing pass over dy also reduces the bias gradient (dy is read once for both)
+                packed_dy = torch.empty(int(nbytes), dtype=torch.uint8, device=dy.device)
+                db = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device)
+                _call("cpc_conv_pack dy", 0.0, lib.cpc_conv_pack_dy, _ptr(dy), _ptr(packed_dy), _ptr(db), ctypes.byref(p),
+                      _stream(), nbytes=4.0 * dy.numel() + float(nbytes))
+            else:
+                packed_dy = _pack_operand(lib, dy, p, 1)
+        # data and weight gradient are independent: when both are small (neither fills the 148 SMs for long) the weight
+        # gradient runs on a side stream next to the data gradient (fork / join inside this call, so every buffer
+        # the side stream touches outlives the join; under graph capture the fork becomes a parallel branch)
+        side = None
+        if need_dx and need_dw and _profiler is None and _conv_flops(p) < _OVERLAP_MAX_FLOPS and not _switch("CPC_NO_BWD_OVERLAP"):
+            side = _side_stream(dy.device)
+            side.wait_stream(torch.cuda.current_stream(dy.device))
+        ws_d = ws_w = None
+        if need_dx:
+            dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
+            ws_d = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1), dy.device)
+            _call(_conv_key("cpc_conv_dgrad", p), _conv_flops(p), lib.cpc_conv_dgrad_ex, _ptr(dy), _ptr(w), _ptr(dx),
+                  ctypes.byref(p), _ptr(packed_dy), _ptr(ws_d), ws_d.numel() if ws_d is not None else 0, _stream())
+        if need_dw:
+            dw = torch.empty(w_shape, dtype=torch.float32, device=dy.device)
+            db_here = None                                   # bias gradient still to be computed by the wgrad call
+            if ctx.has_bias and db is None:
+                db = db_here = torch.empty(w_shape[0], dtype=torch.float32, device=dy.device)
+            ws_w = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2), dy.device)
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                _call(_conv_key("cpc_conv_wgrad", p), _conv_flops(p), lib.cpc_conv_wgrad_ex, _ptr(x), _ptr(dy), _ptr(dw),
+                      _ptr(db_here), ctypes.byref(p), _ptr(packed_x), _ptr(packed_dy), _ptr(ws_w),
+                      ws_w.numel() if ws_w is not None else 0, _stream())
+        if side is not None:
+            torch.cuda.current_stream(dy.device).wait_stream(side)
+    return dx, dw, db
 
 
 class _ConvDgradFunction(torch.autograd.Function):
@@ -373,6 +437,25 @@ def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), extra_top=0, rel
         raise ValueError("conv output would be empty: input %s kernel %s" % (tuple(x.shape), (kh, kw)))
     return _ConvFunction.apply(x, weight, bias, tuple(stride), extra_top + padding[0], padding[1], (oh, ow), relu,
                                precision or _default_precision)
+
+
+def conv2d_with_pool(x, weight, bias, stride, padding, extra_top, pool_kernel, pool_ceil_mode, precision=None):
+    """``(conv2d(x, ...), max_pool2d(x, pool_kernel, ceil_mode))`` for an input both operators read; same values as the
+    two separate calls, one autograd node whose backward needs no add pass over ``x`` (see _ConvPoolFunction)."""
+    if isinstance(stride, int):
+        stride = (stride, stride)
+    if isinstance(padding, int):
+        padding = (padding, padding)
+    b, c, h, w_in = x.shape
+    co, ci, kh, kw = weight.shape
+    if ci != c:
+        raise ValueError("channel mismatch: input has %d channels, weight expects %d" % (c, ci))
+    oh = (h + extra_top + 2 * padding[0] - kh) // stride[0] + 1
+    ow = (w_in + 2 * padding[1] - kw) // stride[1] + 1
+    if oh <= 0 or ow <= 0:
+        raise ValueError("conv output would be empty: input %s kernel %s" % (tuple(x.shape), (kh, kw)))
+    return _ConvPoolFunction.apply(x, weight, bias, tuple(stride), extra_top + padding[0], padding[1], (oh, ow), False,
+                                   precision or _default_precision, int(pool_kernel), bool(pool_ceil_mode))
 
 
 def conv1d(x, weight, bias=None, stride=1, padding=0, relu=False, precision=None):

@@ -36,6 +36,17 @@ static BnGeom bn_geom(const cpc_bn_params* p) {
     return g;
 }
 
+// Threads per block of the plane-per-block streaming kernels (a block owns threads * BN_PER_THREAD consecutive
+// elements): the plane is cut into as few blocks as 256 threads allow and the block is then shrunk to fit its share, so
+// that no block runs mostly empty -- a 34 x 156 plane is 2 x 192 threads (86 % of the slots loaded) instead of one
+// full and one 30 % full 256-thread block.
+static int bn_block_threads(int HW) {
+    const int nseg = ceil_div(HW, BN_SEG);
+    const int per = ceil_div(HW, nseg);
+    const int t = (ceil_div(per, BN_PER_THREAD) + 31) & ~31;
+    return t < 32 ? 32 : (t > BN_THREADS ? BN_THREADS : t);
+}
+
 static int bn_validate(const cpc_bn_params* p) {
     if (!p) return CPC_ERR_NULL;
     if (p->batch <= 0 || p->channels <= 0 || p->height <= 0 || p->width <= 0) return CPC_ERR_BAD_SHAPE;
@@ -59,7 +70,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     __syncthreads();
     double r = 0.0;
     if (threadIdx.x < 32) {
-        r = threadIdx.x < (BN_THREADS / 32) ? red[threadIdx.x] : 0.0;
+        r = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
     }
@@ -80,12 +91,12 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __res
     const float* px = x + (size_t)plane * HW;
     float s = 0.f, q = 0.f;
     for (int seg = 0; seg < BN_RED_SEGS; ++seg) {
-        const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * BN_SEG + threadIdx.x;
+        const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * (int)blockDim.x * BN_PER_THREAD + threadIdx.x;
         if (i0 - (int)threadIdx.x >= HW) break;
         float v[BN_PER_THREAD];
 #pragma unroll
         for (int u = 0; u < BN_PER_THREAD; ++u) {
-            const int i = i0 + u * BN_THREADS;
+            const int i = i0 + u * (int)blockDim.x;
             v[u] = i < HW ? __ldg(px + i) : 0.f;
         }
 #pragma unroll
@@ -145,11 +156,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
     uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
 #pragma unroll 1
     for (int half = 0; half < BN_PER_THREAD / BATCH; ++half) {
-        const int i0 = blockIdx.y * BN_SEG + half * BATCH * BN_THREADS + threadIdx.x;
+        const int i0 = (blockIdx.y * BN_PER_THREAD + half * BATCH) * (int)blockDim.x + threadIdx.x;
         float xv[BATCH], rv[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
-            const int i = i0 + u * BN_THREADS;
+            const int i = i0 + u * (int)blockDim.x;
             xv[u] = i < g.HW ? __ldg(px + i) : 0.f;
             rv[u] = 0.f;
             if (pr && i < g.HW) {
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
         }
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
-            const int i = i0 + u * BN_THREADS;
+            const int i = i0 + u * (int)blockDim.x;
             float v = fmaf(xv[u], sc, sh);
             if (g.relu) v = fmaxf(v, 0.f);
             if (pr) {
@@ -211,13 +222,13 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
     float s = 0.f, q = 0.f;
     for (int seg = 0; seg < BN_RED_SEGS; ++seg) {
-        const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * BN_SEG + threadIdx.x;
+        const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * (int)blockDim.x * BN_PER_THREAD + threadIdx.x;
         if (i0 - (int)threadIdx.x >= g.HW) break;
         float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[MASK ? 1 : BN_PER_THREAD];
         uint32_t ob = 0;                                             // MASK: bit u = saved outer-ReLU bit of element u
 #pragma unroll
         for (int u = 0; u < BN_PER_THREAD; ++u) {
-            const int i = i0 + u * BN_THREADS;
+            const int i = i0 + u * (int)blockDim.x;
             const bool in = i < g.HW;
             xv[u] = in ? __ldg(px + i) : 0.f;
             dv[u] = in ? __ldg(pd + i) : 0.f;
@@ -234,7 +245,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
         }
 #pragma unroll
         for (int u = 0; u < BN_PER_THREAD; ++u) {
-            const int i = i0 + u * BN_THREADS;
+            const int i = i0 + u * (int)blockDim.x;
             if (i < g.HW) {
                 float xhat, g1;
                 const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, MASK ? 0.f : rv[MASK ? 0 : u], g,
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     const size_t roff = (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row;
     const float* pr = res ? res + roff : nullptr;
     float* pdr = d_res ? d_res + roff : nullptr;
-    const int i0 = blockIdx.y * BN_SEG + threadIdx.x;
+    const int i0 = blockIdx.y * (int)blockDim.x * BN_PER_THREAD + threadIdx.x;
     float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[MASK ? 1 : BN_PER_THREAD];
     int ro[MASK ? 1 : BN_PER_THREAD];                                // offset inside the residual plane (MASK: recomputed)
     uint32_t ob = 0;                                                 // MASK: bit u = saved outer-ReLU bit of element u
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * BN_THREADS;
+        const int i = i0 + u * (int)blockDim.x;
         const bool in = i < g.HW;
         xv[u] = in ? __ldg(px + i) : 0.f;
         dv[u] = in ? __ldg(pd + i) : 0.f;
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     }
 #pragma unroll
     for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * BN_THREADS;
+        const int i = i0 + u * (int)blockDim.x;
         if (i < g.HW) {
             float xhat, g1;
             const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, MASK ? 0.f : rv[MASK ? 0 : u], g, xhat,
@@ -464,7 +475,6 @@ struct PackedOut {
     int Wp;
 };
 constexpr int BN_PAIRS = BN_PER_THREAD / 2;
-constexpr int BN_PAIR_SEG = BN_THREADS * BN_PAIRS;               // pairs per block
 
 __device__ __forceinline__ void packed_store2(const PackedOut& po, const BnGeom& g, int plane, int h, int w, float a, float b) {
     __nv_bfloat16* q = po.base + ((long)plane * g.H + h) * po.Wp + w;
@@ -489,16 +499,16 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_packed_kernel(const float
     const float sc = __ldg(affine + 2 * c), sh = __ldg(affine + 2 * c + 1);
     const float2* px = reinterpret_cast<const float2*>(x + (size_t)plane * g.HW);
     const int n_pairs = g.HW >> 1;
-    const int j0 = blockIdx.y * BN_PAIR_SEG + threadIdx.x;
+    const int j0 = blockIdx.y * (int)blockDim.x * BN_PAIRS + threadIdx.x;
     float2 xv[BN_PAIRS];
 #pragma unroll
     for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * BN_THREADS;
+        const int j = j0 + u * (int)blockDim.x;
         xv[u] = j < n_pairs ? __ldg(px + j) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * BN_THREADS;
+        const int j = j0 + u * (int)blockDim.x;
         if (j < n_pairs) {
             float a = fmaf(xv[u].x, sc, sh), b = fmaf(xv[u].y, sc, sh);
             if (g.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
@@ -534,7 +544,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
     const float* pr = res ? res + roff : nullptr;
     float* pdr = d_res ? d_res + roff : nullptr;
     const int n_pairs = g.HW >> 1;
-    const int j0 = blockIdx.y * BN_PAIR_SEG + threadIdx.x;
+    const int j0 = blockIdx.y * (int)blockDim.x * BN_PAIRS + threadIdx.x;
     float2 xv[BN_PAIRS], dv[BN_PAIRS], rv[MASK ? 1 : BN_PAIRS];
     int hh[BN_PAIRS], ww[BN_PAIRS];
     uint32_t ob = 0;                                                 // MASK: bits 2u, 2u + 1 = saved bits of pair u
@@ -542,7 +552,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
     const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
 #pragma unroll
     for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * BN_THREADS;
+        const int j = j0 + u * (int)blockDim.x;
         const bool in = j < n_pairs;
         xv[u] = in ? __ldg(px + j) : make_float2(0.f, 0.f);
         dv[u] = in ? __ldg(pd + j) : make_float2(0.f, 0.f);
@@ -564,7 +574,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
     float total = 0.f;
 #pragma unroll
     for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * BN_THREADS;
+        const int j = j0 + u * (int)blockDim.x;
         if (j < n_pairs) {
             float xh0, xh1, g10, g11;
             const float2 r2 = MASK ? make_float2(0.f, 0.f) : rv[MASK ? 0 : u];
@@ -589,7 +599,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = total;
         __syncthreads();
         if (threadIdx.x < 32) {
-            float v = threadIdx.x < BN_THREADS / 32 ? red[threadIdx.x] : 0.f;
+            float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
             v = warp_sum(v);
             if (threadIdx.x == 0) atomicAdd(dx_sum + c, v);
         }
@@ -635,7 +645,8 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
     BnGeom g = bn_geom(p);
     double* sums = reinterpret_cast<double*>(workspace);
     float* affine = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(sizeof(double) * 2 * (size_t)g.C, 256));
-    const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
+    const int nt = bn_block_threads(g.HW);
+    const dim3 grid(g.B * g.C, ceil_div(g.HW, nt * BN_PER_THREAD));
     int launches = 2;
     const bool small = g.HW < BN_SMALL_HW && !packed_out && (int64_t)g.B * g.HW < 65535ll * BN_SMALL_CHUNK;
     const dim3 sgrid(g.C, ceil_div(g.B * g.HW, BN_SMALL_CHUNK));
@@ -644,8 +655,8 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
         if (small) {
             bn_small_stats_kernel<<<sgrid, BN_THREADS, 0, s>>>(x, sums, g, FastDiv(g.HW));
         } else {
-            const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
-            bn_stats_kernel<<<rgrid, BN_THREADS, 0, s>>>(x, sums, g.C, g.HW);
+            const dim3 rgrid(g.B * g.C, ceil_div(g.HW, nt * BN_PER_THREAD * BN_RED_SEGS));
+            bn_stats_kernel<<<rgrid, nt, 0, s>>>(x, sums, g.C, g.HW);
         }
         CPC_LAUNCH_CHECK();
         ++launches;
@@ -656,15 +667,15 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
     if (packed_out) {
         const int Wp = (g.W + 7) & ~7;
         PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_out), (long)g.B * g.C * g.H * Wp, Wp};
-        const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, BN_PAIR_SEG));
-        bn_apply_packed_kernel<<<pgrid, BN_THREADS, 0, s>>>(x, affine, pk, g, FastDiv(g.W / 2));
+        const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, nt * BN_PAIRS));
+        bn_apply_packed_kernel<<<pgrid, nt, 0, s>>>(x, affine, pk, g, FastDiv(g.W / 2));
     } else if (small) {
         bn_small_apply_kernel<<<sgrid, BN_THREADS, 0, s>>>(x, affine, residual, out, g, FastDiv(g.HW));
     } else {
         if (relu_mask)
-            bn_apply_kernel<true><<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, reinterpret_cast<uint32_t*>(relu_mask), g);
+            bn_apply_kernel<true><<<grid, nt, 0, s>>>(x, affine, residual, out, reinterpret_cast<uint32_t*>(relu_mask), g);
         else
-            bn_apply_kernel<false><<<grid, BN_THREADS, 0, s>>>(x, affine, residual, out, nullptr, g);
+            bn_apply_kernel<false><<<grid, nt, 0, s>>>(x, affine, residual, out, nullptr, g);
     }
     CPC_LAUNCH_CHECK();
     count_launch(launches);
@@ -731,26 +742,27 @@ static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, co
     if (d_residual && crop &&
         cudaMemsetAsync(d_residual, 0, sizeof(float) * (size_t)g.B * g.C * g.RH * g.RW, s) != cudaSuccess)
         return CPC_ERR_CUDA;
-    const dim3 grid(g.B * g.C, ceil_div(g.HW, BN_SEG));
+    const int nt = bn_block_threads(g.HW);
+    const dim3 grid(g.B * g.C, ceil_div(g.HW, nt * BN_PER_THREAD));
     const bool small = g.HW < BN_SMALL_HW && !packed_dx && (int64_t)g.B * g.HW < 65535ll * BN_SMALL_CHUNK;
     const dim3 sgrid(g.C, ceil_div(g.B * g.HW, BN_SMALL_CHUNK));
     if (small) {
         bn_small_bwd_reduce_kernel<<<sgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, g,
                                                                FastDiv(g.HW));
     } else {
-        const dim3 rgrid(g.B * g.C, ceil_div(g.HW, BN_SEG * BN_RED_SEGS));
+        const dim3 rgrid(g.B * g.C, ceil_div(g.HW, nt * BN_PER_THREAD * BN_RED_SEGS));
         if (mask)
-            bn_bwd_reduce_kernel<true><<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, g);
+            bn_bwd_reduce_kernel<true><<<rgrid, nt, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, g);
         else
-            bn_bwd_reduce_kernel<false><<<rgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, g);
+            bn_bwd_reduce_kernel<false><<<rgrid, nt, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, g);
     }
     CPC_LAUNCH_CHECK();
     if (packed_dx) {
         const int Wp = (g.W + 7) & ~7;
         PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_dx), (long)g.B * g.C * g.H * Wp, Wp};
-        const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, BN_PAIR_SEG));
+        const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, nt * BN_PAIRS));
         auto* kern = mask ? bn_bwd_apply_packed_kernel<true> : bn_bwd_apply_packed_kernel<false>;
-        kern<<<pgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, pk, dx_sum, dgamma,
+        kern<<<pgrid, nt, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, pk, dx_sum, dgamma,
                                          dbeta, d_residual, g, FastDiv(g.W / 2), (double)g.B * g.HW, p->training);
     } else if (small) {
         bn_small_bwd_apply_kernel<<<sgrid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, sums2, dx,
@@ -758,7 +770,7 @@ static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, co
                                                               p->training);
     } else {
         auto* kern = mask ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
-        kern<<<grid, BN_THREADS, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, dx, dgamma, dbeta,
+        kern<<<grid, nt, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, dx, dgamma, dbeta,
                                         d_residual, g, (double)g.B * g.HW, p->training);
     }
     CPC_LAUNCH_CHECK();

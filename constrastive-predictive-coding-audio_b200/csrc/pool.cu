@@ -140,6 +140,75 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restri
     }
 }
 
+// dx += max-pool gradient (dx already holds another branch's gradient of the same tensor): the window's dx pairs travel
+// with its x pairs (all loads of a thread issued up front), the arg-max element is incremented and the pairs are
+// written back -- no zero fill, no separate add pass over the tensor.
+__global__ void __launch_bounds__(256) maxpool2_bwd_acc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              float* __restrict__ dx, PoolGeom g) {
+    const int plane = blockIdx.x;
+    const float* px = x + (size_t)plane * g.H * g.W;
+    float* pdx = dx + (size_t)plane * g.H * g.W;
+    const float* pdy = dy + (size_t)plane * g.OH * g.OW;
+    const int n = g.OH * g.OW;
+    const int i0 = blockIdx.y * (256 * POOL2_PER_THREAD) + threadIdx.x;
+    float2 r0[POOL2_PER_THREAD], r1[POOL2_PER_THREAD], d0[POOL2_PER_THREAD], d1[POOL2_PER_THREAD];
+    float gv[POOL2_PER_THREAD];
+    int off[POOL2_PER_THREAD];
+    bool two[POOL2_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < POOL2_PER_THREAD; ++u) {
+        const int idx = i0 + u * 256;
+        r0[u] = make_float2(0.f, 0.f); r1[u] = r0[u]; d0[u] = r0[u]; d1[u] = r0[u]; two[u] = false; off[u] = -1; gv[u] = 0.f;
+        if (idx < n) {
+            int oh, ow;
+            g.d_ow.divmod(idx, oh, ow);
+            off[u] = (2 * oh) * g.W + 2 * ow;
+            r0[u] = __ldg(reinterpret_cast<const float2*>(px + off[u]));
+            d0[u] = *reinterpret_cast<const float2*>(pdx + off[u]);
+            two[u] = 2 * oh + 1 < g.H;
+            if (two[u]) {
+                r1[u] = __ldg(reinterpret_cast<const float2*>(px + off[u] + g.W));
+                d1[u] = *reinterpret_cast<const float2*>(pdx + off[u] + g.W);
+            }
+            gv[u] = __ldg(pdy + idx);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < POOL2_PER_THREAD; ++u) {
+        if (off[u] >= 0) {
+            float m; int arg;
+            pool2_argmax(r0[u], r1[u], two[u], m, arg);
+            if (arg < 2) {
+                if (arg == 0) d0[u].x += gv[u]; else d0[u].y += gv[u];
+                *reinterpret_cast<float2*>(pdx + off[u]) = d0[u];
+            } else {
+                if (arg == 2) d1[u].x += gv[u]; else d1[u].y += gv[u];
+                *reinterpret_cast<float2*>(pdx + off[u] + g.W) = d1[u];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_acc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             float* __restrict__ dx, PoolGeom g) {
+    const int plane = blockIdx.x;
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= g.OH * g.OW) return;
+    int oh, ow;
+    g.d_ow.divmod(idx, oh, ow);
+    const float* px = x + (size_t)plane * g.H * g.W;
+    const int h0 = oh * g.k, w0 = ow * g.k;
+    const int h1 = min(h0 + g.k, g.H), w1 = min(w0 + g.k, g.W);
+    float m = -INFINITY;
+    int ah = h0, aw = w0;
+    for (int h = h0; h < h1; ++h)
+        for (int w = w0; w < w1; ++w) {
+            const float v = __ldg(px + (size_t)h * g.W + w);
+            if (v > m || v != v) { m = v; ah = h; aw = w; }
+        }
+    dx[(size_t)plane * g.H * g.W + (size_t)ah * g.W + aw] += __ldg(dy + (size_t)plane * g.OH * g.OW + idx);
+}
+
 // the 2 x 2 fast path needs every window row to be one aligned 8-byte pair
 static bool pool2_ok(const cpc_pool_params* p, const void* a, const void* b) {
     return p->kernel == 2 && p->w_in % 2 == 0 && p->w_out * 2 == p->w_in &&
@@ -199,6 +268,23 @@ extern "C" int cpc_maxpool_bwd(const float* x, const float* dy, float* dx, const
         maxpool2_bwd_kernel<<<dim3(planes, ceil_div(g.OH * g.OW, 256 * POOL2_PER_THREAD)), 256, 0, s>>>(x, dy, dx, g);
     else
         maxpool_bwd_kernel<<<dim3(planes, ceil_div(g.OH * g.OW, 256)), 256, 0, s>>>(x, dy, dx, g);
+    CPC_LAUNCH_CHECK();
+    count_launch();
+    return CPC_OK;
+}
+
+extern "C" int cpc_maxpool_bwd_accumulate(const float* x, const float* dy, float* dx, const cpc_pool_params* p, void* stream) {
+    int st = pool_validate(p);
+    if (st != CPC_OK) return st;
+    if (!x || !dy || !dx) return CPC_ERR_NULL;
+    if ((st = check_device()) != CPC_OK) return st;
+    PoolGeom g = pool_geom(p);
+    const int planes = p->batch * p->channels;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pool2_ok(p, x, dx))
+        maxpool2_bwd_acc_kernel<<<dim3(planes, ceil_div(g.OH * g.OW, 256 * POOL2_PER_THREAD)), 256, 0, s>>>(x, dy, dx, g);
+    else
+        maxpool_bwd_acc_kernel<<<dim3(planes, ceil_div(g.OH * g.OW, 256)), 256, 0, s>>>(x, dy, dx, g);
     CPC_LAUNCH_CHECK();
     count_launch();
     return CPC_OK;

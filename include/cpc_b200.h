@@ -254,6 +254,10 @@ typedef struct cpc_pool_params {
 
 int cpc_maxpool_fwd(const float* x, float* y, const cpc_pool_params* p, void* stream);
 int cpc_maxpool_bwd(const float* x, const float* dy, float* dx, const cpc_pool_params* p, void* stream);
+/* dx += max-pool gradient.  For a tensor that feeds both a pooling and another operator (the input of a residual
+ * encoder block, scalogram_model.py:446-450): the other operator's backward writes dx, this call adds the pooling's share
+ * in place -- what autograd's accumulation would do with a zero-filled pooling gradient and a separate add pass. */
+int cpc_maxpool_bwd_accumulate(const float* x, const float* dy, float* dx, const cpc_pool_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 3. InfoNCE scoring + loss, forward and backward, scores never written to HBM.

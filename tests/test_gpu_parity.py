@@ -531,6 +531,40 @@ def test_max_pool_matches_torch_reference(cpc, shape, k, ceil):
     assert torch.equal(xg.grad.cpu(), xr.grad)
 
 
+@pytest.mark.parametrize("shape,k,ceil", [((2, 4, 21, 38), 2, True), ((2, 3, 20, 37), 2, True), ((1, 5, 19, 31), 3, False)])
+def test_conv_and_pool_node_matches_separate_operators(cpc, shape, k, ceil):
+    """ops.conv2d_with_pool (one node; the pooling gradient is added in place to the conv's data gradient) against
+    conv2d + max_pool2d as two nodes joined by autograd's add: values bit-identical, gradients to fp32 rounding."""
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(shape, generator=gen)
+    w = torch.randn(6, shape[1], 3, 3, generator=gen) * 0.2
+    b = torch.randn(6, generator=gen)
+    outs = []
+    for fused in (True, False):
+        xg = x.to(DEV).requires_grad_(True)
+        wg = w.to(DEV).requires_grad_(True)
+        bg = b.to(DEV).requires_grad_(True)
+        if fused:
+            y, pooled = cpc.ops.conv2d_with_pool(xg, wg, bg, (2, 2), (0, 0), 1, k, ceil)
+        else:
+            y = cpc.ops.conv2d(xg, wg, bg, (2, 2), (0, 0), 1)
+            pooled = cpc.ops.max_pool2d(xg, k, ceil)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(22)).to(DEV)
+        gp = torch.randn(pooled.shape, generator=torch.Generator().manual_seed(23)).to(DEV)
+        ((y * gy).sum() + (pooled * gp).sum()).backward()
+        outs.append((y.detach(), pooled.detach(), xg.grad, wg.grad, bg.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert rel_err(outs[0][2], outs[1][2]) < 1e-6
+    assert torch.equal(outs[0][3], outs[1][3]) and torch.equal(outs[0][4], outs[1][4])
+    # only one branch used downstream
+    xg = x.to(DEV).requires_grad_(True)
+    y, pooled = cpc.ops.conv2d_with_pool(xg, w.to(DEV), None, (2, 2), (0, 0), 1, k, ceil)
+    pooled.sum().backward()
+    xr = x.to(DEV).requires_grad_(True)
+    cpc.ops.max_pool2d(xr, k, ceil).sum().backward()
+    assert torch.equal(xg.grad, xr.grad)
+
+
 # ---------------------------------------------------------------------------------------------------
 # fused BatchNorm + ReLU (+ cropped residual + ReLU)
 # ---------------------------------------------------------------------------------------------------

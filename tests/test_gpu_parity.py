@@ -555,7 +555,7 @@ def test_conv_and_pool_node_matches_separate_operators(cpc, shape, k, ceil):
         outs.append((y.detach(), pooled.detach(), xg.grad, wg.grad, bg.grad))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert rel_err(outs[0][2], outs[1][2]) < 1e-6
-    assert torch.equal(outs[0][3], outs[1][3]) and torch.equal(outs[0][4], outs[1][4])
+    assert rel_err(outs[0][3], outs[1][3]) < 1e-5 and rel_err(outs[0][4], outs[1][4]) < 1e-5   # split-K atomics: order varies
     # only one branch used downstream
     xg = x.to(DEV).requires_grad_(True)
     y, pooled = cpc.ops.conv2d_with_pool(xg, w.to(DEV), None, (2, 2), (0, 0), 1, k, ceil)

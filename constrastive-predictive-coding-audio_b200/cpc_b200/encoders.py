@@ -277,21 +277,38 @@ class ScalogramEncoderBlock(nn.Module):
         return any(isinstance(m, ActivationWriter) and m.register is not None for m in self.main_modules) or \
             self.output_activation_writer.register is not None
 
-    def _residual_branch(self, x, main_shape, pooled=None):
+    def _residual_branch(self, x, main_shape, pooled=None, crop_early=False):
         """Residual branch output and the crop origin that centre-aligns it with ``main`` (:456-470).  ``pooled``: output
         of the branch's leading MaxPool2d when the caller already has it (ops.conv2d_with_pool)."""
-        if pooled is None:
-            res = _run_modules(self.residual_modules, x)
-        else:
-            res = _run_modules(self.residual_modules[1:], pooled)
+        mods = list(self.residual_modules)
+        if pooled is not None:
+            x, mods = pooled, mods[1:]
         m_h, m_w = main_shape
-        o_h = int((res.shape[2] - m_h + 1) / 2)
-        o_w = int((res.shape[3] - m_w + 1) / 2)
-        off_h = res.shape[2] - (o_h + m_h) if o_h > 0 else 0
-        off_w = res.shape[3] - (o_w + m_w) if o_w > 0 else 0
-        if off_h < 0 or off_w < 0 or off_h + m_h > res.shape[2] or off_w + m_w > res.shape[3]:
-            raise ValueError("residual branch %s cannot be cropped to %s" % (tuple(res.shape), (m_h, m_w)))
+        last = mods[-1] if mods else None
+        if (crop_early and not ops.switch("CPC_NO_EARLY_CROP") and type(last) is Conv2d and last.supported()
+                and tuple(last.kernel_size) == (1, 1) and tuple(last.stride) == (1, 1) and tuple(last.padding) == (0, 0)):
+            # A pointwise conv commutes with the centre crop: crop its input, so that it (and its backward) only works on
+            # the part of the branch the block output reads (34 of 64 rows in block 1 of architecture 7, 2 of 17 in block 2)
+            pre = _run_modules(mods[:-1], x)
+            off_h, off_w = self._crop_origin(pre.shape, main_shape)
+            pre = pre[:, :, off_h:off_h + m_h, off_w:off_w + m_w]
+            return last(pre.contiguous()), (0, 0)
+        res = _run_modules(mods, x)
+        off_h, off_w = self._crop_origin(res.shape, main_shape)
         return res, (off_h, off_w)
+
+    @staticmethod
+    def _crop_origin(res_shape, main_shape):
+        """Origin of the centre crop of the residual branch, with the reference's rounding (:456-470)."""
+        r_h, r_w = res_shape[2], res_shape[3]
+        m_h, m_w = main_shape
+        o_h = int((r_h - m_h + 1) / 2)
+        o_w = int((r_w - m_w + 1) / 2)
+        off_h = r_h - (o_h + m_h) if o_h > 0 else 0
+        off_w = r_w - (o_w + m_w) if o_w > 0 else 0
+        if off_h < 0 or off_w < 0 or off_h + m_h > r_h or off_w + m_w > r_w:
+            raise ValueError("residual branch %s cannot be cropped to %s" % (tuple(res_shape), (m_h, m_w)))
+        return off_h, off_w
 
     def _forward_fused(self, x, outer_relu):
         """conv -> fused(BN, ReLU) -> conv -> fused(BN, ReLU, + residual crop, [ReLU]); used when every stage is
@@ -327,7 +344,8 @@ class ScalogramEncoderBlock(nn.Module):
         if ops.block_tail_eligible(y_a, bn_a, conv_b, top_b, bn_b):
             # bn_a + ReLU + conv_b + bn_b (+ residual) + ReLU as one autograd node with packed intermediates
             oh = y_a.shape[2] + top_b + 2 * conv_b.padding[0] - conv_b.weight.shape[2] + 1
-            res, off = (self._residual_branch(x, (oh, y_a.shape[3]), pooled) if self.residual else (None, (0, 0)))
+            res, off = (self._residual_branch(x, (oh, y_a.shape[3]), pooled, crop_early=True) if self.residual
+                        else (None, (0, 0)))
             return ops.block_tail(y_a, bn_a, conv_b, top_b, bn_b, residual=res, res_off=off, outer_relu=outer_relu)
         h = x
         for idx, (top, conv, bn) in enumerate(stages):
@@ -337,7 +355,7 @@ class ScalogramEncoderBlock(nn.Module):
                 if idx == 1 and outer_relu:
                     h = F.relu(h)
             else:
-                res, off = self._residual_branch(x, (h.shape[2], h.shape[3]), pooled)
+                res, off = self._residual_branch(x, (h.shape[2], h.shape[3]), pooled, crop_early=True)
                 h = ops.bn_relu(h, bn, residual=res, res_off=off, relu=True, outer_relu=outer_relu)
         return h
 

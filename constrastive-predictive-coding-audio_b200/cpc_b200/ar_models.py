@@ -2,10 +2,13 @@
 plugged into ``AudioPredictiveCodingModel`` and run on stock PyTorch.  They are restated here only so that
 the package is usable without the reference checkout (audio_model.py:47-161, attention_model.py:9-82).
 
-Two deliberate deviations, both numerically identical in the forward pass:
+Three deliberate deviations, all numerically identical in the forward pass (the third also in the backward pass):
   * ``ConvolutionalArBlock`` adds the residual out of place (the reference's in-place ``+=`` on a ReLU
     output raises an autograd error on torch >= 1.5, SURVEY.md Appendix D-3);
-  * ``PositionalEncoder`` scales out of place (the reference scales a view of ``z`` in place).
+  * ``PositionalEncoder`` scales out of place (the reference scales a view of ``z`` in place);
+  * a ``ConvolutionalArBlock`` whose two branches start with the same pooling of ``x`` computes it once.
+On a B200 the conv1d and pooling layers of the convolutional AR model (``ArConv1d``, ``ArMaxPool1d``) run on the package's
+kernels in fp32 arithmetic; the modules, parameters and state_dict keys are the stock ones.
 """
 import math
 
@@ -28,6 +31,30 @@ class ArConv1d(nn.Conv1d):
                 and self.padding_mode == 'zeros' and not isinstance(self.padding, str) and self.in_channels >= 16
                 and not ops.second_order_enabled()):
             return ops.conv1d(x, self.weight, self.bias, self.stride[0], self.padding[0])
+        return super().forward(x)
+
+
+class ArMaxPool1d(nn.MaxPool1d):
+    """``nn.MaxPool1d`` of the AR blocks (audio_model.py:95-97, 110-112: ``MaxPool1d(pooling, ceil_mode=True)``).  On a
+    B200 its non-overlapping, unpadded case runs on the package's pooling kernels, as 1 x k windows of the (B, C, 1, T)
+    view (a k x k window clipped to the single row): ATen's max_pool backward takes 22 us per call on these
+    (64, 512, <= 60) tensors.  Anything else takes the stock path."""
+
+    def runs_on_kernels(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else None
+        stride = self.stride if isinstance(self.stride, int) else None
+        return (k is not None and stride == k and self.padding == 0 and self.dilation == 1 and not self.return_indices
+                and x.is_cuda and x.dim() == 3 and x.dtype == torch.float32 and (self.ceil_mode or x.shape[2] % k == 0)
+                and not ops.second_order_enabled())
+
+    def same_pooling(self, other):
+        return (isinstance(other, nn.MaxPool1d) and other.kernel_size == self.kernel_size and other.stride == self.stride
+                and other.padding == self.padding and other.dilation == self.dilation
+                and other.ceil_mode == self.ceil_mode and not other.return_indices and not self.return_indices)
+
+    def forward(self, x):
+        if self.runs_on_kernels(x):
+            return ops.max_pool2d(x.unsqueeze(2), self.kernel_size, True).squeeze(2)
         return super().forward(x)
 
 
@@ -55,7 +82,7 @@ class ConvolutionalArBlock(nn.Module):
         self.name = name
         self.main_modules = nn.ModuleList()
         if pooling > 1:
-            self.main_modules.append(nn.MaxPool1d(pooling, ceil_mode=True))
+            self.main_modules.append(ArMaxPool1d(pooling, ceil_mode=True))
         self.main_modules.append(ArConv1d(in_channels, out_channels, kernel_size, stride=stride, bias=bias))
         if batch_norm:
             self.main_modules.append(nn.BatchNorm1d(out_channels))
@@ -65,19 +92,25 @@ class ConvolutionalArBlock(nn.Module):
         if residual:
             self.residual_modules = nn.ModuleList()
             if pooling * stride > 1:
-                self.residual_modules.append(nn.MaxPool1d(pooling * stride, ceil_mode=True))
+                self.residual_modules.append(ArMaxPool1d(pooling * stride, ceil_mode=True))
             if in_channels != out_channels:
                 self.residual_modules.append(ArConv1d(in_channels, out_channels, kernel_size=1))
         self.output_activation_writer = ActivationWriter(register=activation_register, name=self.name)
 
     def forward(self, x):
-        main = x
-        for m in self.main_modules:
+        main, pooled = x, None
+        for i, m in enumerate(self.main_modules):
             main = m(main)
+            if i == 0 and isinstance(m, ArMaxPool1d):
+                pooled = main
         if self.residual:
             skip = x
-            for m in self.residual_modules:
-                skip = m(skip)
+            for i, m in enumerate(self.residual_modules):
+                # with stride 1 both branches start with the same pooling of x: computed once
+                if i == 0 and pooled is not None and self.main_modules[0].same_pooling(m):
+                    skip = pooled
+                else:
+                    skip = m(skip)
             main = main + skip[:, :, -main.shape[2]:]
         self.output_activation_writer(main)
         return main

@@ -531,6 +531,27 @@ def test_max_pool_matches_torch_reference(cpc, shape, k, ceil):
     assert torch.equal(xg.grad.cpu(), xr.grad)
 
 
+@pytest.mark.parametrize("t,k", [(26, 2), (9, 2), (1, 2), (11, 3)])
+def test_ar_max_pool1d_matches_torch(cpc, t, k):
+    """ArMaxPool1d (audio_model.py:95-97: MaxPool1d(k, ceil_mode=True)) on the pooling kernels: bit-exact forward and
+    backward incl. ties and the ragged last window."""
+    from cpc_b200.ar_models import ArMaxPool1d
+    gen = torch.Generator().manual_seed(t)
+    x = torch.randint(-3, 4, (3, 7, t), generator=gen).float()
+    ref = torch.nn.MaxPool1d(k, ceil_mode=True)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=gen)
+    (yr * gy).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    pool = ArMaxPool1d(k, ceil_mode=True)
+    assert pool.runs_on_kernels(xg)
+    yg = pool(xg)
+    (yg * gy.to(DEV)).sum().backward()
+    assert torch.equal(yg.cpu(), yr.detach())
+    assert torch.equal(xg.grad.cpu(), xr.grad)
+
+
 @pytest.mark.parametrize("shape,k,ceil", [((2, 4, 21, 38), 2, True), ((2, 3, 20, 37), 2, True), ((1, 5, 19, 31), 3, False)])
 def test_conv_and_pool_node_matches_separate_operators(cpc, shape, k, ceil):
     """ops.conv2d_with_pool (one node; the pooling gradient is added in place to the conv's data gradient) against

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--table", action="store_true", help="print every C-ABI call of the measured steps (CUDA-event times)")
     args = ap.parse_args()
     import torch
     import cpc_b200
@@ -33,15 +34,27 @@ def main():
     model.train()
     g = torch.Generator().manual_seed(1234)
     x = (0.1 * torch.randn(args.batch, model.item_length, generator=g)).to(dev)
+    prof = None
     for i in range(args.warmup + args.steps):
         if i == args.warmup:
             torch.cuda.synchronize()
             cpc_b200._lib.reset_launch_count()
+            if args.table:
+                prof = cpc_b200.ops.KernelProfiler()
+                prof.__enter__()
         loss, _ = trainer.loss_on_batch(x)
         model.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
     torch.cuda.synchronize()
+    if prof is not None:
+        prof.__exit__(None, None, None)
+        total = 0.0
+        for k in prof.summary():
+            total += k["total_ms"] / args.steps
+            print("%-105s n=%-3d %.4f ms/step  %.1f TFLOP/s  %.0f GB/s" % (k["key"], k["count"] // args.steps,
+                                                                        k["total_ms"] / args.steps, k["tflops"], k["gbs"]))
+        print("sum of own calls: %.3f ms/step" % total)
     print("loss %.5f, own kernel launches in the measured steps: %d" % (loss.item(), cpc_b200._lib.launch_count()))
 
 

@@ -19,6 +19,11 @@ namespace cpc {
 constexpr int BN_THREADS = 256;
 constexpr int BN_PER_THREAD = 16;
 constexpr int BN_SEG = BN_THREADS * BN_PER_THREAD;
+// The backward kernels walk a thread's BN_PER_THREAD elements in batches of BN_BATCH (loads of a batch issued together).
+// ncu: with all 16 elements of 2-3 tensors live at once they needed 74-86 registers, 2-3 blocks per SM, 20-35 % of the
+// warp slots, and streamed at 3.2-4.4 TB/s, while the 32-register statistics kernel (95 % of the slots) reaches 6.1 TB/s:
+// on B200 resident warps, not loads per thread, fill the memory pipeline.
+constexpr int BN_BATCH = 4;
 
 struct BnGeom {
     int B, C, H, W, HW;
@@ -150,9 +155,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
     const float* px = x + (size_t)plane * g.HW;
     float* po = out + (size_t)plane * g.HW;
     const float* pr = res ? res + (size_t)plane * g.RH * g.RW + (size_t)g.roh * g.RW + g.row : nullptr;
-    // the mask variant works in two half-batches: the ballots pin every load of a batch in front of them, and a full
-    // batch of 2 x 16 live values would halve the occupancy
-    constexpr int BATCH = MASK ? BN_PER_THREAD / 2 : BN_PER_THREAD;
+    // the mask variant works in batches: the ballots pin every load of a batch in front of them, and a full batch of
+    // 2 x 16 live values would halve the occupancy (the plain variant is scheduled that way by the compiler anyway)
+    constexpr int BATCH = MASK ? BN_BATCH : BN_PER_THREAD;
     uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
 #pragma unroll 1
     for (int half = 0; half < BN_PER_THREAD / BATCH; ++half) {
@@ -224,34 +229,39 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const float* 
     for (int seg = 0; seg < BN_RED_SEGS; ++seg) {
         const int i0 = (blockIdx.y * BN_RED_SEGS + seg) * (int)blockDim.x * BN_PER_THREAD + threadIdx.x;
         if (i0 - (int)threadIdx.x >= g.HW) break;
-        float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[MASK ? 1 : BN_PER_THREAD];
-        uint32_t ob = 0;                                             // MASK: bit u = saved outer-ReLU bit of element u
+#pragma unroll 1
+        for (int part = 0; part < BN_PER_THREAD / BN_BATCH; ++part) {
+            const int ib = i0 + part * BN_BATCH * (int)blockDim.x;
+            if (ib - (int)threadIdx.x >= g.HW) break;
+            float xv[BN_BATCH], dv[BN_BATCH], rv[MASK ? 1 : BN_BATCH];
+            uint32_t ob = 0;                                         // MASK: bit u = saved outer-ReLU bit of element u
 #pragma unroll
-        for (int u = 0; u < BN_PER_THREAD; ++u) {
-            const int i = i0 + u * (int)blockDim.x;
-            const bool in = i < g.HW;
-            xv[u] = in ? __ldg(px + i) : 0.f;
-            dv[u] = in ? __ldg(pd + i) : 0.f;
-            if constexpr (MASK) {
-                if (in) ob |= ((__ldg(pm + (i >> 5)) >> (i & 31)) & 1u) << u;
-                continue;
+            for (int u = 0; u < BN_BATCH; ++u) {
+                const int i = ib + u * (int)blockDim.x;
+                const bool in = i < g.HW;
+                xv[u] = in ? __ldg(px + i) : 0.f;
+                dv[u] = in ? __ldg(pd + i) : 0.f;
+                if constexpr (MASK) {
+                    if (in) ob |= ((__ldg(pm + (i >> 5)) >> (i & 31)) & 1u) << u;
+                    continue;
+                }
+                rv[MASK ? 0 : u] = 0.f;
+                if (need_res && in) {
+                    int h, w;
+                    g.d_w.divmod(i, h, w);
+                    rv[MASK ? 0 : u] = __ldg(pr + (size_t)h * g.RW + w);
+                }
             }
-            rv[MASK ? 0 : u] = 0.f;
-            if (need_res && in) {
-                int h, w;
-                g.d_w.divmod(i, h, w);
-                rv[MASK ? 0 : u] = __ldg(pr + (size_t)h * g.RW + w);
-            }
-        }
 #pragma unroll
-        for (int u = 0; u < BN_PER_THREAD; ++u) {
-            const int i = i0 + u * (int)blockDim.x;
-            if (i < g.HW) {
-                float xhat, g1;
-                const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, MASK ? 0.f : rv[MASK ? 0 : u], g,
-                                            xhat, g1, MASK ? (int)((ob >> u) & 1u) : -1);
-                s += g2;
-                q = fmaf(g2, xhat, q);
+            for (int u = 0; u < BN_BATCH; ++u) {
+                const int i = ib + u * (int)blockDim.x;
+                if (i < g.HW) {
+                    float xhat, g1;
+                    const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr,
+                                                MASK ? 0.f : rv[MASK ? 0 : u], g, xhat, g1, MASK ? (int)((ob >> u) & 1u) : -1);
+                    s += g2;
+                    q = fmaf(g2, xhat, q);
+                }
             }
         }
     }
@@ -294,45 +304,50 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* _
     const float* pr = res ? res + roff : nullptr;
     float* pdr = d_res ? d_res + roff : nullptr;
     const int i0 = blockIdx.y * (int)blockDim.x * BN_PER_THREAD + threadIdx.x;
-    float xv[BN_PER_THREAD], dv[BN_PER_THREAD], rv[MASK ? 1 : BN_PER_THREAD];
-    int ro[MASK ? 1 : BN_PER_THREAD];                                // offset inside the residual plane (MASK: recomputed)
-    uint32_t ob = 0;                                                 // MASK: bit u = saved outer-ReLU bit of element u
     const bool need_res = !MASK && pr != nullptr && g.outer_relu;
     const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
+#pragma unroll 1
+    for (int part = 0; part < BN_PER_THREAD / BN_BATCH; ++part) {
+        const int ib = i0 + part * BN_BATCH * (int)blockDim.x;
+        if (ib - (int)threadIdx.x >= g.HW) break;
+        float xv[BN_BATCH], dv[BN_BATCH], rv[MASK ? 1 : BN_BATCH];
+        int ro[MASK ? 1 : BN_BATCH];                                 // offset inside the residual plane (MASK: recomputed)
+        uint32_t ob = 0;                                             // MASK: bit u = saved outer-ReLU bit of element u
 #pragma unroll
-    for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * (int)blockDim.x;
-        const bool in = i < g.HW;
-        xv[u] = in ? __ldg(px + i) : 0.f;
-        dv[u] = in ? __ldg(pd + i) : 0.f;
-        if constexpr (MASK) {
-            if (in) ob |= ((__ldg(pm + (i >> 5)) >> (i & 31)) & 1u) << u;
-            continue;
+        for (int u = 0; u < BN_BATCH; ++u) {
+            const int i = ib + u * (int)blockDim.x;
+            const bool in = i < g.HW;
+            xv[u] = in ? __ldg(px + i) : 0.f;
+            dv[u] = in ? __ldg(pd + i) : 0.f;
+            if constexpr (MASK) {
+                if (in) ob |= ((__ldg(pm + (i >> 5)) >> (i & 31)) & 1u) << u;
+                continue;
+            }
+            rv[MASK ? 0 : u] = 0.f;
+            ro[MASK ? 0 : u] = 0;
+            if ((pr || pdr) && in) {
+                int h, w;
+                g.d_w.divmod(i, h, w);
+                ro[MASK ? 0 : u] = h * g.RW + w;
+                if (need_res) rv[MASK ? 0 : u] = __ldg(pr + ro[MASK ? 0 : u]);
+            }
         }
-        rv[MASK ? 0 : u] = 0.f;
-        ro[MASK ? 0 : u] = 0;
-        if ((pr || pdr) && in) {
-            int h, w;
-            g.d_w.divmod(i, h, w);
-            ro[MASK ? 0 : u] = h * g.RW + w;
-            if (need_res) rv[MASK ? 0 : u] = __ldg(pr + ro[MASK ? 0 : u]);
-        }
-    }
 #pragma unroll
-    for (int u = 0; u < BN_PER_THREAD; ++u) {
-        const int i = i0 + u * (int)blockDim.x;
-        if (i < g.HW) {
-            float xhat, g1;
-            const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, MASK ? 0.f : rv[MASK ? 0 : u], g, xhat,
-                                        g1, MASK ? (int)((ob >> u) & 1u) : -1);
-            pdx[i] = k * (g2 - m1 - xhat * m2);
-            if (pdr) {
-                if constexpr (MASK) {
-                    int h, w;
-                    g.d_w.divmod(i, h, w);
-                    pdr[h * g.RW + w] = g1;
-                } else {
-                    pdr[ro[MASK ? 0 : u]] = g1;
+        for (int u = 0; u < BN_BATCH; ++u) {
+            const int i = ib + u * (int)blockDim.x;
+            if (i < g.HW) {
+                float xhat, g1;
+                const float g2 = bn_grad_in(dv[u], xv[u], mean, rstd, gam, bet, pr != nullptr, MASK ? 0.f : rv[MASK ? 0 : u], g,
+                                            xhat, g1, MASK ? (int)((ob >> u) & 1u) : -1);
+                pdx[i] = k * (g2 - m1 - xhat * m2);
+                if (pdr) {
+                    if constexpr (MASK) {
+                        int h, w;
+                        g.d_w.divmod(i, h, w);
+                        pdr[h * g.RW + w] = g1;
+                    } else {
+                        pdr[ro[MASK ? 0 : u]] = g1;
+                    }
                 }
             }
         }
@@ -500,21 +515,27 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_packed_kernel(const float
     const float2* px = reinterpret_cast<const float2*>(x + (size_t)plane * g.HW);
     const int n_pairs = g.HW >> 1;
     const int j0 = blockIdx.y * (int)blockDim.x * BN_PAIRS + threadIdx.x;
-    float2 xv[BN_PAIRS];
+    constexpr int PB = BN_BATCH / 2;                                 // pairs per load batch
+#pragma unroll 1
+    for (int part = 0; part < BN_PAIRS / PB; ++part) {
+        const int jb = j0 + part * PB * (int)blockDim.x;
+        if (jb - (int)threadIdx.x >= n_pairs) break;
+        float2 xv[PB];
 #pragma unroll
-    for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * (int)blockDim.x;
-        xv[u] = j < n_pairs ? __ldg(px + j) : make_float2(0.f, 0.f);
-    }
+        for (int u = 0; u < PB; ++u) {
+            const int j = jb + u * (int)blockDim.x;
+            xv[u] = j < n_pairs ? __ldg(px + j) : make_float2(0.f, 0.f);
+        }
 #pragma unroll
-    for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * (int)blockDim.x;
-        if (j < n_pairs) {
-            float a = fmaf(xv[u].x, sc, sh), b = fmaf(xv[u].y, sc, sh);
-            if (g.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            int h, wp;
-            d_w2.divmod(j, h, wp);
-            packed_store2(pk, g, plane, h, 2 * wp, a, b);
+        for (int u = 0; u < PB; ++u) {
+            const int j = jb + u * (int)blockDim.x;
+            if (j < n_pairs) {
+                float a = fmaf(xv[u].x, sc, sh), b = fmaf(xv[u].y, sc, sh);
+                if (g.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                int h, wp;
+                d_w2.divmod(j, h, wp);
+                packed_store2(pk, g, plane, h, 2 * wp, a, b);
+            }
         }
     }
 }
@@ -545,49 +566,55 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_packed_kernel(
     float* pdr = d_res ? d_res + roff : nullptr;
     const int n_pairs = g.HW >> 1;
     const int j0 = blockIdx.y * (int)blockDim.x * BN_PAIRS + threadIdx.x;
-    float2 xv[BN_PAIRS], dv[BN_PAIRS], rv[MASK ? 1 : BN_PAIRS];
-    int hh[BN_PAIRS], ww[BN_PAIRS];
-    uint32_t ob = 0;                                                 // MASK: bits 2u, 2u + 1 = saved bits of pair u
     const bool need_res = !MASK && pr != nullptr && g.outer_relu;
     const uint32_t* pm = MASK ? mask + (size_t)plane * ((g.HW + 31) >> 5) : nullptr;
+    constexpr int PB = BN_BATCH / 2;                                 // pairs per load batch
+    float total = 0.f;
+#pragma unroll 1
+    for (int part = 0; part < BN_PAIRS / PB; ++part) {
+        const int jb = j0 + part * PB * (int)blockDim.x;
+        if (jb - (int)threadIdx.x >= n_pairs) break;
+        float2 xv[PB], dv[PB], rv[MASK ? 1 : PB];
+        int hh[PB], ww[PB];
+        uint32_t ob = 0;                                             // MASK: bits 2u, 2u + 1 = saved bits of pair u
 #pragma unroll
-    for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * (int)blockDim.x;
-        const bool in = j < n_pairs;
-        xv[u] = in ? __ldg(px + j) : make_float2(0.f, 0.f);
-        dv[u] = in ? __ldg(pd + j) : make_float2(0.f, 0.f);
-        if constexpr (!MASK) rv[MASK ? 0 : u] = make_float2(0.f, 0.f);
-        hh[u] = 0; ww[u] = 0;
-        if constexpr (MASK) {
-            if (in) ob |= ((__ldg(pm + (j >> 4)) >> ((2 * j) & 31)) & 3u) << (2 * u);   // both bits of the pair
-        }
-        if (in) {
-            int wp;
-            d_w2.divmod(j, hh[u], wp);
-            ww[u] = 2 * wp;
-            if (need_res) {
-                const float* q = pr + (size_t)hh[u] * g.RW + ww[u];
-                rv[MASK ? 0 : u] = make_float2(__ldg(q), __ldg(q + 1));
+        for (int u = 0; u < PB; ++u) {
+            const int j = jb + u * (int)blockDim.x;
+            const bool in = j < n_pairs;
+            xv[u] = in ? __ldg(px + j) : make_float2(0.f, 0.f);
+            dv[u] = in ? __ldg(pd + j) : make_float2(0.f, 0.f);
+            if constexpr (!MASK) rv[MASK ? 0 : u] = make_float2(0.f, 0.f);
+            hh[u] = 0; ww[u] = 0;
+            if constexpr (MASK) {
+                if (in) ob |= ((__ldg(pm + (j >> 4)) >> ((2 * j) & 31)) & 3u) << (2 * u);   // both bits of the pair
+            }
+            if (in) {
+                int wp;
+                d_w2.divmod(j, hh[u], wp);
+                ww[u] = 2 * wp;
+                if (need_res) {
+                    const float* q = pr + (size_t)hh[u] * g.RW + ww[u];
+                    rv[MASK ? 0 : u] = make_float2(__ldg(q), __ldg(q + 1));
+                }
             }
         }
-    }
-    float total = 0.f;
 #pragma unroll
-    for (int u = 0; u < BN_PAIRS; ++u) {
-        const int j = j0 + u * (int)blockDim.x;
-        if (j < n_pairs) {
-            float xh0, xh1, g10, g11;
-            const float2 r2 = MASK ? make_float2(0.f, 0.f) : rv[MASK ? 0 : u];
-            const float g20 = bn_grad_in(dv[u].x, xv[u].x, mean, rstd, gam, bet, pr != nullptr, r2.x, g, xh0, g10,
-                                         MASK ? (int)((ob >> (2 * u)) & 1u) : -1);
-            const float g21 = bn_grad_in(dv[u].y, xv[u].y, mean, rstd, gam, bet, pr != nullptr, r2.y, g, xh1, g11,
-                                         MASK ? (int)((ob >> (2 * u + 1)) & 1u) : -1);
-            const float d0 = k * (g20 - m1 - xh0 * m2), d1 = k * (g21 - m1 - xh1 * m2);
-            packed_store2(pk, g, plane, hh[u], ww[u], d0, d1);
-            total += d0 + d1;
-            if (pdr) {
-                float* q = pdr + (size_t)hh[u] * g.RW + ww[u];
-                q[0] = g10; q[1] = g11;
+        for (int u = 0; u < PB; ++u) {
+            const int j = jb + u * (int)blockDim.x;
+            if (j < n_pairs) {
+                float xh0, xh1, g10, g11;
+                const float2 r2 = MASK ? make_float2(0.f, 0.f) : rv[MASK ? 0 : u];
+                const float g20 = bn_grad_in(dv[u].x, xv[u].x, mean, rstd, gam, bet, pr != nullptr, r2.x, g, xh0, g10,
+                                             MASK ? (int)((ob >> (2 * u)) & 1u) : -1);
+                const float g21 = bn_grad_in(dv[u].y, xv[u].y, mean, rstd, gam, bet, pr != nullptr, r2.y, g, xh1, g11,
+                                             MASK ? (int)((ob >> (2 * u + 1)) & 1u) : -1);
+                const float d0 = k * (g20 - m1 - xh0 * m2), d1 = k * (g21 - m1 - xh1 * m2);
+                packed_store2(pk, g, plane, hh[u], ww[u], d0, d1);
+                total += d0 + d1;
+                if (pdr) {
+                    float* q = pdr + (size_t)hh[u] * g.RW + ww[u];
+                    q[0] = g10; q[1] = g11;
+                }
             }
         }
     }

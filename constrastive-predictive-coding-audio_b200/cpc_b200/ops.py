@@ -629,7 +629,8 @@ class _BnReluFunction(torch.autograd.Function):
             _call(_bn_key("cpc_bn_relu_bwd", p), 0.0, lib.cpc_bn_relu_bwd_mask, _ptr(dout), _ptr(x), _ptr(gamma),
                   _ptr(beta), _ptr(save_mean), _ptr(save_rstd), _ptr(res_arg), _ptr(mask), _ptr(dx), _ptr(dgamma),
                   _ptr(dbeta), _ptr(d_res), ctypes.byref(p), _ptr(ws), ws.numel(), _stream(),
-                  nbytes=4.0 * n * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0)))
+                  nbytes=4.0 * n * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0))
+                  + (2.0 * mask.numel() if mask is not None else 0.0))
         return dx, dgamma, dbeta, None, None, d_res, None, None, None, None, None, None
 
 
@@ -754,7 +755,8 @@ class _BlockTailFunction(torch.autograd.Function):
             _call(_bn_key("cpc_bn_relu_bwd", p1) + " ->packed", 0.0, lib.cpc_bn_relu_bwd_packed_mask, _ptr(dout), _ptr(y_b),
                   _ptr(g1), _ptr(b1), _ptr(mean1), _ptr(rstd1), _ptr(res_arg), _ptr(mask), _ptr(packed_dy), _ptr(db),
                   _ptr(dg1), _ptr(dbt1), _ptr(d_res), ctypes.byref(p1), _ptr(ws1), ws1.numel(), _stream(),
-                  nbytes=4.0 * n1 * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0)))
+                  nbytes=4.0 * n1 * (5 + (2 if (residual is not None and outer_relu) else 0) + (1 if d_res is not None else 0))
+                  + (2.0 * mask.numel() if mask is not None else 0.0))
             wsd = _workspace(lib.cpc_conv_workspace_bytes(ctypes.byref(pc), 1), dev)
             _call(_conv_key("cpc_conv_dgrad", pc), _conv_flops(pc), lib.cpc_conv_dgrad_ex, _ptr(None), _ptr(w), _ptr(dh),
                   ctypes.byref(pc), _ptr(packed_dy), _ptr(wsd), wsd.numel() if wsd is not None else 0, _stream())

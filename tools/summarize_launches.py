@@ -6,7 +6,7 @@ import re
 import sys
 
 
-def main(path, title):
+def main(path, title, steps=1):
     lines = open(path).read().splitlines()
     start = [k for k, l in enumerate(lines) if l.startswith('"ID"')][0]
     rows = list(csv.DictReader(lines[start:]))
@@ -18,7 +18,9 @@ def main(path, title):
         agg[name][1] += float(r['Metric Value']) / 1e6
     total = sum(v[1] for v in agg.values())
     print("# %s\n" % title)
-    print("%d launches, %.2f ms summed device time (cold-cache, serialised under ncu: compare SHARES).\n" % (len(rows), total))
+    print("%d launches over %d identical eager steps = %d launches and %.2f ms of summed device time per step (cold-cache, "
+          "serialised under ncu: compare SHARES; the graph-replayed step is faster).  Launch counts and ms below are totals "
+          "over the %d steps.\n" % (len(rows), steps, len(rows) // steps, total / steps, steps))
     print("| kernel | launches | total ms | share |")
     print("|---|---:|---:|---:|")
     for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
@@ -26,4 +28,4 @@ def main(path, title):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], int(sys.argv[3]) if len(sys.argv) > 3 else 1)

@@ -18,7 +18,7 @@ CONV_FLAG_CUDA_CORE, CONV_FLAG_NO_TALL, CONV_FLAG_NO_SMALLK, CONV_FLAG_NO_FUSED_
 CONV_FLAG_NO_MMA_SMALL_WGRAD = 16
 INFONCE_FLAG_NO_TENSOR = 1
 INFONCE_OUT_FLOATS = 4
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class CqtParams(ctypes.Structure):
@@ -46,7 +46,7 @@ class BnParams(ctypes.Structure):
                 ("width", ctypes.c_int32), ("res_height", ctypes.c_int32), ("res_width", ctypes.c_int32),
                 ("res_off_h", ctypes.c_int32), ("res_off_w", ctypes.c_int32), ("relu", ctypes.c_int32),
                 ("outer_relu", ctypes.c_int32), ("training", ctypes.c_int32), ("eps", ctypes.c_float),
-                ("momentum", ctypes.c_float)]
+                ("momentum", ctypes.c_float), ("packed_planes", ctypes.c_int32)]
 
 
 class PoolParams(ctypes.Structure):

@@ -550,8 +550,9 @@ def depthwise_conv2d(x, weight, stride=(1, 1), padding=(0, 0), extra_top=0):
 # fused BatchNorm2d + ReLU (+ cropped residual add + ReLU)
 # --------------------------------------------------------------------------------------------------
 
-def _bn_params(x_shape, res_shape, res_off, relu, outer_relu, training, eps, momentum):
+def _bn_params(x_shape, res_shape, res_off, relu, outer_relu, training, eps, momentum, packed_planes=0):
     p = _lib.BnParams()
+    p.packed_planes = int(packed_planes)                         # *_packed calls: 1 = hi plane only (bf16 conv mode)
     p.batch, p.channels, p.height, p.width = x_shape
     if res_shape is not None:
         p.res_height, p.res_width = res_shape[2], res_shape[3]
@@ -689,7 +690,8 @@ class _BlockTailFunction(torch.autograd.Function):
         dev = y_a.device
         B, C, H, W = y_a.shape
         # bn0 + relu -> packed h
-        p0 = _bn_params((B, C, H, W), None, (0, 0), True, False, tr0, eps0, mom0)
+        planes = 1 if precision == "bf16" else 2                 # operand planes the conv kernels of this mode read
+        p0 = _bn_params((B, C, H, W), None, (0, 0), True, False, tr0, eps0, mom0, planes)
         packed_h = torch.empty(int(lib.cpc_bn_packed_bytes(ctypes.byref(p0))), dtype=torch.uint8, device=dev)
         mean0 = torch.empty(C, dtype=torch.float32, device=dev)
         rstd0 = torch.empty(C, dtype=torch.float32, device=dev)
@@ -733,7 +735,8 @@ class _BlockTailFunction(torch.autograd.Function):
         dout = dout.contiguous()
         B, C, H, W = y_a.shape
         co = w.shape[0]
-        p1 = _bn_params(tuple(y_b.shape), ctx.res_shape, res_off, True, outer_relu, tr1, eps1, mom1)
+        planes = 1 if precision == "bf16" else 2
+        p1 = _bn_params(tuple(y_b.shape), ctx.res_shape, res_off, True, outer_relu, tr1, eps1, mom1, planes)
         # with the saved mask the residual is not read: y_b stands in for "there is a residual"
         res_arg = residual if residual is not None else (y_b if ctx.res_shape is not None else None)
         pc = _conv_params((B, C, H, W), tuple(w.shape), (1, 1), top, 0, out_hw, False, precision)
@@ -774,8 +777,8 @@ class _BlockTailFunction(torch.autograd.Function):
 def block_tail_eligible(y_a, bn0, conv, top, bn1):
     """True when ``relu(bn0(y_a)) -> conv -> bn1`` can run as one node with packed intermediates: kh x 1 stride-1 conv
     without horizontal padding on the row-streaming kernels (forward, data and weight gradient), fp32-faithful mode,
-    affine batch norms, first-order autograd."""
-    if _switch("CPC_NO_BLOCK_TAIL") or _second_order or _default_precision != "fp32":
+    affine batch norms, first-order autograd.  Both operand modes: fp32-faithful (hi + lo planes) and bf16 (hi plane)."""
+    if _switch("CPC_NO_BLOCK_TAIL") or _second_order:
         return False
     if not (y_a.is_cuda and y_a.dtype == torch.float32 and y_a.dim() == 4 and y_a.shape[3] % 2 == 0):
         return False                                             # the packed-output kernels own pairs of columns
@@ -790,7 +793,7 @@ def block_tail_eligible(y_a, bn0, conv, top, bn1):
     oh = H + top + 2 * conv.padding[0] - w.shape[2] + 1
     if oh <= 0:
         return False
-    p = _conv_params((B, C, H, W), tuple(w.shape), (1, 1), top + conv.padding[0], 0, (oh, W), False, "fp32")
+    p = _conv_params((B, C, H, W), tuple(w.shape), (1, 1), top + conv.padding[0], 0, (oh, W), False, _default_precision)
     lib = _lib.load()
     return all(lib.cpc_conv_kernel_family(ctypes.byref(p), which) in (2, 3) for which in (0, 1, 2))
 
@@ -802,7 +805,8 @@ def block_tail(y_a, bn0, conv, top, bn1, residual=None, res_off=(0, 0), outer_re
     w = conv.weight
     pad_top = top + conv.padding[0]
     oh = y_a.shape[2] + top + 2 * conv.padding[0] - w.shape[2] + 1
-    cfg = (pad_top, (oh, y_a.shape[3]), tuple(res_off), bool(outer_relu), tr0, bn0.eps, mom0, tr1, bn1.eps, mom1, "fp32")
+    cfg = (pad_top, (oh, y_a.shape[3]), tuple(res_off), bool(outer_relu), tr0, bn0.eps, mom0, tr1, bn1.eps, mom1,
+           _default_precision)
     return _BlockTailFunction.apply(y_a, bn0.weight, bn0.bias, rm0, rv0, w, conv.bias, bn1.weight, bn1.bias, rm1, rv1,
                                     residual, cfg)
 

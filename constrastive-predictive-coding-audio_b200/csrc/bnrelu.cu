@@ -64,6 +64,7 @@ static int bn_validate(const cpc_bn_params* p) {
         if ((int64_t)p->res_height * p->res_width > (1ll << 30)) return CPC_ERR_BAD_SHAPE;
     }
     if (!(p->eps > 0.f) || p->momentum < 0.f || p->momentum > 1.f) return CPC_ERR_BAD_SHAPE;
+    if (p->packed_planes < 0 || p->packed_planes > 2) return CPC_ERR_BAD_SHAPE;
     return CPC_OK;
 }
 
@@ -486,7 +487,7 @@ constexpr int BN_SMALL_HW = 2048;
 // elements (8-byte loads, 4-byte bf16x2 stores; 2-byte stores ran the kernel 25 % slower than the fp32 version).
 struct PackedOut {
     __nv_bfloat16* base;
-    long plane_stride;       // elements between the hi and the lo plane
+    long plane_stride;       // elements between the hi and the lo plane; 0: hi plane only (bf16 operand mode)
     int Wp;
 };
 constexpr int BN_PAIRS = BN_PER_THREAD / 2;
@@ -496,12 +497,12 @@ __device__ __forceinline__ void packed_store2(const PackedOut& po, const BnGeom&
     const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
     const __nv_bfloat162 lo = __floats2bfloat162_rn(a - __low2float(hi), b - __high2float(hi));
     *reinterpret_cast<__nv_bfloat162*>(q) = hi;
-    *reinterpret_cast<__nv_bfloat162*>(q + po.plane_stride) = lo;
+    if (po.plane_stride) *reinterpret_cast<__nv_bfloat162*>(q + po.plane_stride) = lo;
     if (w + 2 == g.W) {                                          // last pair of the row: zero the pad columns
         const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
         for (int k = 2; k < po.Wp - w; k += 2) {
             *reinterpret_cast<__nv_bfloat162*>(q + k) = z;
-            *reinterpret_cast<__nv_bfloat162*>(q + po.plane_stride + k) = z;
+            if (po.plane_stride) *reinterpret_cast<__nv_bfloat162*>(q + po.plane_stride + k) = z;
         }
     }
 }
@@ -693,7 +694,7 @@ static int bn_fwd_impl(const float* x, const float* gamma, const float* beta, fl
     CPC_LAUNCH_CHECK();
     if (packed_out) {
         const int Wp = (g.W + 7) & ~7;
-        PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_out), (long)g.B * g.C * g.H * Wp, Wp};
+        PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_out), p->packed_planes == 1 ? 0l : (long)g.B * g.C * g.H * Wp, Wp};
         const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, nt * BN_PAIRS));
         bn_apply_packed_kernel<<<pgrid, nt, 0, s>>>(x, affine, pk, g, FastDiv(g.W / 2));
     } else if (small) {
@@ -738,7 +739,7 @@ extern "C" int cpc_bn_relu_fwd_packed(const float* x, const float* gamma, const 
 extern "C" size_t cpc_bn_packed_bytes(const cpc_bn_params* p) {
     if (bn_validate(p) != CPC_OK) return 0;
     const size_t Wp = (size_t)((p->width + 7) & ~7);
-    return 2 * (size_t)p->batch * p->channels * p->height * Wp * sizeof(__nv_bfloat16);
+    return (p->packed_planes == 1 ? 1 : 2) * (size_t)p->batch * p->channels * p->height * Wp * sizeof(__nv_bfloat16);
 }
 
 static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, const float* beta, const float* save_mean,
@@ -786,7 +787,7 @@ static int bn_bwd_impl(const float* dout, const float* x, const float* gamma, co
     CPC_LAUNCH_CHECK();
     if (packed_dx) {
         const int Wp = (g.W + 7) & ~7;
-        PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_dx), (long)g.B * g.C * g.H * Wp, Wp};
+        PackedOut pk{reinterpret_cast<__nv_bfloat16*>(packed_dx), p->packed_planes == 1 ? 0l : (long)g.B * g.C * g.H * Wp, Wp};
         const dim3 pgrid(g.B * g.C, ceil_div(g.HW / 2, nt * BN_PAIRS));
         auto* kern = mask ? bn_bwd_apply_packed_kernel<true> : bn_bwd_apply_packed_kernel<false>;
         kern<<<pgrid, nt, 0, s>>>(dout, x, gamma, beta, save_mean, save_rstd, residual, mask, sums2, pk, dx_sum, dgamma,

@@ -18,6 +18,8 @@
 //   * fp32-faithful arithmetic = bf16 hi/lo split, products hi*hi + hi*lo + lo*hi (both planes of a
 //     weight row share one 128-byte swizzle row: [hi c0..31 | lo c0..31]).
 //   * the data gradient is the same kernel on dy with channel roles swapped and taps flipped.
+//   * bf16 operand mode (cpc_conv_params.precision = 1): the activation operand has its hi plane only (half the
+//     bytes per row) and one product, hi*hi, is issued instead of three.
 // Weight gradient (tall_wgrad_kernel):
 //   dW[co, ci, i] = sum_{b, r, w} dy[b, co, r, w] * x[b, ci, r - P + i, w]
 //   * both operands are K-major over 64-pixel chunks; M = (ci, 4 x rows), N = (co, 4 dy rows), so one
@@ -48,6 +50,7 @@ struct TallConv {
     int kh, P;                               // taps, zero rows above the source
     int n_units, n_pairs, n_rtiles, n_tiles;
     int relu;
+    int planes;                              // 2: bf16 hi/lo (fp32-faithful), 1: hi plane only (bf16 operand mode)
     const float* bias;
     float* out;                              // (B, 32, H_out, W) fp32
 };
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
                 int pair, r0, j_lo, j_hi;
                 tall_tile_rows(p, tile, pair, r0, j_lo, j_hi);
                 if (j_hi == j_lo) continue;                   // no input row inside the source: bias-only tile
+                const uint32_t a_bytes = p.planes == 2 ? TL_ASTAGE : TL_ASTAGE / 2;   // hi plane only: rows 0..31 of an atom
                 int ab[2], aw0[2];
                 for (int a = 0; a < 2; ++a) {
                     const int u = pair * 2 + a;               // unit >= n_units -> batch index out of range -> zeros
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     const int slot = (TL_T - (int)(v % TL_T)) % TL_T;
                     const bool with_row = j >= j_lo;
-                    const uint32_t bytes = TL_SLOT * (slot < 3 ? 2 : 1) + (with_row ? TL_ASTAGE : 0);
+                    const uint32_t bytes = TL_SLOT * (slot < 3 ? 2 : 1) + (with_row ? a_bytes : 0);
                     mbar_expect_tx(&bars->full[stage], bytes);
                     tma_load_3d(w_ring + slot * TL_SLOT, &tmap_w, &bars->full[stage], 0, 0, j);   // j outside [0,kh) -> zeros
                     if (slot < 3) tma_load_3d(w_ring + (TL_T + slot) * TL_SLOT, &tmap_w, &bars->full[stage], 0, 0, j);
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
                                 const uint32_t d_tmem = tmem_base + (uint32_t)g * 128;
                                 mma_bf16(d_tmem, a_hi, b_hi, idesc, accum0);                                   // hi * hi
                                 mma_bf16(d_tmem, a_hi + (uint64_t)((16 * 128) >> 4), b_hi + 2, idesc, 1u);
+                                if (p.planes == 1) continue;                                                   // bf16 operand mode
                                 mma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);                                       // hi * lo
                                 mma_bf16(d_tmem, a_hi + (uint64_t)((16 * 128) >> 4), b_lo + 2, idesc, 1u);
                                 mma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);                                       // lo * hi
@@ -257,6 +262,7 @@ struct TallWgrad {
     int n_units, n_splits, n_dgroups;
     int d_min;                               // block d covers taps 4*d + P + delta - rho
     int Q;                                   // dy row groups
+    int planes;                              // 2: hi/lo planes, 1: hi plane only (bf16 operand mode)
     float* dw;                               // (32, 32, kh) fp32, zero-initialised
 };
 
@@ -296,10 +302,11 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
     if (warp == 0) {
         if (lane == 0) {
             uint32_t xn = 0, yn = 0;
+            const uint32_t g_bytes = p.planes == 2 ? TW_GROUP : TW_GROUP / 2;
             auto load_x = [&](int b, int w0, int n) {            // x row group d0 + n of the current atom
                 const int slot = xn % TW_XS;
                 mbar_wait(&bars->xempty[slot], ((xn / TW_XS) & 1) ^ 1);
-                mbar_expect_tx(&bars->xfull[slot], TW_GROUP);
+                mbar_expect_tx(&bars->xfull[slot], g_bytes);
                 tma_load_5d(x_ring + slot * TW_GROUP, &tmap_x, &bars->xfull[slot], w0, 4 * (d0 + n), 0, b, 0);
                 ++xn;
             };
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
                     load_x(b, w0, q + 2);
                     const int slot = yn % TW_YS;
                     mbar_wait(&bars->yempty[slot], ((yn / TW_YS) & 1) ^ 1);
-                    mbar_expect_tx(&bars->yfull[slot], TW_GROUP);
+                    mbar_expect_tx(&bars->yfull[slot], g_bytes);
                     tma_load_5d(y_ring + slot * TW_GROUP, &tmap_dy, &bars->yfull[slot], w0, 4 * q, 0, b, 0);
                     ++yn;
                 }
@@ -321,6 +328,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
             const int n_xgroups = (p.H_src + 3) >> 2;
+            const int n_cb = p.planes == 2 ? 3 : 1;
             uint32_t xn = 0, yn = 0, started = 0;
             for (int u = split; u < p.n_units; u += p.n_splits) {
                 // x groups n = 0, 1 of this atom are consumed together with n = 2 at step 0
@@ -342,6 +350,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
                         const uint32_t d_tmem = tmem_base + (uint32_t)k * 128;
 #pragma unroll
                         for (int cb = 0; cb < 3; ++cb) {                       // (x hi, dy hi) (x hi, dy lo) (x lo, dy hi)
+                            if (cb >= n_cb) break;
                             const uint64_t a_d = x_d0 + (uint64_t)(cb == 2 ? (128 * 128) >> 4 : 0);
                             const uint64_t b_d = y_d0 + (uint64_t)(cb == 1 ? (128 * 128) >> 4 : 0);
 #pragma unroll
@@ -396,30 +405,33 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
 
 // ---- host side ------------------------------------------------------------------------------------------
 static bool tall_shape_ok(const cpc_conv_params* p) {
-    return p->precision == 0 && p->kw == 1 && p->stride_h == 1 && p->stride_w == 1 && p->pad_left == 0 &&
-           p->c_in == TL_C && p->c_out == TL_C && p->kh >= 8 && p->w_out == p->w_in && p->pad_top < p->kh &&
+    return (p->precision == 0 || p->precision == 1) && p->kw == 1 && p->stride_h == 1 && p->stride_w == 1 &&
+           p->pad_left == 0 && p->c_in == TL_C && p->c_out == TL_C && p->kh >= 8 && p->w_out == p->w_in && p->pad_top < p->kh &&
            (int64_t)p->batch * ((p->w_in + 63) / 64) < (1 << 28);
 }
 bool tall_conv_eligible(const cpc_conv_params* p, int which) { (void)which; return tall_shape_ok(p); }
 
-static size_t tall_act_bytes(int B, int H, int W) {
+static int tall_planes(const cpc_conv_params* p) { return p->precision == 1 ? 1 : 2; }
+static size_t tall_act_bytes(int B, int H, int W, int planes) {
     const int Wp = (W + 7) & ~7;
-    return align_up((size_t)2 * B * TL_C * H * Wp * 2, 1024);
+    return align_up((size_t)planes * B * TL_C * H * Wp * 2, 1024);
 }
 static size_t tall_w_bytes(int kh) { return align_up((size_t)kh * TL_C * 64 * 2, 1024); }
 
 size_t tall_conv_workspace(const cpc_conv_params* p, int which) {
     if (!tall_shape_ok(p)) return 0;
-    if (which == 2) return tall_act_bytes(p->batch, p->h_in, p->w_in) + tall_act_bytes(p->batch, p->h_out, p->w_out) + 1024;
+    const int planes = tall_planes(p);
+    if (which == 2)
+        return tall_act_bytes(p->batch, p->h_in, p->w_in, planes) + tall_act_bytes(p->batch, p->h_out, p->w_out, planes) + 1024;
     const int H = which == 0 ? p->h_in : p->h_out;
-    return tall_act_bytes(p->batch, H, p->w_in) + tall_w_bytes(p->kh) + 1024;
+    return tall_act_bytes(p->batch, H, p->w_in, planes) + tall_w_bytes(p->kh) + 1024;
 }
 
-static bool tall_act_tmap(CUtensorMap* t, const void* base, int B, int H, int Wp, int box_rows) {
+static bool tall_act_tmap(CUtensorMap* t, const void* base, int B, int H, int Wp, int box_rows, int planes) {
     const uint64_t rb = (uint64_t)Wp * 2;
-    const uint64_t dims[5] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)TL_C, (uint64_t)B, 2};
+    const uint64_t dims[5] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)TL_C, (uint64_t)B, (uint64_t)planes};
     const uint64_t strides[4] = {rb, rb * H, rb * H * TL_C, rb * H * TL_C * B};
-    const uint32_t box[5] = {64, (uint32_t)box_rows, (uint32_t)TL_C, 1, 2};
+    const uint32_t box[5] = {64, (uint32_t)box_rows, (uint32_t)TL_C, 1, (uint32_t)planes};
     return make_tmap_bf16(t, base, 5, dims, strides, box);
 }
 
@@ -432,15 +444,17 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
     const int H_src = which == 0 ? p->h_in : p->h_out;
     const int H_out = which == 0 ? p->h_out : p->h_in;
     const int P = which == 0 ? p->pad_top : p->kh - 1 - p->pad_top;
+    const int planes = tall_planes(p);
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     const __nv_bfloat16* act = pre ? reinterpret_cast<const __nv_bfloat16*>(pre) : reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, H_src, W));
-    int st = pre ? CPC_OK : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * TL_C * H_src, W, Wp, 2, 1, 1, 1, 0, s);
+    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, H_src, W, planes));
+    int st = pre ? CPC_OK
+                 : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * TL_C * H_src, W, Wp, planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     tall_pack_weights_kernel<<<ceil_div(p->kh * TL_C * TL_C, 256), 256, 0, s>>>(w, wp, p->kh, which);
     CPC_LAUNCH_CHECK();
     CUtensorMap ta, tw;
-    if (!tall_act_tmap(&ta, act, B, H_src, Wp, 1)) return CPC_ERR_CUDA;
+    if (!tall_act_tmap(&ta, act, B, H_src, Wp, 1, planes)) return CPC_ERR_CUDA;
     {
         const uint64_t dims[3] = {64, (uint64_t)TL_C, (uint64_t)p->kh};
         const uint64_t strides[2] = {128, 128 * TL_C};
@@ -453,6 +467,7 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
     k.n_units = B * k.AW; k.n_pairs = (k.n_units + 1) / 2; k.n_rtiles = ceil_div(H_out, TL_R);
     k.n_tiles = k.n_pairs * k.n_rtiles;
     k.relu = which == 0 ? p->relu : 0; k.bias = which == 0 ? bias : nullptr; k.out = out;
+    k.planes = planes;
     if (cudaFuncSetAttribute(tall_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int grid = k.n_tiles < 148 ? k.n_tiles : 148;
@@ -467,22 +482,26 @@ int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv
     if (!tall_shape_ok(p)) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < tall_conv_workspace(p, 2)) return CPC_ERR_WORKSPACE;
     const int B = p->batch, W = p->w_in, Wp = (W + 7) & ~7;
+    const int planes = tall_planes(p);
+    const size_t x_bytes = tall_act_bytes(B, p->h_in, W, planes);
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     const __nv_bfloat16* xp = pre_x ? reinterpret_cast<const __nv_bfloat16*>(pre_x) : reinterpret_cast<__nv_bfloat16*>(ws);
     const __nv_bfloat16* dyp = pre_dy ? reinterpret_cast<const __nv_bfloat16*>(pre_dy)
-                                      : reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, p->h_in, W));
-    int st = pre_x ? CPC_OK : pack_split_launch(x, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * TL_C * p->h_in, W, Wp, 2, 1, 1, 1, 0, s);
+                                      : reinterpret_cast<__nv_bfloat16*>(ws + x_bytes);
+    int st = pre_x ? CPC_OK
+                   : pack_split_launch(x, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * TL_C * p->h_in, W, Wp, planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
-    st = pre_dy ? CPC_OK : pack_split_launch(dy, reinterpret_cast<__nv_bfloat16*>(ws + tall_act_bytes(B, p->h_in, W)),
-                                             (long)B * TL_C * p->h_out, W, Wp, 2, 1, 1, 1, 0, s);
+    st = pre_dy ? CPC_OK : pack_split_launch(dy, reinterpret_cast<__nv_bfloat16*>(ws + x_bytes), (long)B * TL_C * p->h_out, W, Wp,
+                                             planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     CUtensorMap tx, tdy;
-    if (!tall_act_tmap(&tx, xp, B, p->h_in, Wp, 4)) return CPC_ERR_CUDA;
-    if (!tall_act_tmap(&tdy, dyp, B, p->h_out, Wp, 4)) return CPC_ERR_CUDA;
+    if (!tall_act_tmap(&tx, xp, B, p->h_in, Wp, 4, planes)) return CPC_ERR_CUDA;
+    if (!tall_act_tmap(&tdy, dyp, B, p->h_out, Wp, 4, planes)) return CPC_ERR_CUDA;
     TallWgrad k{};
     k.B = B; k.H_src = p->h_in; k.H_out = p->h_out; k.W = W; k.AW = (W + 63) / 64; k.kh = p->kh; k.P = p->pad_top;
     k.n_units = B * k.AW;
     k.Q = (p->h_out + 3) / 4;
+    k.planes = planes;
     // blocks d with some tap 4d + P + delta - rho in [0, kh):  4d + P + 3 >= 0  and  4d + P - 3 <= kh - 1
     const int d_lo = -((k.P + 3) / 4);                                  // ceil((-3 - P) / 4)
     int d_hi = p->kh + 2 - k.P;                                          // floor((kh + 2 - P) / 4)

@@ -10,6 +10,7 @@
 //     32 KB with both bf16 planes) and weight tap (j, q) (K-major B operand, 32 KB) and issues, for every
 //     output row rho whose tap j - rho is inside the kernel, D[rho] += A_j * B_{j - rho}.  The last R taps
 //     stay resident in a 5-slot ring, so activations and weights are each read once per tile and chunk.
+//   * bf16 operand mode (cpc_conv_params.precision = 1): hi planes only (half the bytes per step), one product.
 // Weight gradient (tall128_wgrad_kernel):
 //   dW[co, ci, i] = sum_{b, r, w} dy[b, co, r, w] * x[b, ci, r - P + i, w]
 //   * K = 64-pixel chunks, both operands K-major: A = one x row (128 ci x 64 px), B = one dy row.
@@ -36,6 +37,7 @@ struct Tall128Conv {
     int B, H_src, H_out, W, AW, kh, P, NQ;
     int n_units, n_pairs, n_rtiles, n_tiles;
     int relu;
+    int planes;                              // 2: bf16 hi/lo (fp32-faithful), 1: hi plane only (bf16 operand mode)
     const float* bias;
     float* out;                              // (B, 128, H_out, W)
 };
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
     if (warp == 0) {
         if (lane == 0) {
             uint32_t v = 0;
+            const uint32_t op_bytes = p.planes == 2 ? T8_TILE : T8_TILE / 2;   // one operand tile: both planes or hi only
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 int pair, r0, j_lo, j_hi;
                 t8_tile_rows(p, tile, pair, r0, j_lo, j_hi);
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
                         const int stage = v % T8_S;
                         mbar_wait(&bars->empty[stage], ((v / T8_S) & 1) ^ 1);
                         const bool with_row = j >= j_lo;
-                        mbar_expect_tx(&bars->full[stage], T8_TILE * (with_row ? 2 : 1));
+                        mbar_expect_tx(&bars->full[stage], op_bytes * (with_row ? 2 : 1));
                         // tap j of chunk q; j outside [0, kh) addresses outside the tensor -> zero fill
                         const int tq = (j < 0 || j >= p.kh) ? -1 : j * p.NQ + q;
                         tma_load_3d(w_ring + (v % T8_T) * T8_TILE, &tmap_w, &bars->full[stage], 0, 0, tq);
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, T8_N, /*A MN-major*/ 1, /*B K-major*/ 0);
             const uint32_t w_base = smem_u32(w_ring);
+            const int n_cb = p.planes == 2 ? 3 : 1;
             uint32_t v = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 int pair, r0, j_lo, j_hi;
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
                                 const uint32_t d_tmem = tmem_base + (uint32_t)rho * T8_N;
 #pragma unroll
                                 for (int cb = 0; cb < 3; ++cb) {               // (hi,hi) (hi,lo) (lo,hi)
+                                    if (cb >= n_cb) break;
                                     const uint64_t a_d = a_d0 + (uint64_t)(cb == 2 ? (64 * 128) >> 4 : 0);
                                     const uint64_t b_d = b_d0 + (uint64_t)(cb == 1 ? (T8_N * 128) >> 4 : 0);
 #pragma unroll
@@ -240,6 +245,7 @@ constexpr int T8W_SMEM = (T8W_XS + T8W_YS) * T8_TILE + 1024 + 256;
 struct Tall128Wgrad {
     int B, H_src, H_out, W, AW, kh, P;
     int n_units, n_splits, n_tgroups;
+    int planes;
     float* dw;                               // (128, 128, kh) fp32, zero-initialised
 };
 
@@ -280,13 +286,14 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_wgrad_kernel(const __gr
     if (warp == 0) {
         if (lane == 0) {
             uint32_t xn = 0, yn = 0;
+            const uint32_t op_bytes = p.planes == 2 ? T8_TILE : T8_TILE / 2;
             for (int u = split; u < p.n_units; u += p.n_splits) {
                 const int b = u / p.AW, w0 = (u - b * p.AW) * 64;
                 for (int n = 0; n < n_rows; ++n) {
                     {   // x row n
                         const int slot = xn % T8W_XS;
                         mbar_wait(&bars->xempty[slot], ((xn / T8W_XS) & 1) ^ 1);
-                        mbar_expect_tx(&bars->xfull[slot], T8_TILE);
+                        mbar_expect_tx(&bars->xfull[slot], op_bytes);
                         tma_load_5d(x_ring + slot * T8_TILE, &tmap_x, &bars->xfull[slot], w0, n - p.P + i0, 0, b, 0);
                         ++xn;
                     }
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_wgrad_kernel(const __gr
                     if (r >= 0) {
                         const int slot = yn % T8W_YS;
                         mbar_wait(&bars->yempty[slot], ((yn / T8W_YS) & 1) ^ 1);
-                        mbar_expect_tx(&bars->yfull[slot], T8_TILE);
+                        mbar_expect_tx(&bars->yfull[slot], op_bytes);
                         tma_load_5d(y_ring + slot * T8_TILE, &tmap_dy, &bars->yfull[slot], w0, r, 0, b, 0);
                         ++yn;
                     }
@@ -304,6 +311,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_wgrad_kernel(const __gr
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, T8_N, 0, 0);
+            const int n_cb = p.planes == 2 ? 3 : 1;
             uint32_t xn = 0, yn = 0, started = 0;
             for (int u = split; u < p.n_units; u += p.n_splits) {
                 for (int n = 0; n < n_rows; ++n, ++xn) {
@@ -322,6 +330,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_wgrad_kernel(const __gr
                             const uint32_t d_tmem = tmem_base + (uint32_t)k * T8_N;
 #pragma unroll
                             for (int cb = 0; cb < 3; ++cb) {                   // (x hi, dy hi) (x hi, dy lo) (x lo, dy hi)
+                                if (cb >= n_cb) break;
                                 const uint64_t a_d = x_d0 + (uint64_t)(cb == 2 ? (128 * 128) >> 4 : 0);
                                 const uint64_t b_d = y_d0 + (uint64_t)(cb == 1 ? (128 * 128) >> 4 : 0);
 #pragma unroll
@@ -370,7 +379,8 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_wgrad_kernel(const __gr
 
 // ---- host side --------------------------------------------------------------------------------------------
 static bool t8_common(const cpc_conv_params* p) {
-    return p->precision == 0 && p->kw == 1 && p->stride_h == 1 && p->stride_w == 1 && p->pad_left == 0 && p->kh >= 4 &&
+    return (p->precision == 0 || p->precision == 1) && p->kw == 1 && p->stride_h == 1 && p->stride_w == 1 &&
+           p->pad_left == 0 && p->kh >= 4 &&
            p->w_out == p->w_in && p->pad_top < p->kh && (int64_t)p->batch * ((p->w_in + 63) / 64) < (1 << 28);
 }
 bool tall128_eligible(const cpc_conv_params* p, int which) {
@@ -380,25 +390,28 @@ bool tall128_eligible(const cpc_conv_params* p, int which) {
     return p->c_in == T8_N && p->c_out == T8_N;
 }
 
-static size_t t8_act_bytes(int B, int C, int H, int W) {
+static int t8_planes(const cpc_conv_params* p) { return p->precision == 1 ? 1 : 2; }
+static size_t t8_act_bytes(int B, int C, int H, int W, int planes) {
     const int Wp = (W + 7) & ~7;
-    return align_up((size_t)2 * B * C * H * Wp * 2, 1024);
+    return align_up((size_t)planes * B * C * H * Wp * 2, 1024);
 }
 static size_t t8_w_bytes(int kh, int C) { return align_up((size_t)kh * (C / 64) * 2 * T8_N * 64 * 2, 1024); }
 
 size_t tall128_workspace(const cpc_conv_params* p, int which) {
     if (!tall128_eligible(p, which)) return 0;
+    const int planes = t8_planes(p);
     if (which == 2)
-        return t8_act_bytes(p->batch, p->c_in, p->h_in, p->w_in) + t8_act_bytes(p->batch, p->c_out, p->h_out, p->w_out) + 1024;
+        return t8_act_bytes(p->batch, p->c_in, p->h_in, p->w_in, planes) +
+               t8_act_bytes(p->batch, p->c_out, p->h_out, p->w_out, planes) + 1024;
     const int C = which == 0 ? p->c_in : p->c_out, H = which == 0 ? p->h_in : p->h_out;
-    return t8_act_bytes(p->batch, C, H, p->w_in) + t8_w_bytes(p->kh, C) + 1024;
+    return t8_act_bytes(p->batch, C, H, p->w_in, planes) + t8_w_bytes(p->kh, C) + 1024;
 }
 
-static bool t8_act_tmap(CUtensorMap* t, const void* base, int B, int C, int H, int Wp, int box_c) {
+static bool t8_act_tmap(CUtensorMap* t, const void* base, int B, int C, int H, int Wp, int box_c, int planes) {
     const uint64_t rb = (uint64_t)Wp * 2;
-    const uint64_t dims[5] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)C, (uint64_t)B, 2};
+    const uint64_t dims[5] = {(uint64_t)Wp, (uint64_t)H, (uint64_t)C, (uint64_t)B, (uint64_t)planes};
     const uint64_t strides[4] = {rb, rb * H, rb * H * C, rb * H * C * B};
-    const uint32_t box[5] = {64, 1, (uint32_t)box_c, 1, 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)box_c, 1, (uint32_t)planes};
     return make_tmap_bf16(t, base, 5, dims, strides, box);
 }
 
@@ -411,10 +424,12 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
     const int H_src = which == 0 ? p->h_in : p->h_out;
     const int H_out = which == 0 ? p->h_out : p->h_in;
     const int P = which == 0 ? p->pad_top : p->kh - 1 - p->pad_top;
+    const int planes = t8_planes(p);
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     const __nv_bfloat16* act = pre ? reinterpret_cast<const __nv_bfloat16*>(pre) : reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, C, H_src, W));
-    int st = pre ? CPC_OK : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * C * H_src, W, Wp, 2, 1, 1, 1, 0, s);
+    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, C, H_src, W, planes));
+    int st = pre ? CPC_OK
+                 : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * C * H_src, W, Wp, planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     {
         const long total = (long)p->kh * (C / 64) * T8_N * 64;
@@ -424,12 +439,12 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
         CPC_LAUNCH_CHECK();
     }
     CUtensorMap ta, tw;
-    if (!t8_act_tmap(&ta, act, B, C, H_src, Wp, 64)) return CPC_ERR_CUDA;
+    if (!t8_act_tmap(&ta, act, B, C, H_src, Wp, 64, planes)) return CPC_ERR_CUDA;
     {
         const uint64_t n_tq = (uint64_t)p->kh * (C / 64);
         const uint64_t dims[3] = {64, 2 * T8_N, n_tq};
         const uint64_t strides[2] = {128, 128 * 2 * T8_N};
-        const uint32_t box[3] = {64, 2 * T8_N, 1};
+        const uint32_t box[3] = {64, (uint32_t)(planes * T8_N), 1};      // bf16 operand mode: the hi rows of a tap only
         if (!make_tmap_bf16(&tw, wp, 3, dims, strides, box)) return CPC_ERR_CUDA;
     }
     Tall128Conv k{};
@@ -437,6 +452,7 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
     k.n_units = B * k.AW; k.n_pairs = (k.n_units + 1) / 2; k.n_rtiles = ceil_div(H_out, T8_R);
     k.n_tiles = k.n_pairs * k.n_rtiles;
     k.relu = which == 0 ? p->relu : 0; k.bias = which == 0 ? bias : nullptr; k.out = out;
+    k.planes = planes;
     if (cudaFuncSetAttribute(tall128_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int grid = k.n_tiles < 148 ? k.n_tiles : 148;
@@ -451,21 +467,25 @@ int tall128_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_c
     if (!tall128_eligible(p, 2)) return CPC_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < tall128_workspace(p, 2)) return CPC_ERR_WORKSPACE;
     const int B = p->batch, W = p->w_in, Wp = (W + 7) & ~7;
+    const int planes = t8_planes(p);
+    const size_t x_bytes = t8_act_bytes(B, T8_N, p->h_in, W, planes);
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     const __nv_bfloat16* xp = pre_x ? reinterpret_cast<const __nv_bfloat16*>(pre_x) : reinterpret_cast<__nv_bfloat16*>(ws);
     const __nv_bfloat16* dyp = pre_dy ? reinterpret_cast<const __nv_bfloat16*>(pre_dy)
-                                      : reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, T8_N, p->h_in, W));
-    int st = pre_x ? CPC_OK : pack_split_launch(x, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * T8_N * p->h_in, W, Wp, 2, 1, 1, 1, 0, s);
+                                      : reinterpret_cast<__nv_bfloat16*>(ws + x_bytes);
+    int st = pre_x ? CPC_OK
+                   : pack_split_launch(x, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * T8_N * p->h_in, W, Wp, planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
-    st = pre_dy ? CPC_OK : pack_split_launch(dy, reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, T8_N, p->h_in, W)),
-                                             (long)B * T8_N * p->h_out, W, Wp, 2, 1, 1, 1, 0, s);
+    st = pre_dy ? CPC_OK : pack_split_launch(dy, reinterpret_cast<__nv_bfloat16*>(ws + x_bytes), (long)B * T8_N * p->h_out, W, Wp,
+                                             planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
     CUtensorMap tx, tdy;
-    if (!t8_act_tmap(&tx, xp, B, T8_N, p->h_in, Wp, T8_N)) return CPC_ERR_CUDA;
-    if (!t8_act_tmap(&tdy, dyp, B, T8_N, p->h_out, Wp, T8_N)) return CPC_ERR_CUDA;
+    if (!t8_act_tmap(&tx, xp, B, T8_N, p->h_in, Wp, T8_N, planes)) return CPC_ERR_CUDA;
+    if (!t8_act_tmap(&tdy, dyp, B, T8_N, p->h_out, Wp, T8_N, planes)) return CPC_ERR_CUDA;
     Tall128Wgrad k{};
     k.B = B; k.H_src = p->h_in; k.H_out = p->h_out; k.W = W; k.AW = (W + 63) / 64; k.kh = p->kh; k.P = p->pad_top;
     k.n_units = B * k.AW;
+    k.planes = planes;
     k.n_tgroups = ceil_div(p->kh, T8W_NT);
     k.n_splits = 148 / k.n_tgroups;
     if (k.n_splits < 1) k.n_splits = 1;

@@ -190,6 +190,8 @@ typedef struct cpc_bn_params {
     int32_t training;                /* 1: batch statistics, running stats updated (nn.BatchNorm2d.train());
                                         0: running statistics (eval())                                     */
     float eps, momentum;
+    int32_t packed_planes;           /* *_packed variants only: 0 or 2 = bf16 hi + lo planes (operands of an fp32-faithful
+                                        conv, precision 0); 1 = the hi plane only (operand of a precision-1 conv)     */
 } cpc_bn_params;
 
 size_t cpc_bn_relu_workspace_bytes(const cpc_bn_params* p);

@@ -1240,10 +1240,21 @@ def test_e24_full_size_training_steps_match_reference_golden(cpc, graphed):
     dict(cin=32, cout=128, k2=(4, 1), top=3, residual=True, hw=(21, 133), outer=False),
     dict(cin=32, cout=32, k2=(9, 1), top=8, residual=True, hw=(41, 75), outer=True, node=False),   # odd width: unfused chain
 ])
-def test_block_tail_node_matches_literal_modules(cpc, cfg):
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_block_tail_node_matches_literal_modules(cpc, cfg, precision):
     """ScalogramEncoderBlock whose second conv runs on the row-streaming kernels: the single block-tail node (packed
     activations between bn_a and conv_b, packed dy between bn_b and conv_b) against the same block evaluated module by
-    module (torch BatchNorm / ReLU, conv Functions) -- output, running statistics and every gradient."""
+    module (torch BatchNorm / ReLU, conv Functions) -- output, running statistics and every gradient.  In the bf16
+    operand mode the node hands over the hi plane only; the literal chain rounds the same fp32 values to bf16 inside
+    the conv calls, so the two agree far inside the mode's stated 1e-2 (bound here: 3e-3)."""
+    cpc.ops.set_default_precision(precision)
+    try:
+        _block_tail_case(cpc, cfg, *((1e-4, TOL) if precision == "fp32" else (3e-3, 3e-3)))
+    finally:
+        cpc.ops.set_default_precision("fp32")
+
+
+def _block_tail_case(cpc, cfg, out_tol, grad_tol):
     import copy
     block_cfg = {'in_channels': cfg['cin'], 'hidden_channels': None, 'out_channels': cfg['cout'], 'kernel_size_1': (3, 3),
                  'kernel_size_2': cfg['k2'], 'top_padding_1': None, 'top_padding_2': cfg['top'], 'padding_1': 0,
@@ -1265,19 +1276,19 @@ def test_block_tail_node_matches_literal_modules(cpc, cfg):
     assert type(y.grad_fn).__name__.startswith("_BlockTailFunction") == cfg.get('node', True), type(y.grad_fn).__name__
     with cpc.ops.second_order():                                   # literal module sequence
         y_ref = ref_block(x2, outer_relu=cfg['outer'])
-    assert rel_err(y, y_ref) < 1e-4
+    assert rel_err(y, y_ref) < out_tol
     gy = torch.randn(y.shape, generator=gen).to(DEV)
     (y * gy).sum().backward()
     (y_ref * gy).sum().backward()
-    assert rel_err(x1.grad, x2.grad) < TOL
+    assert rel_err(x1.grad, x2.grad) < grad_tol
     noise_only = bn_shadowed_biases(block.state_dict().keys())
     for (n, p), (_, q) in zip(block.named_parameters(), ref_block.named_parameters()):
         if n in noise_only:
             assert float((p.grad - q.grad).abs().max()) < 1e-3 * float(gy.abs().sum()) ** 0.5, n   # both are rounding noise
         else:
-            assert grad_err(p.grad, q.grad) < TOL, n
+            assert grad_err(p.grad, q.grad) < grad_tol, n
     for (n, b), (_, c) in zip(block.named_buffers(), ref_block.named_buffers()):
-        assert rel_err(b.float(), c.float()) < 1e-4, n
+        assert rel_err(b.float(), c.float()) < out_tol, n
     # eval mode (validate()): running statistics, no autograd
     block.eval()
     ref_block.eval()
@@ -1285,7 +1296,7 @@ def test_block_tail_node_matches_literal_modules(cpc, cfg):
         y_eval = block(x, outer_relu=cfg['outer'])
         with cpc.ops.second_order():
             y_eval_ref = ref_block(x, outer_relu=cfg['outer'])
-    assert rel_err(y_eval, y_eval_ref) < 1e-4
+    assert rel_err(y_eval, y_eval_ref) < out_tol
 
 
 def test_activation_taps_receive_intermediates_and_match_the_fused_path(cpc):

@@ -49,6 +49,11 @@ def test_abi_rejects_bad_arguments_before_touching_the_device(built_lib):
     b = _lib.BnParams()
     b.batch, b.channels, b.height, b.width, b.eps, b.training = 2, 3, 4, 6, 1e-5, 1
     assert lib.cpc_bn_packed_bytes(ctypes.byref(b)) == 2 * 2 * 3 * 4 * 8 * 2                   # two planes, pitch 8, bf16
+    b.packed_planes = 1                                                                      # operand of a bf16-mode conv
+    assert lib.cpc_bn_packed_bytes(ctypes.byref(b)) == 2 * 3 * 4 * 8 * 2
+    b.packed_planes = 3
+    assert lib.cpc_bn_packed_bytes(ctypes.byref(b)) == 0                                       # rejected by validation
+    b.packed_planes = 0
     assert lib.cpc_bn_relu_fwd_packed(*([None] * 9), ctypes.byref(b), None, 0, None) == -7     # null pointers
     assert lib.cpc_bn_relu_bwd_packed(*([None] * 12), ctypes.byref(b), None, 0, None) == -7
     b.width = 0
@@ -111,8 +116,10 @@ def test_conv_dispatch_table_for_the_baseline_layers(built_lib):
         assert lib.cpc_conv_workspace_bytes(ctypes.byref(p), 1) >= 0
     # bf16 mode and the CUDA-core override change the answer
     p = table["block0 conv_b"][0]
-    p.precision = 1
-    assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 4                   # row-streaming kernels are fp32-faithful only
+    p.precision = 1                                                              # bf16 operand mode: same kernels, hi plane only
+    assert [lib.cpc_conv_kernel_family(ctypes.byref(p), which) for which in (0, 1, 2)] == [2, 2, 2]
+    rows = 64 * p.c_out * p.h_out
+    assert lib.cpc_conv_packed_bytes(ctypes.byref(p), 1) == (rows * round8(p.w_out) * 2 + 1023) // 1024 * 1024
     p.precision = 0
     p.flags = _lib.CONV_FLAG_CUDA_CORE                                           # per-call switch in the struct: no global state
     assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 0

@@ -4,11 +4,14 @@ Same public surface as audio_model.py:164-284 of the reference.  The composition
 (slicing, one Linear = the K stacked predictors W_k); the encoder inside runs on the B200 kernels and the
 autoregressive model is whatever ``nn.Module`` the caller plugs in.
 """
+import contextlib
 from collections import OrderedDict
 
 import numpy as np
 import torch
 import torch.nn as nn
+
+from . import ops
 
 
 class ActivationRegister:
@@ -109,12 +112,19 @@ class AudioPredictiveCodingModel(nn.Module):
         k, v = self.prediction_steps, self.visible_steps
         targets = code[:, :, -k:]
         z = self.z_activation_writer(code[:, :, -(v + k):-k])
-        c = self.autoregressive_model(z)
-        if c.dim() == 3:
-            c = c[:, :, 0]
+        # bf16 operand mode (ops.set_default_precision("bf16"), BASELINE configs[2]): the stock-PyTorch parts -- the AR
+        # model and the predictors W_k -- run under bf16 autocast (library GEMMs with bf16 operands and fp32 accumulation,
+        # softmax / layer norm in fp32), like the conv kernels of that mode; results return to fp32 for the scoring.
+        bf16 = z.is_cuda and ops.get_default_precision() == "bf16"
+        with (torch.autocast("cuda", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()):
+            c = self.autoregressive_model(z)
+            if c.dim() == 3:
+                c = c[:, :, 0]
+            predicted_z = self.prediction_model(c)
+        if bf16:
+            c, predicted_z = c.float(), predicted_z.float()
         c = self.c_activation_writer(c)
-        predicted_z = self.prediction_model(c).view(-1, k, self.enc_size)
-        predicted_z = self.prediction_activation_writer(predicted_z)
+        predicted_z = self.prediction_activation_writer(predicted_z.view(-1, k, self.enc_size))
         return predicted_z, targets, z, c
 
     def parameter_count(self):

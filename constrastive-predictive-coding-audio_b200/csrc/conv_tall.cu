@@ -18,6 +18,10 @@
 //   * fp32-faithful arithmetic = bf16 hi/lo split, products hi*hi + hi*lo + lo*hi (both planes of a
 //     weight row share one 128-byte swizzle row: [hi c0..31 | lo c0..31]).
 //   * the data gradient is the same kernel on dy with channel roles swapped and taps flipped.
+//   * tiles are handed out by an atomic counter (zeroed by the weight-packing kernel that precedes the launch): the cost
+//     of a tile depends on how many of its taps fall into the zero padding (31 ... 94 steps in arch-7 block 0), a static
+//     round-robin gave some CTAs only cheap and others only expensive tiles (83 % balance), and a CTA that starts late
+//     because another kernel (an NCCL all-reduce on the communication stream) holds its SM simply takes fewer tiles.
 //   * bf16 operand mode (cpc_conv_params.precision = 1): the activation operand has its hi plane only (half the
 //     bytes per row) and one product, hi*hi, is issued instead of three.
 // Weight gradient (tall_wgrad_kernel):
@@ -51,12 +55,16 @@ struct TallConv {
     int n_units, n_pairs, n_rtiles, n_tiles;
     int relu;
     int planes;                              // 2: bf16 hi/lo (fp32-faithful), 1: hi plane only (bf16 operand mode)
+    int rt_rev;                              // row tiles of a pixel pair are handed out bottom-up (expensive ones first)
     const float* bias;
     float* out;                              // (B, 32, H_out, W) fp32
+    int* counter;                            // tile scheduler (workspace; zero at launch)
 };
 
 struct __align__(8) TallBarriers {
     uint64_t full[TL_S], empty[TL_S], acc_full, acc_empty;
+    uint64_t sfull[2], sempty[2];            // tile-id queue: scheduler (producer lane) -> MMA warp + 4 epilogue warps
+    int tile_id[2];
     uint32_t tmem_base;
 };
 
@@ -64,7 +72,8 @@ struct __align__(8) TallBarriers {
 //   flip_swap = 0: n = co, c = ci, tap = i            (forward)
 //   flip_swap = 1: n = ci, c = co, tap = kh - 1 - i   (data gradient)
 __global__ void __launch_bounds__(256) tall_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                               int kh, int flip_swap) {
+                                                               int kh, int flip_swap, int* __restrict__ counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;        // tile scheduler of the conv kernel that follows
     const int total = kh * TL_C * TL_C;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int c = idx % TL_C;
@@ -82,7 +91,8 @@ __global__ void __launch_bounds__(256) tall_pack_weights_kernel(const float* __r
 
 __device__ __forceinline__ void tall_tile_rows(const TallConv& p, int tile, int& pair, int& r0, int& j_lo, int& j_hi) {
     pair = tile / p.n_rtiles;
-    r0 = (tile - pair * p.n_rtiles) * TL_R;
+    const int rt = tile - pair * p.n_rtiles;
+    r0 = (p.rt_rev ? p.n_rtiles - 1 - rt : rt) * TL_R;
     j_lo = max(0, p.P - r0);
     j_hi = min(TL_R + p.kh - 1, p.H_src + p.P - r0);
     if (j_hi < j_lo) j_hi = j_lo;
@@ -104,6 +114,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
         for (int s = 0; s < TL_S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->acc_full, 1);
         mbar_init(&bars->acc_empty, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->sfull[s], 1); mbar_init(&bars->sempty[s], 5); }
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
@@ -113,10 +124,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer: one step = (weight tap j, optionally input row j) =====
+        // ===== tile scheduler + TMA producer: one step = (weight tap j, optionally input row j) =====
         if (lane == 0) {
             uint32_t v = 0;                                   // running step counter -> stage and tap slot
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (uint32_t ti = 0;; ++ti) {
+                const int tile = sched_push(bars, ti, p.counter, p.n_tiles);
+                if (tile < 0) break;
                 int pair, r0, j_lo, j_hi;
                 tall_tile_rows(p, tile, pair, r0, j_lo, j_hi);
                 if (j_hi == j_lo) continue;                   // no input row inside the source: bias-only tile
@@ -151,7 +164,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
             const uint32_t idesc = make_idesc_bf16(128, 128, /*A MN-major*/ 1, /*B K-major*/ 0);
             const uint32_t w_base = smem_u32(w_ring);
             uint32_t v = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (uint32_t ti = 0;; ++ti) {
+                const int tile = sched_pop(bars, ti, lane);
+                if (tile < 0) break;
                 int pair, r0, j_lo, j_hi;
                 tall_tile_rows(p, tile, pair, r0, j_lo, j_hi);
                 if (j_hi == j_lo) continue;
@@ -202,7 +217,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_conv_kernel(const __grid_c
         const int ew = warp & 3;
         const int r = ew * 32 + lane;                                          // tile pixel
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (uint32_t ti = 0;; ++ti) {
+            const int tile = sched_pop(bars, ti, lane);
+            if (tile < 0) break;
             int pair, r0, j_lo, j_hi;
             tall_tile_rows(p, tile, pair, r0, j_lo, j_hi);
             const int u = pair * 2 + (r >> 6);
@@ -424,7 +441,7 @@ size_t tall_conv_workspace(const cpc_conv_params* p, int which) {
     if (which == 2)
         return tall_act_bytes(p->batch, p->h_in, p->w_in, planes) + tall_act_bytes(p->batch, p->h_out, p->w_out, planes) + 1024;
     const int H = which == 0 ? p->h_in : p->h_out;
-    return tall_act_bytes(p->batch, H, p->w_in, planes) + tall_w_bytes(p->kh) + 1024;
+    return tall_act_bytes(p->batch, H, p->w_in, planes) + tall_w_bytes(p->kh) + 256 + 1024;   // + tile counter
 }
 
 static bool tall_act_tmap(CUtensorMap* t, const void* base, int B, int H, int Wp, int box_rows, int planes) {
@@ -451,7 +468,8 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
     int st = pre ? CPC_OK
                  : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * TL_C * H_src, W, Wp, planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
-    tall_pack_weights_kernel<<<ceil_div(p->kh * TL_C * TL_C, 256), 256, 0, s>>>(w, wp, p->kh, which);
+    int* counter = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(wp) + tall_w_bytes(p->kh));
+    tall_pack_weights_kernel<<<ceil_div(p->kh * TL_C * TL_C, 256), 256, 0, s>>>(w, wp, p->kh, which, counter);
     CPC_LAUNCH_CHECK();
     CUtensorMap ta, tw;
     if (!tall_act_tmap(&ta, act, B, H_src, Wp, 1, planes)) return CPC_ERR_CUDA;
@@ -468,6 +486,17 @@ int tall_conv_launch(const float* in, const float* w, const float* bias, float* 
     k.n_tiles = k.n_pairs * k.n_rtiles;
     k.relu = which == 0 ? p->relu : 0; k.bias = which == 0 ? bias : nullptr; k.out = out;
     k.planes = planes;
+    k.counter = counter;
+    {
+        // steps of the first and the last row tile of a pair (tall_tile_rows): the cheaper end goes last, so that the
+        // tiles still running when the counter runs out are short ones
+        auto steps = [&](int r0) {
+            const int j_lo = P - r0 > 0 ? P - r0 : 0;
+            const int j_hi = TL_R + p->kh - 1 < H_src + P - r0 ? TL_R + p->kh - 1 : H_src + P - r0;
+            return j_hi > j_lo ? j_hi - j_lo + TL_R - 1 : 0;
+        };
+        k.rt_rev = steps(0) < steps((k.n_rtiles - 1) * TL_R) ? 1 : 0;
+    }
     if (cudaFuncSetAttribute(tall_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int grid = k.n_tiles < 148 ? k.n_tiles : 148;

@@ -10,6 +10,7 @@
 //     32 KB with both bf16 planes) and weight tap (j, q) (K-major B operand, 32 KB) and issues, for every
 //     output row rho whose tap j - rho is inside the kernel, D[rho] += A_j * B_{j - rho}.  The last R taps
 //     stay resident in a 5-slot ring, so activations and weights are each read once per tile and chunk.
+//   * tiles come from an atomic counter (conv_tall.cu explains why); the weight-packing kernel zeroes it.
 //   * bf16 operand mode (cpc_conv_params.precision = 1): hi planes only (half the bytes per step), one product.
 // Weight gradient (tall128_wgrad_kernel):
 //   dW[co, ci, i] = sum_{b, r, w} dy[b, co, r, w] * x[b, ci, r - P + i, w]
@@ -40,10 +41,13 @@ struct Tall128Conv {
     int planes;                              // 2: bf16 hi/lo (fp32-faithful), 1: hi plane only (bf16 operand mode)
     const float* bias;
     float* out;                              // (B, 128, H_out, W)
+    int* counter;                            // tile scheduler (workspace; zero at launch)
 };
 
 struct __align__(8) Tall128Barriers {
     uint64_t full[T8_S], empty[T8_S], acc_full, acc_empty;
+    uint64_t sfull[2], sempty[2];            // tile-id queue (umma.cuh: sched_push / sched_pop)
+    int tile_id[2];
     uint32_t tmem_base;
 };
 
@@ -51,7 +55,8 @@ struct __align__(8) Tall128Barriers {
 //   flip_swap = 0: n = co, c = ci, tap = i;   1: n = ci, c = co, tap = kh - 1 - i
 __global__ void __launch_bounds__(256) tall128_pack_weights_kernel(const float* __restrict__ w,
                                                                   __nv_bfloat16* __restrict__ out, int Cin, int kh, int C,
-                                                                  int flip_swap) {
+                                                                  int flip_swap, int* __restrict__ counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;        // tile scheduler of the conv kernel that follows
     const int NQ = C >> 6;
     const long total = (long)kh * NQ * T8_N * 64;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -94,6 +99,7 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
         for (int s = 0; s < T8_S; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->acc_full, 1);
         mbar_init(&bars->acc_empty, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars->sfull[s], 1); mbar_init(&bars->sempty[s], 5); }
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
@@ -106,7 +112,9 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
         if (lane == 0) {
             uint32_t v = 0;
             const uint32_t op_bytes = p.planes == 2 ? T8_TILE : T8_TILE / 2;   // one operand tile: both planes or hi only
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (uint32_t ti = 0;; ++ti) {
+                const int tile = sched_push(bars, ti, p.counter, p.n_tiles);
+                if (tile < 0) break;
                 int pair, r0, j_lo, j_hi;
                 t8_tile_rows(p, tile, pair, r0, j_lo, j_hi);
                 if (j_hi == j_lo) continue;
@@ -140,7 +148,9 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
             const uint32_t w_base = smem_u32(w_ring);
             const int n_cb = p.planes == 2 ? 3 : 1;
             uint32_t v = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (uint32_t ti = 0;; ++ti) {
+                const int tile = sched_pop_thread(bars, ti);          // this role is a single thread
+                if (tile < 0) break;
                 int pair, r0, j_lo, j_hi;
                 t8_tile_rows(p, tile, pair, r0, j_lo, j_hi);
                 if (j_hi == j_lo) continue;
@@ -184,7 +194,9 @@ __global__ void __launch_bounds__(T8_THREADS, 1) tall128_conv_kernel(const __gri
         const int ew = warp & 3;
         const int r = ew * 32 + lane;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (uint32_t ti = 0;; ++ti) {
+            const int tile = sched_pop(bars, ti, lane);
+            if (tile < 0) break;
             int pair, r0, j_lo, j_hi;
             t8_tile_rows(p, tile, pair, r0, j_lo, j_hi);
             const int u = pair * 2 + (r >> 6);
@@ -404,7 +416,7 @@ size_t tall128_workspace(const cpc_conv_params* p, int which) {
         return t8_act_bytes(p->batch, p->c_in, p->h_in, p->w_in, planes) +
                t8_act_bytes(p->batch, p->c_out, p->h_out, p->w_out, planes) + 1024;
     const int C = which == 0 ? p->c_in : p->c_out, H = which == 0 ? p->h_in : p->h_out;
-    return t8_act_bytes(p->batch, C, H, p->w_in, planes) + t8_w_bytes(p->kh, C) + 1024;
+    return t8_act_bytes(p->batch, C, H, p->w_in, planes) + t8_w_bytes(p->kh, C) + 256 + 1024;   // + tile counter
 }
 
 static bool t8_act_tmap(CUtensorMap* t, const void* base, int B, int C, int H, int Wp, int box_c, int planes) {
@@ -428,6 +440,7 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     const __nv_bfloat16* act = pre ? reinterpret_cast<const __nv_bfloat16*>(pre) : reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(ws + t8_act_bytes(B, C, H_src, W, planes));
+    int* counter = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(wp) + t8_w_bytes(p->kh, C));
     int st = pre ? CPC_OK
                  : pack_split_launch(in, reinterpret_cast<__nv_bfloat16*>(ws), (long)B * C * H_src, W, Wp, planes, 1, 1, 1, 0, s);
     if (st != CPC_OK) return st;
@@ -435,7 +448,7 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
         const long total = (long)p->kh * (C / 64) * T8_N * 64;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        tall128_pack_weights_kernel<<<blocks, 256, 0, s>>>(w, wp, p->c_in, p->kh, C, which);
+        tall128_pack_weights_kernel<<<blocks, 256, 0, s>>>(w, wp, p->c_in, p->kh, C, which, counter);
         CPC_LAUNCH_CHECK();
     }
     CUtensorMap ta, tw;
@@ -453,6 +466,7 @@ int tall128_conv_launch(const float* in, const float* w, const float* bias, floa
     k.n_tiles = k.n_pairs * k.n_rtiles;
     k.relu = which == 0 ? p->relu : 0; k.bias = which == 0 ? bias : nullptr; k.out = out;
     k.planes = planes;
+    k.counter = counter;
     if (cudaFuncSetAttribute(tall128_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM) != cudaSuccess)
         return CPC_ERR_CUDA;
     const int grid = k.n_tiles < 148 ? k.n_tiles : 148;

@@ -176,5 +176,40 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const u
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- dynamic tile scheduling of a persistent kernel -----------------------------------------------------------------
+// A two-entry queue in shared memory: `sfull[2]` (count 1), `sempty[2]` (count = number of consumer warps), `tile_id[2]`.
+// One scheduler thread takes tile numbers from a global counter that is zero at launch; every consumer warp reads each
+// entry.  -1 ends the kernel.
+// Scheduler side (one thread): next tile from the global counter, -1 when the work is used up.
+template <class Bars>
+__device__ __forceinline__ int sched_push(Bars* bars, uint32_t i, int* counter, int n_tiles) {
+    const int slot = i & 1;
+    mbar_wait(&bars->sempty[slot], ((i >> 1) & 1) ^ 1);
+    int tile = atomicAdd(counter, 1);
+    if (tile >= n_tiles) tile = -1;
+    bars->tile_id[slot] = tile;
+    mbar_arrive(&bars->sfull[slot]);
+    return tile;
+}
+// Consumer side (a whole warp): reads entry i and releases its slot.
+template <class Bars>
+__device__ __forceinline__ int sched_pop(Bars* bars, uint32_t i, int lane) {
+    const int slot = i & 1;
+    mbar_wait(&bars->sfull[slot], (i >> 1) & 1);
+    const int tile = *reinterpret_cast<volatile int*>(&bars->tile_id[slot]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars->sempty[slot]);
+    return tile;
+}
+// The same for a consumer role that is a single thread.
+template <class Bars>
+__device__ __forceinline__ int sched_pop_thread(Bars* bars, uint32_t i) {
+    const int slot = i & 1;
+    mbar_wait(&bars->sfull[slot], (i >> 1) & 1);
+    const int tile = *reinterpret_cast<volatile int*>(&bars->tile_id[slot]);
+    mbar_arrive(&bars->sempty[slot]);
+    return tile;
+}
+
 }  // namespace umma
 }  // namespace cpc

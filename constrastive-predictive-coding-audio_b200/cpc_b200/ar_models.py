@@ -11,6 +11,7 @@ On a B200 the conv1d and pooling layers of the convolutional AR model (``ArConv1
 kernels in fp32 arithmetic; the modules, parameters and state_dict keys are the stock ones.
 """
 import math
+import warnings
 
 import torch
 import torch.nn as nn
@@ -59,18 +60,41 @@ class ArMaxPool1d(nn.MaxPool1d):
 
 
 class AudioGRUModel(nn.Module):
-    """GRUCell unrolled over the visible steps; input (batch, input_size, steps) -> last hidden state."""
+    """GRUCell unrolled over the visible steps; input (batch, input_size, steps) -> last hidden state
+    (audio_model.py:47-77).  The parameters are the stock ``nn.GRUCell``'s (state_dict keys ``gruCell.*``).
+
+    On a CUDA device the recurrence runs as ONE fused library call over the whole sequence (``torch._VF.gru`` = cuDNN's GRU,
+    the same gate equations as ``nn.GRUCell``: r, z, n with ``n = tanh(W_in x + b_in + r * (W_hn h + b_hn))``) instead of
+    ``steps`` cell launches forward and ~8 x ``steps`` backward: the raw-wave configuration (BASELINE configs[0], 100
+    steps) was bound by exactly those launches.  The unrolled loop remains for CPU tensors and for second-order autograd
+    (cuDNN's RNN backward is not differentiable again); ``fused`` = True / False forces one path (tests)."""
 
     def __init__(self, input_size, hidden_size, bias=True, reset_hidden=True):
         super().__init__()
         self.gruCell = nn.GRUCell(input_size=input_size, hidden_size=hidden_size, bias=bias)
         self.hidden = None
         self.reset_hidden = reset_hidden
+        self.fused = None                                        # None: fused on CUDA outside second-order mode
+
+    def _use_fused(self, input):
+        if self.fused is not None:
+            return bool(self.fused)
+        return input.is_cuda and not ops.second_order_enabled()
 
     def forward(self, input):
         state = None if self.reset_hidden else self.hidden
-        for frame in input.unbind(dim=2):
-            state = self.gruCell(frame, state)
+        if self._use_fused(input):
+            cell = self.gruCell
+            weights = [cell.weight_ih, cell.weight_hh] + ([cell.bias_ih, cell.bias_hh] if cell.bias else [])
+            h0 = state if state is not None else input.new_zeros(input.shape[0], cell.hidden_size)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")                  # "weights are not one contiguous chunk": 0.6 M floats, copied
+                _, h_n = torch._VF.gru(input.permute(2, 0, 1), h0.unsqueeze(0), weights, bool(cell.bias), 1, 0.0,
+                                       self.training, False, False)
+            state = h_n[0]
+        else:
+            for frame in input.unbind(dim=2):
+                state = self.gruCell(frame, state)
         self.hidden = None if self.reset_hidden else state
         return state
 

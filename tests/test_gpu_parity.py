@@ -1075,6 +1075,29 @@ def test_experiment_configs_train_one_step(cpc, name):
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
 
 
+def test_gru_model_cudnn_sequence_call_matches_the_cell_loop(cpc):
+    """AudioGRUModel on the device: one fused cuDNN GRU call over the 100 visible steps (BASELINE configs[0] geometry:
+    512 -> 256) against the unrolled GRUCell loop in float64 -- hidden state and every gradient at fp32 rounding."""
+    import copy
+    torch.manual_seed(3)
+    fused = cpc.AudioGRUModel(512, 256).to(DEV)
+    loop = copy.deepcopy(fused).double()
+    loop.fused = False
+    x = torch.randn(8, 512, 100, generator=torch.Generator().manual_seed(4))
+    xa, xb = x.clone().to(DEV).requires_grad_(True), x.clone().to(DEV).double().requires_grad_(True)
+    assert fused._use_fused(xa) and not loop._use_fused(xb)
+    ya, yb = fused(xa), loop(xb)
+    assert rel_err(ya, yb) < 1e-5
+    g = torch.randn(ya.shape, generator=torch.Generator().manual_seed(5)).to(DEV)
+    (ya * g).sum().backward()
+    (yb * g.double()).sum().backward()
+    assert rel_err(xa.grad, xb.grad) < 1e-4
+    for (n, p_), (_, q_) in zip(fused.named_parameters(), loop.named_parameters()):
+        assert rel_err(p_.grad, q_.grad) < 1e-4, n
+    with cpc.ops.second_order():                                     # the gradient penalty needs a twice-differentiable path
+        assert not fused._use_fused(xa)
+
+
 def test_bf16_mode_tracks_fp32_mode_on_e20(cpc):
     """BASELINE configs[2] (arch 7 + attention AR in the bf16 operand mode: row-streaming and generic conv kernels on the
     hi plane only, block-tail nodes handing over one plane, AR model and W_k under bf16 autocast) against the fp32-faithful

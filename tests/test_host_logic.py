@@ -455,6 +455,41 @@ def test_literal_loss_block_and_small_helpers():
     assert enc.receptive_field == 465 and enc.downsampling_factor == 160
 
 
+def test_gru_model_fused_sequence_call_equals_the_unrolled_cells():
+    """AudioGRUModel (audio_model.py:47-77): the single fused library call over the whole sequence (the CUDA path; on the
+    CPU torch's native kernel behind the same entry point) computes exactly the unrolled nn.GRUCell loop of the reference
+    -- last hidden state, input and parameter gradients, with and without biases, with a persistent hidden state."""
+    import copy
+    import torch
+    from cpc_b200 import ar_models
+    torch.manual_seed(0)
+    for bias in (True, False):
+        fused = ar_models.AudioGRUModel(12, 7, bias=bias).double()
+        loop = copy.deepcopy(fused)
+        fused.fused, loop.fused = True, False
+        assert set(fused.state_dict()) == ({"gruCell.weight_ih", "gruCell.weight_hh", "gruCell.bias_ih", "gruCell.bias_hh"}
+                                           if bias else {"gruCell.weight_ih", "gruCell.weight_hh"})
+        x = torch.randn(5, 12, 9, dtype=torch.double)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya, yb = fused(xa), loop(xb)
+        assert float((ya - yb).abs().max()) < 1e-12
+        g = torch.randn_like(ya)
+        (ya * g).sum().backward()
+        (yb * g).sum().backward()
+        assert float((xa.grad - xb.grad).abs().max()) < 1e-12
+        for p_, q_ in zip(fused.parameters(), loop.parameters()):
+            assert float((p_.grad - q_.grad).abs().max()) < 1e-12
+    fused = ar_models.AudioGRUModel(12, 7, reset_hidden=False)
+    loop = copy.deepcopy(fused)
+    fused.fused, loop.fused = True, False
+    x = torch.randn(5, 12, 9)
+    for _ in range(2):                                              # the second call starts from the kept state
+        ya, yb = fused(x), loop(x)
+        fused.hidden, loop.hidden = fused.hidden.detach(), loop.hidden.detach()
+    assert float((ya - yb).abs().max()) < 1e-6
+    assert ar_models.AudioGRUModel(12, 7)._use_fused(x) is False    # CPU tensors keep the stock loop by default
+
+
 def test_preprocessing_identity_and_geometry_without_kernels():
     """PreprocessingModule(cqt_dict=None) is the identity (scalogram_model.py:77-78); with a CQT its geometry attributes
     follow the filterbank (:48-51, :70-72); unsupported scalogram pooling is refused at construction time."""

@@ -141,21 +141,26 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 // ---- forward ------------------------------------------------------------------------------------
-// grid (col tiles, row tiles).  part_m/part_s: [rowtile][ncols]; diag: [ncols]; cta: [ncta][3] = max,sum,reg
+// grid (col tiles, row tiles, problems).  part_m/part_s: [rowtile][ncols]; diag: [ncols]; cta: [ncta][3] = max,sum,reg.
+// Per-step mode: one CTA per (tile, prediction step) -- the K problems used to run one after the other inside a CTA,
+// which left the raw-wave configuration (B = 8 ... 64, K = 12: ONE tile) on a single SM for 0.6 - 0.9 ms.  Its
+// regulariser couples the problems (mean over k of S_k[d, t]): the CTAs add their scores into rsum (R x C, zeroed by the
+// caller) and nce_final_kernel squares the means.
 __global__ void __launch_bounds__(TILE_THREADS) nce_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Z,
                                                               NceGeom g, float* __restrict__ part_m,
                                                               float* __restrict__ part_s, float* __restrict__ diag,
                                                               float* __restrict__ cta, float* __restrict__ rowp_m,
-                                                              int* __restrict__ rowp_i) {
+                                                              int* __restrict__ rowp_i, float* __restrict__ rsum) {
     __shared__ TileSmem sm;
     __shared__ float Ss[TILE][TILE + 1];
     __shared__ float red[8];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int col0 = blockIdx.x * TILE, row0 = blockIdx.y * g.tmr;
-    float rs[4][4] = {};
     float tmax = -INFINITY, tsum = 0.f, reg = 0.f;
     const float inv_k = 1.f / (float)g.K;
-    for (int prob = 0; prob < g.nprob; ++prob) {
+    const bool reg_steps = !g.all && g.lambda != 0.f;            // per-step regulariser: through rsum
+    {
+        const int prob = blockIdx.z;
         float acc[4][4] = {};
         tile_gemm(make_p(P, g, prob), make_z(Z, g, prob), row0, col0, 0, g.E, acc, sm);
         float s[4][4];
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(TILE_THREADS) nce_fwd_kernel(const float* __re
                     tmax = fmaxf(tmax, v);
                     tsum += v;
                     if (r == c) diag[prob * g.C + c] = v;
-                    rs[i][j] += v;
+                    if (reg_steps) atomicAdd(rsum + (size_t)r * g.C + c, v);
                 }
             }
         // column statistics over this tile's rows
@@ -232,13 +237,7 @@ __global__ void __launch_bounds__(TILE_THREADS) nce_fwd_kernel(const float* __re
             __syncthreads();
         }
     }
-    if (!g.all && g.lambda != 0.f) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float a = rs[i][j] * inv_k; reg += a * a; }
-    }
-    const int id = blockIdx.y * gridDim.x + blockIdx.x;
+    const int id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const float bm = block_max(tmax, red);
     const float bs = block_sum(tsum, red);
     const float br = block_sum(reg, red);
@@ -266,9 +265,14 @@ __global__ void __launch_bounds__(256) nce_combine_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) nce_final_kernel(const float* __restrict__ blk, int nblk, const float* __restrict__ cta,
-                                                       int ncta, NceGeom g, float* __restrict__ out) {
+                                                       int ncta, NceGeom g, float* __restrict__ out,
+                                                       const float* __restrict__ rsum) {
     __shared__ float red[8];
     float a = 0.f, mx = -INFINITY, sm = 0.f, rg = 0.f;
+    if (rsum != nullptr) {                                        // per-step regulariser: sum over (d, t) of (mean_k S)^2
+        const float inv_k = 1.f / (float)g.K;
+        for (int i = threadIdx.x; i < g.R * g.C; i += blockDim.x) { const float m = rsum[i] * inv_k; rg += m * m; }
+    }
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) a += blk[i];
     for (int i = threadIdx.x; i < ncta; i += blockDim.x) {
         mx = fmaxf(mx, cta[i * 3 + 0]);
@@ -332,10 +336,33 @@ __global__ void __launch_bounds__(256) nce_validate_final_kernel(const float* __
 }
 
 // ---- backward -----------------------------------------------------------------------------------
+// Per-step regulariser, pass 1: rsum[d, t] += S_k[d, t] for every step k (grid (col tiles, row tiles, K); rsum zeroed).
+__global__ void __launch_bounds__(TILE_THREADS) nce_rsum_kernel(const float* __restrict__ P, const float* __restrict__ Z,
+                                                               NceGeom g, float* __restrict__ rsum) {
+    __shared__ TileSmem sm;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int col0 = blockIdx.x * TILE, row0 = blockIdx.y * g.tmr;
+    const int prob = blockIdx.z;
+    float acc[4][4] = {};
+    tile_gemm(make_p(P, g, prob), make_z(Z, g, prob), row0, col0, 0, g.E, acc, sm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int lr = tx * 4 + i, r = row0 + lr, c = col0 + ty * 4 + j;
+            if (lr < g.tmr && r < g.R && c < g.C)
+                atomicAdd(rsum + (size_t)r * g.C + c, g.kind == CPC_SCORE_SOFTPLUS ? softplus_f(acc[i][j]) : acc[i][j]);
+        }
+}
+
+// grid (col tiles, row tiles, problems x esplit): a CTA recomputes the score tile of ONE problem and produces the
+// gradient columns e = (es + n * esplit) * 64 ... of it (small problems -- one or a few tiles -- are spread over the SMs by
+// the problem and by the slice of E; they used to run their K problems and 8 slices one after the other on one SM).
 __global__ void __launch_bounds__(TILE_THREADS) nce_bwd_kernel(const float* __restrict__ P, const float* __restrict__ Z,
                                                               const float* __restrict__ lse,
                                                               const float* __restrict__ grad_loss, NceGeom g,
-                                                              float* __restrict__ dP, float* __restrict__ dZ) {
+                                                              float* __restrict__ dP, float* __restrict__ dZ,
+                                                              const float* __restrict__ rsum, int esplit) {
     __shared__ TileSmem sm;
     __shared__ float Gs[TILE][TILE + 1];
     __shared__ float Sbar[TILE][TILE];         // all-steps regulariser: (group, column); groups = tmr/K <= 64
@@ -348,17 +375,16 @@ __global__ void __launch_bounds__(TILE_THREADS) nce_bwd_kernel(const float* __re
                               : gl * g.lambda * 2.f * inv_k / ((float)g.B * (float)g.B);
     float sbar[4][4] = {};
     if (!g.all && g.lambda != 0.f) {
-        for (int prob = 0; prob < g.nprob; ++prob) {
-            float acc[4][4] = {};
-            tile_gemm(make_p(P, g, prob), make_z(Z, g, prob), row0, col0, 0, g.E, acc, sm);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    sbar[i][j] += (g.kind == CPC_SCORE_SOFTPLUS ? softplus_f(acc[i][j]) : acc[i][j]) * inv_k;
-        }
+            for (int j = 0; j < 4; ++j) {
+                const int lr = tx * 4 + i, r = row0 + lr, c = col0 + ty * 4 + j;
+                if (lr < g.tmr && r < g.R && c < g.C) sbar[i][j] = __ldg(rsum + (size_t)r * g.C + c) * inv_k;
+            }
     }
-    for (int prob = 0; prob < g.nprob; ++prob) {
+    const int prob = blockIdx.z / esplit, es = blockIdx.z - prob * esplit;
+    {
         const PRows pr = make_p(P, g, prob);
         const ZRows zr = make_z(Z, g, prob);
         float acc[4][4] = {};
@@ -407,7 +433,7 @@ __global__ void __launch_bounds__(TILE_THREADS) nce_bwd_kernel(const float* __re
                 Gs[lr][ty * 4 + j] = gv;
             }
         __syncthreads();
-        for (int e0 = 0; e0 < g.E; e0 += TILE) {
+        for (int e0 = es * TILE; e0 < g.E; e0 += esplit * TILE) {
             {   // dP[r, e] += sum_c G[r,c] Zc[c,e]
                 float a2[4][4] = {};
                 tile_gemm(SmemTile{Gs, 0}, ZByE{zr, col0}, 0, e0, 0, TILE, a2, sm);
@@ -444,14 +470,23 @@ __global__ void __launch_bounds__(TILE_THREADS) nce_bwd_kernel(const float* __re
 }
 
 struct NceWs {
-    float *part_m, *part_s, *diag, *cta, *blk;
+    float *part_m, *part_s, *diag, *cta, *blk, *rsum;
     int ncta, nblk;
     size_t bytes;
 };
+// per-step mode with a regulariser: (R x C) sums over the steps
+static size_t nce_rsum_floats(const NceGeom& g) { return (!g.all && g.lambda != 0.f) ? (size_t)g.R * g.C : 0; }
+// slices of E per problem in the CUDA-core backward: enough CTAs for the 148 SMs, at most one 64-wide chunk each
+static int nce_esplit(const NceGeom& g) {
+    const int ctas = ceil_div(g.C, TILE) * g.nrowtiles * g.nprob, chunks = ceil_div(g.E, TILE);
+    int e = 148 / ctas;
+    if (e > chunks) e = chunks;
+    return e < 1 ? 1 : e;
+}
 static NceWs nce_ws(const NceGeom& g, void* base) {
     NceWs w;
     const int coltiles = ceil_div(g.C, TILE);
-    w.ncta = coltiles * g.nrowtiles;
+    w.ncta = coltiles * g.nrowtiles * g.nprob;
     w.nblk = ceil_div(g.ncols, 256);
     size_t o = 0;
     char* b = reinterpret_cast<char*>(base);
@@ -461,6 +496,7 @@ static NceWs nce_ws(const NceGeom& g, void* base) {
     w.diag = take((size_t)g.ncols);
     w.cta = take((size_t)w.ncta * 3);
     w.blk = take((size_t)w.nblk);
+    w.rsum = take(nce_rsum_floats(g));
     w.bytes = o;
     return w;
 }
@@ -471,8 +507,9 @@ using namespace cpc;
 
 extern "C" size_t cpc_infonce_workspace_bytes(const cpc_infonce_params* p, int which) {
     if (nce_validate(p) != CPC_OK) return 0;
-    if (which == 1) return nce_umma_eligible(p, 1) ? nce_umma_workspace(p, 1) : 0;
     const NceGeom g = nce_geom(p);
+    if (which == 1)
+        return nce_umma_eligible(p, 1) ? nce_umma_workspace(p, 1) : align_up(sizeof(float) * nce_rsum_floats(g), 256);
     size_t fwd = nce_ws(g, nullptr).bytes;
     if (which == 0) {
         if (nce_umma_eligible(p, 0) && nce_umma_workspace(p, 0) > fwd) fwd = nce_umma_workspace(p, 0);
@@ -494,12 +531,15 @@ extern "C" int cpc_infonce_fwd(const float* pred, const float* targets, float* o
     if ((st = check_device()) != CPC_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     if (nce_tensor_path(p, 0)) return nce_umma_fwd(pred, targets, out, lse, p, workspace, workspace_bytes, s);
-    dim3 grid(ceil_div(g.C, TILE), g.nrowtiles);
-    nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta, nullptr, nullptr);
+    const size_t n_rsum = nce_rsum_floats(g);
+    if (n_rsum && cudaMemsetAsync(w.rsum, 0, sizeof(float) * n_rsum, s) != cudaSuccess) return CPC_ERR_CUDA;
+    dim3 grid(ceil_div(g.C, TILE), g.nrowtiles, g.nprob);
+    nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta, nullptr, nullptr,
+                                                 n_rsum ? w.rsum : nullptr);
     CPC_LAUNCH_CHECK();
     nce_combine_kernel<<<w.nblk, 256, 0, s>>>(w.part_m, w.part_s, w.diag, lse, w.blk, g.ncols, g.nrowtiles);
     CPC_LAUNCH_CHECK();
-    nce_final_kernel<<<1, 256, 0, s>>>(w.blk, w.nblk, w.cta, w.ncta, g, out);
+    nce_final_kernel<<<1, 256, 0, s>>>(w.blk, w.nblk, w.cta, w.ncta, g, out, n_rsum ? w.rsum : nullptr);
     CPC_LAUNCH_CHECK();
     count_launch(3);
     return CPC_OK;
@@ -521,8 +561,18 @@ extern "C" int cpc_infonce_bwd(const float* pred, const float* targets, const fl
     const size_t n = sizeof(float) * (size_t)g.B * g.K * g.E;
     if (cudaMemsetAsync(d_pred, 0, n, s) != cudaSuccess) return CPC_ERR_CUDA;
     if (cudaMemsetAsync(d_targets, 0, n, s) != cudaSuccess) return CPC_ERR_CUDA;
-    dim3 grid(ceil_div(g.C, TILE), g.nrowtiles);
-    nce_bwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, lse, grad_loss, g, d_pred, d_targets);
+    float* rsum = nullptr;
+    if (const size_t n_rsum = nce_rsum_floats(g)) {
+        if (!workspace || workspace_bytes < sizeof(float) * n_rsum) return CPC_ERR_WORKSPACE;
+        rsum = reinterpret_cast<float*>(workspace);
+        if (cudaMemsetAsync(rsum, 0, sizeof(float) * n_rsum, s) != cudaSuccess) return CPC_ERR_CUDA;
+        nce_rsum_kernel<<<dim3(ceil_div(g.C, TILE), g.nrowtiles, g.nprob), TILE_THREADS, 0, s>>>(pred, targets, g, rsum);
+        CPC_LAUNCH_CHECK();
+        count_launch();
+    }
+    const int esplit = nce_esplit(g);
+    dim3 grid(ceil_div(g.C, TILE), g.nrowtiles, g.nprob * esplit);
+    nce_bwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, lse, grad_loss, g, d_pred, d_targets, rsum, esplit);
     CPC_LAUNCH_CHECK();
     count_launch();
     return CPC_OK;
@@ -549,12 +599,12 @@ extern "C" int cpc_infonce_validate(const float* pred, const float* targets, flo
     float* rowp_m = reinterpret_cast<float*>(base);
     int* rowp_i = reinterpret_cast<int*>(base + align_up(sizeof(float) * rows, 256));
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 grid(ncoltiles, g.nrowtiles);
-    nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta, rowp_m, rowp_i);
+    dim3 grid(ncoltiles, g.nrowtiles, g.nprob);
+    nce_fwd_kernel<<<grid, TILE_THREADS, 0, s>>>(pred, targets, g, w.part_m, w.part_s, w.diag, w.cta, rowp_m, rowp_i, nullptr);
     CPC_LAUNCH_CHECK();
     nce_combine_kernel<<<w.nblk, 256, 0, s>>>(w.part_m, w.part_s, w.diag, lse, w.blk, g.ncols, g.nrowtiles);
     CPC_LAUNCH_CHECK();
-    nce_final_kernel<<<1, 256, 0, s>>>(w.blk, w.nblk, w.cta, w.ncta, g, out4);
+    nce_final_kernel<<<1, 256, 0, s>>>(w.blk, w.nblk, w.cta, w.ncta, g, out4, nullptr);
     CPC_LAUNCH_CHECK();
     nce_validate_final_kernel<<<1, 256, 0, s>>>(lse, w.diag, rowp_m, rowp_i, ncoltiles, out4, g, metrics);
     CPC_LAUNCH_CHECK();

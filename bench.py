@@ -458,9 +458,12 @@ def run_ours(args):
                             frac=dom["tflops"] / peaks["tensor"],
                             algorithmic_flops_per_launch=dom["flops_per_launch"],
                             peak_source=peaks["source"] + " bf16 dense cuBLAS, sustained",
-                            note="achieved = algorithmic FLOPs of the launch (conv: 2*Cout*Cin*kh*kw*B*OH*OW) / its average "
-                                 "CUDA-event time; fp32-faithful mode issues 3 bf16 MMAs per product, so the ceiling of "
-                                 "`frac` is 1/3")
+                            mma_passes=1 if w["dtype"] == "bf16" else 3,
+                            frac_of_mode_ceiling=dom["tflops"] * (1 if w["dtype"] == "bf16" else 3) / peaks["tensor"],
+                            note="achieved = algorithmic FLOPs of the launch (conv: 2*Cout*Cin*kh*kw*B*OH*OW, taps that fall "
+                                 "into zero padding included) / its average CUDA-event time; the fp32-faithful mode issues 3 "
+                                 "bf16 MMAs per product, so the ceiling of `frac` is 1/3 there; frac_of_mode_ceiling = "
+                                 "mma_passes * frac")
         else:
             roofline = dict(common, bound="hbm", achieved=dom["gbs"], peak=peaks["hbm"], unit="GB/s",
                             frac=dom["gbs"] / peaks["hbm"], algorithmic_bytes_per_launch=dom["bytes_per_launch"],

@@ -14,6 +14,7 @@ CQT_MAX_GROUPS = 16
 CQT_COMPLEX, CQT_LOGPOW, CQT_LOGPOW_PHASE = 0, 1, 2
 SCORE_LINEAR, SCORE_SOFTPLUS = 0, 1
 CQT_FLAG_NO_TENSOR = 1
+CQT_FLAG_HALF_OPERANDS = 2
 CONV_FLAG_CUDA_CORE, CONV_FLAG_NO_TALL, CONV_FLAG_NO_SMALLK, CONV_FLAG_NO_FUSED_DGRAD = 1, 2, 4, 8
 CONV_FLAG_NO_MMA_SMALL_WGRAD = 16
 INFONCE_FLAG_NO_TENSOR = 1

@@ -975,6 +975,8 @@ def _cqt_params(plan, batch, n_samples, x_pitch, n_frames, mode, pool_t, eps, lo
     p.mode, p.pool_t = mode, pool_t
     p.eps, p.log_offset, p.norm, p.power = eps, log_offset, norm, power
     p.flags = _lib.CQT_FLAG_NO_TENSOR if _switch("CPC_NO_TENSOR_CQT") else 0
+    if _default_precision == "bf16":
+        p.flags |= _lib.CQT_FLAG_HALF_OPERANDS                  # front end of the bf16 operand mode: one fp16 plane per operand
     import os
     p.flags |= (int(kernel_switches.get("CPC_CQT_ROUND", os.environ.get("CPC_CQT_ROUND", "0"))) & 0xff) << 8
     return p

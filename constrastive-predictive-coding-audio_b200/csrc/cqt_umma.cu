@@ -79,6 +79,7 @@ struct CqtUmma {
     CqGroup g[CPC_CQT_MAX_GROUPS];
     int n_groups;
     int mode, To;
+    int half;                                            // CPC_CQT_FLAG_HALF_OPERANDS: hi planes only, one product
     float eps, log_offset, norm, power;
     const float* phase_fixed;
     const float* phase_scale;
@@ -264,6 +265,10 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
     const int slab_bytes = p.halves * 2 * CQ_SLAB_PLANE;
     uint8_t* b_ring = smem + slab_bytes;
     const int b_stage = 2 * p.NP * 128;
+    // one-plane mode: the tensor maps' boxes cover the hi plane / the W_hi rows only (the lo halves of the slab and of a
+    // ring stage stay unused)
+    const uint32_t slab_tx = p.half ? (uint32_t)slab_bytes / 2 : (uint32_t)slab_bytes;
+    const uint32_t b_tx = p.half ? (uint32_t)b_stage / 2 : (uint32_t)b_stage;
     CqBarriers* bars = reinterpret_cast<CqBarriers*>(b_ring + CQ_BSTAGES * b_stage);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                 int set, b, blk;
                 cq_tile(p, tile, set, b, blk);
                 mbar_wait(&bars->slab_empty, (tn & 1) ^ 1);
-                mbar_expect_tx(&bars->slab_full, (uint32_t)slab_bytes);
+                mbar_expect_tx(&bars->slab_full, slab_tx);
                 for (int h = 0; h < p.halves; ++h)
                     tma_load_4d(slab + h * 2 * CQ_SLAB_PLANE, &tmap_x, &bars->slab_full, h * 64, blk * p.fpb, b, 0);
                 ++tn;
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                         for (int c = c0; c < c1; ++c, ++bn) {
                             const int stage = bn % CQ_BSTAGES;
                             mbar_wait(&bars->bempty[stage], ((bn / CQ_BSTAGES) & 1) ^ 1);
-                            mbar_expect_tx(&bars->bfull[stage], (uint32_t)b_stage);
+                            mbar_expect_tx(&bars->bfull[stage], b_tx);
                             tma_load_3d(b_ring + stage * b_stage, &tmap_w, &bars->bfull[stage], 0, g.w_row0 + c * 2 * p.NP, 0);
                         }
                     }
@@ -384,7 +389,12 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
                                 const uint64_t a_d_hi = make_smem_desc(a_hi, 16, 1024), a_d_lo = make_smem_desc(a_hi + CQ_SLAB_PLANE, 16, 1024);
                                 const uint64_t b_d_hi = make_smem_desc(b_hi, 16, 1024), b_d_lo = make_smem_desc(b_hi + p.NP * 128, 16, 1024);
                                 const uint32_t first = (uint32_t)(c - c0);     // 0 on the first chunk of the round: overwrite
-                                if (g.wide) {
+                                if (p.half) {
+                                    // one-plane mode (bf16 operand mode of the model): X_hi * W_hi into the main block
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        mma_bf16(d_tmem, a_d_hi + (uint64_t)(2 * k), b_d_hi + (uint64_t)(2 * k), idesc_np, first | (uint32_t)k);
+                                } else if (g.wide) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {              // +32 B per K step = +2 in the address field
                                         // X_hi * [W_hi | W_lo] -> both column blocks; X_lo * W_hi -> onto the second block
@@ -440,7 +450,7 @@ __global__ void __launch_bounds__(CQ_THREADS, 1) cqt_umma_kernel(const __grid_co
             const uint32_t base = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * CQ_ACC_COLS + (uint32_t)(g.col + j0);
             pull_part(base, re, fresh);                                       // main block: real | imaginary columns
             pull_part(base + (uint32_t)(p.NP >> 1), im, fresh);
-            if (g.wide) {                                                     // the hi*lo + lo*hi correction block
+            if (g.wide && !p.half) {                                          // the hi*lo + lo*hi correction block
                 pull_part(base + (uint32_t)p.NP, re, false);
                 pull_part(base + (uint32_t)(p.NP + (p.NP >> 1)), im, false);
             }
@@ -745,16 +755,18 @@ int cqt_umma_launch(const float* x, const float* weights, const void* packed_fil
         // 16-bit elements: the tensor maps only move bytes, so the bf16 encoder serves the fp16 planes
         const uint64_t dims[4] = {(uint64_t)p->hop, (uint64_t)u.S, (uint64_t)p->batch, 2};
         const uint64_t strides[3] = {(uint64_t)p->hop * 2, (uint64_t)u.Lp * 2, (uint64_t)u.Lp * 2 * p->batch};
-        const uint32_t box[4] = {64, CQ_SLAB_ROWS, 1, 2};
+        const uint32_t half = (p->flags & CPC_CQT_FLAG_HALF_OPERANDS) ? 1u : 0u;
+        const uint32_t box[4] = {64, CQ_SLAB_ROWS, 1, half ? 1u : 2u};
         if (!make_tmap_bf16(&tx, xp, 4, dims, strides, box)) return CPC_ERR_CUDA;
         const uint64_t wd[3] = {64, (uint64_t)u.total_rows, 1};
         const uint64_t wsr[2] = {128, 128 * (uint64_t)u.total_rows};
-        const uint32_t wbox[3] = {64, (uint32_t)(2 * u.NP), 1};
+        const uint32_t wbox[3] = {64, (uint32_t)((half ? 1 : 2) * u.NP), 1};       // [W_hi | W_lo] rows of a chunk, or W_hi
         if (!make_tmap_bf16(&tw, wp, 3, wd, wsr, wbox)) return CPC_ERR_CUDA;
     }
     k.B = p->batch; k.T = p->n_frames; k.F = p->n_bins; k.hop = p->hop; k.halves = u.halves; k.NP = u.NP;
     k.n_groups = u.n_tensor_groups;
     k.mode = p->mode;
+    k.half = (p->flags & CPC_CQT_FLAG_HALF_OPERANDS) ? 1 : 0;
     k.fpb = p->mode == CPC_CQT_LOGPOW_PHASE ? 127 : 128;
     const int t_out = p->mode == CPC_CQT_LOGPOW_PHASE ? p->n_frames - 1 : p->n_frames;
     k.To = t_out;

@@ -88,6 +88,9 @@ typedef struct cpc_cqt_params {
     int32_t flags;          /* CPC_CQT_FLAG_*: kernel selection switches (A/B tests); 0 = default     */
 } cpc_cqt_params;
 #define CPC_CQT_FLAG_NO_TENSOR 1   /* every octave group on the fp32 CUDA-core kernels                  */
+#define CPC_CQT_FLAG_HALF_OPERANDS 2 /* tensor-core groups on ONE fp16 plane per operand (11-bit mantissas after the exact
+                                      power-of-two scaling; ~2e-4 relative) instead of the fp32-accurate hi/lo pair: the front
+                                      end of the bf16 operand mode (cpc_conv_params.precision = 1 downstream)            */
 
 size_t cpc_cqt_workspace_bytes(const cpc_cqt_params* p);
 /* x (B, x_pitch) fp32; weights: packed group blocks, fp32; phase_fixed / phase_scale: (n_bins) fp32, only

@@ -55,7 +55,7 @@ with open(path, "w") as fh:
 print(key, "->", dram, "bytes per launch")
 if summary:
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
-            "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
             "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",

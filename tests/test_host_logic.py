@@ -138,6 +138,39 @@ def test_conv_dispatch_table_for_the_baseline_layers(built_lib):
     assert cpc_b200.ops._conv_flags() == 0
 
 
+def test_workspace_queries_cover_the_schedulers_and_the_per_step_regulariser(built_lib):
+    """Host-side sizes (no device needed): the row-streaming conv kernels' workspace holds the packed operands plus the
+    tile counter of their scheduler, also in the one-plane (bf16 operand) mode; the CUDA-core InfoNCE backward asks for
+    the (R x C) sum buffer of the per-step regulariser and for nothing otherwise."""
+    from cpc_b200 import _lib
+    lib = _lib.load()
+    p = _lib.ConvParams()
+    p.batch, p.c_in, p.h_in, p.w_in, p.c_out, p.kh, p.kw = 4, 32, 127, 314, 32, 64, 1
+    p.stride_h = p.stride_w = 1
+    p.pad_top, p.h_out, p.w_out = 63, 127, 314
+
+    def act(planes, h):
+        return (planes * 4 * 32 * h * ((314 + 7) // 8 * 8) * 2 + 1023) // 1024 * 1024
+    w_bytes = (64 * 32 * 64 * 2 + 1023) // 1024 * 1024
+    for precision, planes in ((0, 2), (1, 1)):
+        p.precision = precision
+        assert lib.cpc_conv_kernel_family(ctypes.byref(p), 0) == 2
+        assert lib.cpc_conv_workspace_bytes(ctypes.byref(p), 0) == act(planes, 127) + w_bytes + 256 + 1024
+        assert lib.cpc_conv_workspace_bytes(ctypes.byref(p), 2) == 2 * act(planes, 127) + 1024
+    q = _lib.InfoNceParams()
+    q.batch, q.steps, q.enc, q.all_steps, q.score_kind, q.regularization = 8, 12, 512, 0, 1, 1.0
+    assert lib.cpc_infonce_workspace_bytes(ctypes.byref(q), 1) == 8 * 8 * 4                 # per-step + regulariser
+    q.regularization = 0.0
+    assert lib.cpc_infonce_workspace_bytes(ctypes.byref(q), 1) == 0
+    q.regularization, q.all_steps = 1.0, 1
+    assert lib.cpc_infonce_workspace_bytes(ctypes.byref(q), 1) == 0                         # all-steps: sums stay in the tile
+    fwd_reg = lib.cpc_infonce_workspace_bytes(ctypes.byref(q), 0)
+    q.all_steps = 0
+    assert lib.cpc_infonce_workspace_bytes(ctypes.byref(q), 0) >= 8 * 8 * 4 and fwd_reg > 0
+    c = _lib.CqtParams()
+    assert _lib.CQT_FLAG_HALF_OPERANDS == 2 and _lib.CQT_FLAG_NO_TENSOR == 1 and hasattr(c, "flags")
+
+
 def test_second_order_switch_and_block_tail_gate():
     """ops.second_order() is a re-entrant context flag; the block-tail node never claims CPU tensors."""
     import cpc_b200

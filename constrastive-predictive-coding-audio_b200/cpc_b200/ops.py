@@ -304,7 +304,9 @@ def _conv_backward(ctx, saved, dy):
     lib = _lib.load()
     x_shape, w_shape, stride, pad_top, pad_left, out_hw, precision = ctx.params
     if ctx.relu:
-        dy = dy * (y > 0).to(dy.dtype)
+        # gradient of the fused ReLU epilogue: one pass (aten's relu backward) outside second-order mode, the plainly
+        # differentiable expression under create_graph
+        dy = dy * (y > 0).to(dy.dtype) if torch.is_grad_enabled() else torch.ops.aten.threshold_backward(dy, y, 0.0)
     dy = dy.contiguous()
     if torch.is_grad_enabled():
         # backward under create_graph=True: record dgrad / wgrad as differentiable nodes

@@ -277,6 +277,9 @@ constexpr int TW_SMEM = (TW_XS + TW_YS) * TW_GROUP + 1024 + 256;
 struct TallWgrad {
     int B, H_src, H_out, W, AW, kh, P;
     int n_units, n_splits, n_dgroups;
+    int n_blocks;                            // tap blocks that hold at least one tap inside [0, kh)
+    int balanced;                            // 1: group g owns CTAs cta_start[g] .. cta_start[g + 1] (work-proportional)
+    int cta_start[kMaxSplitGroups + 1];
     int d_min;                               // block d covers taps 4*d + P + delta - rho
     int Q;                                   // dy row groups
     int planes;                              // 2: hi/lo planes, 1: hi plane only (bf16 operand mode)
@@ -299,8 +302,21 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
     uint8_t* y_ring = smem + TW_XS * TW_GROUP;
     TallWgradBarriers* bars = reinterpret_cast<TallWgradBarriers*>(y_ring + TW_YS * TW_GROUP);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int dg = blockIdx.x % p.n_dgroups, split = blockIdx.x / p.n_dgroups;
+    // accumulator group and share of the pixel atoms: groups whose taps mostly pair with rows outside the source do less
+    // work per atom and get fewer CTAs (host: balance_group_ctas)
+    int dg, split, n_splits;
+    if (p.balanced) {
+        dg = 0;
+        while (dg + 1 < p.n_dgroups && (int)blockIdx.x >= p.cta_start[dg + 1]) ++dg;
+        split = (int)blockIdx.x - p.cta_start[dg];
+        n_splits = p.cta_start[dg + 1] - p.cta_start[dg];
+    } else {
+        dg = blockIdx.x % p.n_dgroups;
+        split = blockIdx.x / p.n_dgroups;
+        n_splits = p.n_splits;
+    }
     const int d0 = p.d_min + dg * TW_NB;     // x group index = dy group index + d
+    const int nb_live = min(TW_NB, p.n_blocks - dg * TW_NB);     // blocks of this group that hold a tap inside [0, kh)
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
@@ -327,7 +343,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
                 tma_load_5d(x_ring + slot * TW_GROUP, &tmap_x, &bars->xfull[slot], w0, 4 * (d0 + n), 0, b, 0);
                 ++xn;
             };
-            for (int u = split; u < p.n_units; u += p.n_splits) {
+            for (int u = split; u < p.n_units; u += n_splits) {
                 const int b = u / p.AW, w0 = (u - b * p.AW) * 64;
                 load_x(b, w0, 0);
                 load_x(b, w0, 1);
@@ -347,7 +363,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
             const int n_xgroups = (p.H_src + 3) >> 2;
             const int n_cb = p.planes == 2 ? 3 : 1;
             uint32_t xn = 0, yn = 0, started = 0;
-            for (int u = split; u < p.n_units; u += p.n_splits) {
+            for (int u = split; u < p.n_units; u += n_splits) {
                 // x groups n = 0, 1 of this atom are consumed together with n = 2 at step 0
                 for (int q = 0; q < p.Q; ++q) {
                     // wait for the newest x group of this step (and, at q = 0, the two before it)
@@ -360,7 +376,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
                     mbar_wait(&bars->yfull[yslot], (yn / TW_YS) & 1);
                     tc_fence_after();
                     const uint64_t y_d0 = make_smem_desc(smem_u32(y_ring + yslot * TW_GROUP), 16, 1024);
-                    for (int k = 0; k < TW_NB; ++k) {
+                    for (int k = 0; k < nb_live; ++k) {
                         const int pg = q + d0 + k;                            // x row group index
                         if (pg < 0 || pg >= n_xgroups) continue;              // rows outside the source: zeros
                         const uint64_t x_d0 = make_smem_desc(smem_u32(x_ring + ((xn + k) % TW_XS) * TW_GROUP), 16, 1024);
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tall_wgrad_kernel(const __grid_
         mbar_wait(&bars->acc_full, 0);
         tc_fence_after();
         const int n_xgroups = (p.H_src + 3) >> 2;
-        for (int k = 0; k < TW_NB; ++k) {
+        for (int k = 0; k < nb_live; ++k) {
             // the block was touched iff some dy group q in [0, Q) pairs with an x group inside the source
             const int q_lo = max(0, -(d0 + k)), q_hi = min(p.Q, n_xgroups - (d0 + k));
             if (q_hi <= q_lo) continue;
@@ -538,14 +554,35 @@ int tall_wgrad_launch(const float* x, const float* dy, float* dw, const cpc_conv
     const int n_blocks = d_hi - d_lo + 1;
     k.d_min = d_lo;
     k.n_dgroups = ceil_div(n_blocks, TW_NB);
+    k.n_blocks = n_blocks;
     k.n_splits = 148 / k.n_dgroups;
     if (k.n_splits < 1) k.n_splits = 1;
     if (k.n_splits > k.n_units) k.n_splits = k.n_units;
+    int n_ctas = k.n_dgroups * k.n_splits;
+    {
+        // cost of one pixel atom for group g, in MMA blocks: (dy group q, x group q + d) pairs inside the source over its
+        // live blocks, but never less than the time its Q ring steps take to load (~2 block times per step)
+        int cost[kMaxSplitGroups];
+        const int n_xg = (p->h_in + 3) / 4;
+        bool ok = k.n_dgroups <= kMaxSplitGroups;
+        for (int g = 0; ok && g < k.n_dgroups; ++g) {
+            int c = 0;
+            for (int b = 0; b < TW_NB && g * TW_NB + b < n_blocks; ++b) {
+                const int d = d_lo + g * TW_NB + b;
+                const int q_lo = -d > 0 ? -d : 0, q_hi = k.Q < n_xg - d ? k.Q : n_xg - d;
+                c += q_hi > q_lo ? q_hi - q_lo : 0;
+            }
+            cost[g] = c > 2 * k.Q ? c : 2 * k.Q;
+        }
+        const int total = ok ? balance_group_ctas(cost, k.n_dgroups, k.n_units, 148, k.cta_start) : 0;
+        k.balanced = total > 0 ? 1 : 0;
+        if (k.balanced) n_ctas = total;
+    }
     k.dw = dw;
     if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)TL_C * TL_C * p->kh, s) != cudaSuccess) return CPC_ERR_CUDA;
     if (cudaFuncSetAttribute(tall_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM) != cudaSuccess)
         return CPC_ERR_CUDA;
-    tall_wgrad_kernel<<<k.n_dgroups * k.n_splits, TL_THREADS, TW_SMEM, s>>>(tx, tdy, k);
+    tall_wgrad_kernel<<<n_ctas, TL_THREADS, TW_SMEM, s>>>(tx, tdy, k);
     CPC_LAUNCH_CHECK();
     count_launch(3);
     return CPC_OK;

@@ -176,6 +176,32 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const u
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- CTAs per accumulator group of a split-K weight-gradient kernel -------------------------------------------------
+// A CTA owns one group of accumulators (taps) for the whole launch and a share of the `n_units` reduction units; the
+// cost of one unit differs between groups (taps that pair with rows outside the source are skipped).  Hands `total`
+// CTAs to the groups so that the largest per-CTA cost ceil(n_units / ctas[g]) * cost[g] is as small as possible
+// (greedy: the next CTA goes to the currently slowest group); start[g] .. start[g + 1] are group g's CTAs.
+constexpr int kMaxSplitGroups = 48;
+inline int balance_group_ctas(const int* cost, int n_groups, int n_units, int total, int* start) {
+    int ctas[kMaxSplitGroups];
+    if (n_groups > kMaxSplitGroups || n_groups > total) return 0;
+    for (int g = 0; g < n_groups; ++g) ctas[g] = 1;
+    for (int used = n_groups; used < total; ++used) {
+        int worst = -1;
+        long worst_cost = -1;
+        for (int g = 0; g < n_groups; ++g) {
+            if (ctas[g] >= n_units) continue;                     // one unit per CTA already
+            const long c = (long)((n_units + ctas[g] - 1) / ctas[g]) * (cost[g] > 0 ? cost[g] : 1);
+            if (c > worst_cost) { worst_cost = c; worst = g; }
+        }
+        if (worst < 0) break;
+        ++ctas[worst];
+    }
+    start[0] = 0;
+    for (int g = 0; g < n_groups; ++g) start[g + 1] = start[g] + ctas[g];
+    return start[n_groups];
+}
+
 // ---- dynamic tile scheduling of a persistent kernel -----------------------------------------------------------------
 // A two-entry queue in shared memory: `sfull[2]` (count 1), `sempty[2]` (count = number of consumer warps), `tile_id[2]`.
 // One scheduler thread takes tile numbers from a global counter that is zero at launch; every consumer warp reads each

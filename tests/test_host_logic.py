@@ -171,6 +171,53 @@ def test_workspace_queries_cover_the_schedulers_and_the_per_step_regulariser(bui
     assert _lib.CQT_FLAG_HALF_OPERANDS == 2 and _lib.CQT_FLAG_NO_TENSOR == 1 and hasattr(c, "flags")
 
 
+def test_weight_gradient_cta_hand_out(tmp_path):
+    """umma.cuh: balance_group_ctas (pure host code, compiled here with nvcc and run on the CPU): the CTAs of a split-K
+    weight-gradient launch are dealt to the accumulator groups so that atoms-per-CTA x cost-per-atom is level -- the arch-7
+    64 x 1 layer's six tap groups (costs from its top padding) get 22 / 22 / 25 / 27 / 30 / 22 of the 148 SMs instead of 24
+    each -- and degenerate inputs fall back (more groups than the table holds) or saturate (fewer atoms than CTAs)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "hand_out.cu"
+    src.write_text("""
+#include <cstdio>
+#include <cstdlib>
+#include "umma.cuh"
+int main(int argc, char** argv) {
+    int n_units = atoi(argv[1]), total = atoi(argv[2]), n = argc - 3;
+    int cost[256], start[cpc::umma::kMaxSplitGroups + 1];
+    for (int g = 0; g < n; ++g) cost[g] = atoi(argv[3 + g]);
+    int used = cpc::umma::balance_group_ctas(cost, n, n_units, total, start);
+    printf("%d", used);
+    for (int g = 0; used && g < n; ++g) printf(" %d", start[g + 1] - start[g]);
+    printf("\\n");
+    return 0;
+}
+""")
+    exe = tmp_path / "hand_out"
+    csrc = os.path.join(ROOT, "constrastive-predictive-coding-audio_b200", "csrc")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([nvcc, "-std=c++17", "-I", csrc, "-I", inc, "-o", str(exe), str(src), "-lcuda"], check=True,
+                   capture_output=True)
+
+    def run(n_units, total, *cost):
+        out = subprocess.run([str(exe), str(n_units), str(total)] + [str(c) for c in cost], check=True,
+                             capture_output=True, text=True).stdout.split()
+        return [int(v) for v in out]
+
+    got = run(320, 148, 64, 64, 69, 78, 87, 64)                  # e24 block 0 conv_b, B = 64: 320 pixel atoms
+    assert got == [148, 22, 22, 25, 27, 30, 22]
+    worst = max(-(-320 // c) * k for c, k in zip(got[1:], (64, 64, 69, 78, 87, 64)))
+    assert worst == 960 and worst < 14 * 94                     # uniform split of the old kernel: 14 atoms x 94 blocks
+    assert run(20, 148, 64, 64, 69, 78, 87, 64) == [120] + [20] * 6     # 20 atoms: one per CTA is the finest split
+    assert run(192, 148, *([136] * 7 + [68])) == [148, 20, 20, 20, 20, 20, 20, 19, 9]
+    assert run(100, 148, *([5] * 49)) == [0]                    # more groups than the table holds: caller keeps uniform
+    assert run(100, 3, 1, 1, 1, 1) == [0]                       # fewer CTAs than groups
+
+
 def test_second_order_switch_and_block_tail_gate():
     """ops.second_order() is a re-entrant context flag; the block-tail node never claims CPU tensors."""
     import cpc_b200
